@@ -1,0 +1,87 @@
+/* libldot_sm100a - C ABI of the B200-native LightningDOT retrieval hot path.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, < 0 on error; ldot_last_error() returns a thread-local description of the last failure;
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; `stream` is a cudaStream_t (NULL =
+ *     legacy default stream); calls only enqueue work - they never synchronise and never allocate: scratch memory
+ *     is passed in by the caller and sized with the matching *_workspace_bytes() query;
+ *   - row-major, contiguous matrices; row ids are int64 like faiss labels.
+ *
+ * The reference has no FFI for this path (it is pure Python over third-party wheels); each entry point cites the
+ * reference call it replaces.  See INTEGRATION.md for the ctypes binding the reference's Python would add.
+ */
+#ifndef LDOT_H_
+#define LDOT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDOT_ABI_VERSION 1
+
+#define LDOT_OK 0
+#define LDOT_ERR_ARG (-1)
+#define LDOT_ERR_CUDA (-2)
+#define LDOT_ERR_WORKSPACE (-3)
+#define LDOT_ERR_ARCH (-4)
+
+/* 16-bit storage type of the coarse (tensor-core) copy of queries and index */
+#define LDOT_COARSE_FP16 0
+#define LDOT_COARSE_BF16 1
+
+int ldot_abi_version(void);
+const char* ldot_last_error(void);
+/* 0 when the current device is an sm_100 part the kernels can run on, LDOT_ERR_ARCH / LDOT_ERR_CUDA otherwise */
+int ldot_device_check(void);
+
+/* ---- index build: replaces faiss.IndexFlatIP.add (dvl/indexer/faiss_indexers.py:77) -------------------------
+ * d_x      [n, d] fp32 master copy of the index (kept by the caller; the search reads it for exact rescoring)
+ * d_x16    [n, d] out: centred 16-bit copy (x - mean row) for the tensor-core pass
+ * d_mu     [d]    out: the centring vector (all zeros when center == 0)
+ * d_xstats [2]    out: max_j |(x_j - mu) - x16_j|_2 and max_j |x16_j|_2 (inputs of the search certificate)     */
+size_t ldot_index_prepare_workspace_bytes(int64_t n, int32_t d);
+int ldot_index_prepare(const float* d_x, int64_t n, int32_t d, int32_t coarse_dtype, int32_t center, void* d_x16,
+                       float* d_mu, float* d_xstats, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ---- search: replaces faiss.IndexFlatIP.search (dvl/indexer/faiss_indexers.py:83) ----------------------------
+ * Exact inner-product top-k of every query against every index row, ranked (score desc, row id asc).
+ * d_q          [nq, d] fp32 queries
+ * coarse_k     candidates kept by the tensor-core pass per query (0 = automatic, >= k)
+ * id_offset    added to every returned row id (row offset of this shard in a row-sharded index)
+ * d_out_scores [nq, k] fp32, d_out_idx [nq, k] int64 (-1 / -FLT_MAX past the end of a short index)
+ * d_out_flags  [nq] int32: 0 = result proven exact; 1 = certificate failed - the caller must re-run that query
+ *              through ldot_flatip_exact (DenseFlatIndexer.search_knn does)
+ * d_out_flag_count [1] int32 number of flagged queries (may be NULL)                                            */
+size_t ldot_flatip_search_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k, int32_t coarse_k);
+int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const void* d_x16, const float* d_mu,
+                       const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,
+                       int32_t coarse_dtype, int64_t id_offset, float* d_out_scores, int64_t* d_out_idx,
+                       int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Exhaustive fp64-accumulated scan (no tensor cores): the fallback for flagged queries; same outputs/ranking. */
+size_t ldot_flatip_exact_workspace_bytes(int64_t n);
+int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n, int32_t d, int32_t k,
+                      int64_t id_offset, float* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes,
+                      void* stream);
+
+/* Merge the exact top-k lists of `world` index shards (after the NCCL all-gather):
+ * d_scores [world, nq, k], d_idx [world, nq, k] (global ids) -> d_out_* [nq, k], same ranking rule.             */
+int ldot_topk_merge(const float* d_scores, const int64_t* d_idx, int32_t world, int64_t nq, int32_t k,
+                    float* d_out_scores, int64_t* d_out_idx, void* stream);
+
+/* ---- encoder Linear: replaces nn.Linear (+ fused GELU / residual) on the tower path ---------------------------
+ * (uniter_model/model/layer.py:76-78,107,133,148; model.py:252; dvl/models/bi_encoder.py:83-88,138-143)
+ * out[M, N] = act(A[M, K] . W[N, K]^T + bias[N]) (+ residual[M, N]);  A / W / residual: 16-bit of `dtype`
+ * (LDOT_COARSE_FP16 / LDOT_COARSE_BF16), fp32 accumulation; lda / ldw / ldr / ldo are row pitches in ELEMENTS;
+ * act: 0 identity, 1 erf-GELU; out_f32: 1 = fp32 output, 0 = 16-bit output.  bias / residual may be NULL.        */
+int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
+                const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
+                int32_t dtype, int32_t act, int32_t out_f32, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDOT_H_ */

@@ -1,0 +1,77 @@
+"""ctypes binding of libldot_sm100a.so (C ABI in include/ldot.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing, or the device is not sm_100, every entry
+point raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"` (or
+`python -m lightningdot_b200.build`).
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
+
+COARSE_FP16 = 0
+COARSE_BF16 = 1
+
+_lib = None
+
+# name -> (restype, argtypes): every symbol include/ldot.h declares
+SIGNATURES = {
+    "ldot_abi_version": (c_int32, []),
+    "ldot_last_error": (c_char_p, []),
+    "ldot_device_check": (c_int32, []),
+    "ldot_index_prepare_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "ldot_index_prepare": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "ldot_flatip_search_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
+    "ldot_flatip_search": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                     c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    "ldot_flatip_exact_workspace_bytes": (c_size_t, [c_int64]),
+    "ldot_flatip_exact": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ldot_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "ldot_linear": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                              c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+}
+
+
+class LdotError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises LdotError when the extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LdotError(
+            f"{LIB_PATH} not found: the CUDA extension is not built and there is no fallback path. "
+            "Run `python -m lightningdot_b200.build`.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ldot_abi_version() != 1:
+        raise LdotError(f"ABI version mismatch: library reports {lib.ldot_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().ldot_last_error()
+        raise LdotError(f"libldot_sm100a error {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

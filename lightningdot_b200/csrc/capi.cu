@@ -1,0 +1,162 @@
+// extern "C" surface of libldot_sm100a.so (declared in include/ldot.h) + shared host helpers.
+#include "../../include/ldot.h"
+#include <cstring>
+#include "host_common.h"
+#include "search_plan.h"
+
+namespace ldot {
+
+char* error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                         uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(kErrCuda, "cuTensorMapEncodeTiled entry point not available");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  LDOT_REQUIRE(row_stride_bytes % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+  LDOT_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {row_stride_bytes};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  // the element type only matters for OOB fill / arithmetic; bf16 and fp16 are both plain 2-byte moves
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(kErrCuda, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return kOk;
+}
+
+int device_sm_count(int* out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  LDOT_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && cached[dev]) {
+    *out = cached[dev];
+    return kOk;
+  }
+  int sms = 0;
+  LDOT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (dev < 64) cached[dev] = sms;
+  *out = sms;
+  return kOk;
+}
+
+}  // namespace ldot
+
+namespace ldot {
+int linear_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
+               long long ldr, void* out, long long ldo, long long M, int N, int K, int fmt, int act, int out_f32,
+               void* stream);
+}
+
+using namespace ldot;
+
+extern "C" {
+
+int ldot_abi_version(void) { return LDOT_ABI_VERSION; }
+
+const char* ldot_last_error(void) { return error_buffer(); }
+
+int ldot_device_check(void) {
+  int dev = 0, major = 0, minor = 0;
+  LDOT_CUDA(cudaGetDevice(&dev));
+  LDOT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  LDOT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) return set_error(kErrArch, "libldot_sm100a needs an sm_100 device, found sm_%d%d", major, minor);
+  return kOk;
+}
+
+size_t ldot_index_prepare_workspace_bytes(int64_t n, int32_t d) {
+  (void)n;
+  return index_prepare_workspace_bytes(d);
+}
+
+int ldot_index_prepare(const float* d_x, int64_t n, int32_t d, int32_t coarse_dtype, int32_t center, void* d_x16,
+                       float* d_mu, float* d_xstats, void* d_ws, size_t ws_bytes, void* stream) {
+  LDOT_REQUIRE(d_x && d_x16 && d_mu && d_xstats && d_ws, "null pointer argument");
+  return index_prepare_run(d_x, n, d, coarse_dtype, center, d_x16, d_mu, d_xstats, d_ws, ws_bytes, stream);
+}
+
+size_t ldot_flatip_search_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k, int32_t coarse_k) {
+  SearchPlan pl;
+  int sms = 0;
+  if (device_sm_count(&sms) != kOk) sms = 148;
+  if (search_make_plan(&pl, nq, n, d, k, coarse_k, sms) != kOk) return 0;
+  return pl.total_bytes;
+}
+
+int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const void* d_x16, const float* d_mu,
+                       const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,
+                       int32_t coarse_dtype, int64_t id_offset, float* d_out_scores, int64_t* d_out_idx,
+                       int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, void* stream) {
+  LDOT_REQUIRE(d_q && d_x && d_x16 && d_mu && d_xstats && d_out_scores && d_out_idx && d_out_flags && d_ws,
+               "null pointer argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
+  SearchArgs a;
+  a.q = d_q;
+  a.nq = nq;
+  a.x = d_x;
+  a.x16 = d_x16;
+  a.mu = d_mu;
+  a.xstats = d_xstats;
+  a.n = n;
+  a.d = d;
+  a.k = k;
+  a.coarse_k = coarse_k;
+  a.coarse_dtype = coarse_dtype;
+  a.id_offset = id_offset;
+  a.out_scores = d_out_scores;
+  a.out_idx = reinterpret_cast<long long*>(d_out_idx);
+  a.out_flags = d_out_flags;
+  a.out_flag_count = d_out_flag_count;
+  a.ws = d_ws;
+  a.ws_bytes = ws_bytes;
+  a.stream = stream;
+  return search_run(a);
+}
+
+size_t ldot_flatip_exact_workspace_bytes(int64_t n) { return exact_workspace_bytes(n); }
+
+int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n, int32_t d, int32_t k,
+                      int64_t id_offset, float* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes,
+                      void* stream) {
+  LDOT_REQUIRE(d_q && d_x && d_out_scores && d_out_idx && d_ws, "null pointer argument");
+  return exact_run(d_q, nq, d_x, n, d, k, id_offset, d_out_scores, reinterpret_cast<long long*>(d_out_idx), d_ws,
+                   ws_bytes, stream);
+}
+
+int ldot_topk_merge(const float* d_scores, const int64_t* d_idx, int32_t world, int64_t nq, int32_t k,
+                    float* d_out_scores, int64_t* d_out_idx, void* stream) {
+  LDOT_REQUIRE(d_scores && d_idx && d_out_scores && d_out_idx, "null pointer argument");
+  return merge_run(d_scores, reinterpret_cast<const long long*>(d_idx), world, nq, k, d_out_scores,
+                   reinterpret_cast<long long*>(d_out_idx), stream);
+}
+
+int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
+                const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
+                int32_t dtype, int32_t act, int32_t out_f32, void* stream) {
+  LDOT_REQUIRE(d_a && d_w && d_out, "null pointer argument");
+  return linear_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_out, ldo, M, N, K, dtype, act, out_f32, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,753 @@
+// Exact inner-product top-k search (DenseFlatIndexer.search_knn, reference dvl/indexer/faiss_indexers.py:82-87,
+// i.e. faiss.IndexFlatIP.search) as a B200 pipeline:
+//
+//   1. query_prepare   fp32 queries -> 16-bit copy + per-query norms / rounding residual / q.mu
+//   2. coarse pass     tcgen05 GEMM  Q16[nq,d] x X16[n,d]^T  (fp32 accumulate in TMEM) whose epilogue keeps, per
+//                      query, a thresholded candidate list - score rows never reach HBM
+//   3. select          per query: the k' best coarse candidates over all index chunks + c_min (the k'-th coarse score)
+//   4. rescore         exact scores (fp32 inputs, fp64 accumulation, rounded to fp32) of the k' candidates from the
+//                      fp32 master index, ranked (score desc, row id asc); a per-query CERTIFICATE proves that no
+//                      row outside the candidate list can belong to the top-k; uncertified queries are flagged
+//   5. exact fallback  (separate entry point) full fp64-accumulated scan for flagged queries
+//
+// The 16-bit index copy is CENTRED (x - mean row): a per-query constant shift of all scores that leaves the
+// ranking unchanged but removes the common component that dominates near-collinear embeddings.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cfloat>
+#include <cmath>
+#include "gemm_tc.cuh"
+#include "host_common.h"
+#include "search_plan.h"
+#include "topk_common.cuh"
+
+namespace ldot {
+
+// ================================================================================================
+// 2. coarse pass epilogue: thresholded candidate lists with warp-cooperative compaction
+// ================================================================================================
+struct TopKParams {
+  int nq;                     // valid queries
+  int n;                      // valid index rows
+  int kprime;                 // entries kept by a compaction
+  int cap;                    // list capacity per (unit, query) = EPL * 32  (>= 2 * kprime)
+  unsigned long long* cand;   // [num_units][128][cap] packed (coarse key, row id)
+  int* cand_cnt;              // [num_units][128]
+  unsigned int* gtau;         // [m_tiles * 128] best known lower bound of the k'-th coarse key, shared by all units
+};
+
+// The list of lane `owner` is full: keep its k' largest entries (in place), return the k'-th key.
+template <int EPL>
+__device__ __noinline__ uint32_t warp_compact(unsigned long long* buf, int n, int kprime, int lane, int& new_cnt) {
+  const unsigned lt = (1u << lane) - 1u;
+  __syncwarp();
+  uint32_t key[EPL];
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int idx = i * 32 + lane;
+    key[i] = idx < n ? static_cast<uint32_t>(__ldcg(buf + idx) >> 32) : 0u;
+  }
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) c += (key[i] >= cand);
+    if (__reduce_add_sync(0xFFFFFFFFu, c) >= kprime) T = cand;
+  }
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) c += (key[i] > T);
+  const int need_eq = kprime - __reduce_add_sync(0xFFFFFFFFu, c);
+  int base = 0, eq_seen = 0;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    const int idx = i * 32 + lane;
+    const bool valid = idx < n;
+    const unsigned long long e = valid ? __ldcg(buf + idx) : 0ull;
+    const bool is_eq = valid && key[i] == T;
+    const unsigned m_eq = __ballot_sync(0xFFFFFFFFu, is_eq);
+    const bool take = (key[i] > T) || (is_eq && (eq_seen + __popc(m_eq & lt)) < need_eq);
+    const unsigned m_take = __ballot_sync(0xFFFFFFFFu, take);
+    __syncwarp();  // every lane has read chunk i before anyone overwrites positions <= i*32+31
+    if (take) buf[base + __popc(m_take & lt)] = e;
+    base += __popc(m_take);
+    eq_seen += __popc(m_eq);
+  }
+  __syncwarp();
+  new_cnt = base;
+  return T;
+}
+
+template <int EPL>
+struct EpiTopK {
+  using Params = TopKParams;
+  struct State {
+    float tau;
+    int cnt;
+    int q;
+    unsigned long long* buf;
+  };
+
+  static __device__ __forceinline__ void unit_begin(State& st, const Params& p, const UnitInfo& u, int row) {
+    st.q = u.m_tile * kBM + row;
+    st.buf = p.cand + (static_cast<size_t>(u.unit) * kBM + row) * p.cap;
+    st.cnt = 0;
+    st.tau = st.q < p.nq ? -INFINITY : INFINITY;  // padded query rows never collect anything
+  }
+
+  static __device__ __forceinline__ void tile(State& st, const Params& p, const UnitInfo& u, int row, int nt,
+                                              uint32_t taddr) {
+    const int lane = threadIdx.x & 31;
+    if (st.q < p.nq) {
+      const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.gtau + st.q);
+      if (g > kKeyNegInf) st.tau = fmaxf(st.tau, fkey_inv(g));
+    }
+    const int col0 = nt * kSearchBN;
+    const bool full_tile = col0 + kSearchBN <= p.n;
+#pragma unroll 1
+    for (int c = 0; c < kSearchBN; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld32(taddr + c, v);
+      ptx::tmem_ld_wait();
+      if (full_tile) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]);
+          if (s > st.tau) {
+            st.buf[st.cnt] = pack_entry(fkey(s), static_cast<uint32_t>(col0 + c + j));
+            ++st.cnt;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float s = __uint_as_float(v[j]);
+          if (s > st.tau && col0 + c + j < p.n) {
+            st.buf[st.cnt] = pack_entry(fkey(s), static_cast<uint32_t>(col0 + c + j));
+            ++st.cnt;
+          }
+        }
+      }
+      // a list that could overflow in the next 32 columns is compacted now, by the whole warp
+      unsigned need = __ballot_sync(0xFFFFFFFFu, st.cnt > p.cap - 32);
+      while (need) {
+        const int owner = __ffs(need) - 1;
+        need &= need - 1;
+        unsigned long long* obuf =
+            reinterpret_cast<unsigned long long*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(st.buf), owner));
+        const int ocnt = __shfl_sync(0xFFFFFFFFu, st.cnt, owner);
+        int new_cnt;
+        const uint32_t T = warp_compact<EPL>(obuf, ocnt, p.kprime, lane, new_cnt);
+        if (lane == owner) {
+          st.cnt = new_cnt;
+          st.tau = fmaxf(st.tau, fkey_inv(T));
+          atomicMax(p.gtau + st.q, T);
+        }
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void unit_end(State& st, const Params& p, const UnitInfo& u, int row) {
+    p.cand_cnt[static_cast<size_t>(u.unit) * kBM + row] = st.cnt;
+  }
+};
+
+// ================================================================================================
+// 3. select: merge the per-chunk lists of one query into its k' best coarse candidates
+// ================================================================================================
+constexpr int kSelStage = 4096;  // entries staged in shared memory; larger unions are read from global
+
+__global__ void __launch_bounds__(256) select_kernel(const unsigned long long* __restrict__ cand,
+                                                     const int* __restrict__ cand_cnt, int m_tiles, int chunks,
+                                                     int cap, int nq, int kprime, int* __restrict__ sel_idx,
+                                                     float* __restrict__ sel_cmin) {
+  extern __shared__ unsigned long long sel_smem[];
+  unsigned long long* stage = sel_smem;                             // [kSelStage]
+  int* prefix = reinterpret_cast<int*>(sel_smem + kSelStage);       // [chunks + 1]
+  __shared__ int scratch[33];
+  __shared__ int out_pos;
+
+  const int q = blockIdx.x;
+  const int m_tile = q / kBM, row = q % kBM;
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x)
+    prefix[c + 1] = cand_cnt[(static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row];
+  if (threadIdx.x == 0) {
+    prefix[0] = 0;
+    out_pos = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int c = 0; c < chunks; ++c) prefix[c + 1] += prefix[c];
+  __syncthreads();
+  const int L = prefix[chunks];
+  const bool staged = L <= kSelStage;
+  auto list_of = [&](int c) { return cand + ((static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row) * cap; };
+  if (staged) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < chunks; c += 8) {
+      const unsigned long long* src = list_of(c);
+      const int b = prefix[c], cnt = prefix[c + 1] - b;
+      for (int i = lane; i < cnt; i += 32) stage[b + i] = __ldcg(src + i);
+    }
+    __syncthreads();
+  }
+  auto get = [&](int i) -> unsigned long long {
+    if (staged) return stage[i];
+    int lo = 0, hi = chunks;  // largest c with prefix[c] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (prefix[mid] <= i) lo = mid; else hi = mid;
+    }
+    return __ldcg(list_of(lo) + (i - prefix[lo]));
+  };
+
+  int* out = sel_idx + static_cast<size_t>(q) * kprime;
+  if (L < kprime) {
+    // Fewer than k' entries in total: no list was ever compacted (a compaction leaves k' entries behind), so the
+    // threshold never rose above -inf and no row of the index was dropped for this query.
+    for (int i = threadIdx.x; i < kprime; i += blockDim.x) out[i] = i < L ? static_cast<int>(get(i) & 0xFFFFFFFFu) : -1;
+    if (threadIdx.x == 0) sel_cmin[q] = -INFINITY;
+    return;
+  }
+  const unsigned long long T = block_kth_largest_u64(get, L, kprime, scratch);
+  for (int i = threadIdx.x; i < L; i += blockDim.x) {
+    const unsigned long long e = get(i);
+    if (e >= T) out[atomicAdd(&out_pos, 1)] = static_cast<int>(e & 0xFFFFFFFFu);
+  }
+  if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(static_cast<uint32_t>(T >> 32));
+}
+
+// ================================================================================================
+// 4. rescore + rank + certificate
+// ================================================================================================
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// exact score of one (query, row) pair: fp32 products are exact in fp64, the 768-term sum carries ~1e-13 relative
+// error, so the fp32 rounding of the result is (almost surely) the correctly rounded inner product.
+__device__ __forceinline__ double warp_dot_f64(const float4* __restrict__ xr, const float4* qs, int d4, int lane) {
+  double acc = 0.0;
+  for (int i = lane; i < d4; i += 32) {
+    const float4 a = __ldg(xr + i);
+    const float4 b = qs[i];
+    acc = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc);
+    acc = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc);
+    acc = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc);
+    acc = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc);
+  }
+  return warp_sum_f64(acc);
+}
+
+__device__ void block_bitonic_desc(unsigned long long* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct RescoreParams {
+  const float* q;        // [nq, d] fp32 queries
+  const float* x;        // [n, d] fp32 master index
+  const int* sel_idx;    // [nq, kprime] candidate rows (-1 = none)
+  const float* sel_cmin; // [nq]
+  const float* qstats;   // [nq, 2]: |q16|, |q - q16|
+  const double* qmu;     // [nq]: q . mu
+  const float* xstats;   // [2]: max_j |x'_j - x16_j|, max_j |x16_j|
+  float* out_scores;     // [nq, k]
+  long long* out_idx;    // [nq, k]
+  int* flags;            // [nq] 1 = not certified
+  int* flag_count;
+  long long id_offset;   // added to every returned row id (shard offset)
+  int d, k, kprime, kp_pad;
+};
+
+__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
+  extern __shared__ unsigned long long rs_smem[];
+  unsigned long long* keys = rs_smem;                              // [kp_pad]
+  float4* qs = reinterpret_cast<float4*>(rs_smem + p.kp_pad);      // [d / 4]
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d4 = p.d >> 2;
+  const float4* qrow = reinterpret_cast<const float4*>(p.q + static_cast<size_t>(q) * p.d);
+  for (int i = threadIdx.x; i < d4; i += blockDim.x) qs[i] = qrow[i];
+  for (int i = p.kprime + threadIdx.x; i < p.kp_pad; i += blockDim.x) keys[i] = 0ull;
+  __syncthreads();
+  const int* cand = p.sel_idx + static_cast<size_t>(q) * p.kprime;
+  for (int j = warp; j < p.kprime; j += 8) {
+    const int id = cand[j];
+    if (id < 0) {
+      if (lane == 0) keys[j] = 0ull;
+      continue;
+    }
+    const double s = warp_dot_f64(reinterpret_cast<const float4*>(p.x + static_cast<size_t>(id) * p.d), qs, d4, lane);
+    if (lane == 0) keys[j] = rank_key(static_cast<float>(s), static_cast<uint32_t>(id));
+  }
+  __syncthreads();
+  block_bitonic_desc(keys, p.kp_pad);
+  for (int r = threadIdx.x; r < p.k; r += blockDim.x) {
+    const unsigned long long kk = keys[r];
+    const bool ok = kk != 0ull;
+    p.out_scores[static_cast<size_t>(q) * p.k + r] = ok ? rank_key_score(kk) : -FLT_MAX;
+    p.out_idx[static_cast<size_t>(q) * p.k + r] = ok ? static_cast<long long>(rank_key_id(kk)) + p.id_offset : -1ll;
+  }
+  if (threadIdx.x == 0) {
+    // Certificate.  Every row j outside the candidate list has coarse score c_j <= c_min, and its exact CENTRED score
+    // s'_j = q.(x_j - mu) satisfies |s'_j - c_j| <= E, so s'_j <= c_min + E.  If the k-th best exact centred score
+    // among the candidates is strictly larger, the true top-k is inside the list (and the list is ranked exactly).
+    const float cmin = p.sel_cmin[q];
+    bool certified;
+    if (cmin == -INFINITY) {
+      certified = true;  // no row was dropped anywhere
+    } else {
+      const unsigned long long kk = keys[p.k - 1];
+      if (kk == 0ull) {
+        certified = false;
+      } else {
+        const double sk = static_cast<double>(rank_key_score(kk));
+        const double nq16 = p.qstats[2 * q], rq = p.qstats[2 * q + 1];
+        const double rmax = p.xstats[0], xmax = p.xstats[1];
+        // rounding of x, rounding of q, cross term, tensor-core fp32 accumulation (d terms, <= 2^-22 relative each)
+        const double E = nq16 * rmax + rq * (xmax + rmax) + 2.0 * p.d * 2.384185791015625e-07 * nq16 * xmax;
+        const double slack = 1.1920928955078125e-07 * (fabs(sk) + fabs(p.qmu[q])) + 1e-30;
+        certified = (sk - p.qmu[q] - slack) > (static_cast<double>(cmin) + E * 1.0001);
+      }
+    }
+    p.flags[q] = certified ? 0 : 1;
+    if (!certified) atomicAdd(p.flag_count, 1);
+  }
+}
+
+// ================================================================================================
+// 1. query / index preparation
+// ================================================================================================
+template <class T> __device__ __forceinline__ T to16(float v);
+template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <class T> __device__ __forceinline__ float from16(T v);
+template <> __device__ __forceinline__ float from16<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float from16<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// one warp per query row
+template <class T>
+__global__ void __launch_bounds__(256) query_prepare_kernel(const float* __restrict__ q, const float* __restrict__ mu,
+                                                            int nq, int d, T* __restrict__ q16,
+                                                            float* __restrict__ qstats, double* __restrict__ qmu) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= nq) return;
+  const float* src = q + static_cast<size_t>(row) * d;
+  T* dst = q16 + static_cast<size_t>(row) * d;
+  double n16 = 0.0, r2 = 0.0, dm = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const float v = src[i];
+    const T h = to16<T>(v);
+    dst[i] = h;
+    const double hv = static_cast<double>(from16<T>(h));
+    n16 = fma(hv, hv, n16);
+    const double e = static_cast<double>(v) - hv;
+    r2 = fma(e, e, r2);
+    dm = fma(static_cast<double>(v), static_cast<double>(mu[i]), dm);
+  }
+  n16 = warp_sum_f64(n16);
+  r2 = warp_sum_f64(r2);
+  dm = warp_sum_f64(dm);
+  if (lane == 0) {
+    qstats[2 * row] = static_cast<float>(sqrt(n16) * 1.000001);
+    qstats[2 * row + 1] = static_cast<float>(sqrt(r2) * 1.000001) + FLT_MIN;
+    qmu[row] = dm;
+  }
+}
+
+// column sums in fp64 (thread per column, coalesced over columns; rows strided over blocks)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long n, int d,
+                                                     double* __restrict__ acc) {
+  const long long rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * rows_per_block;
+  const long long r1 = min(n, r0 + rows_per_block);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double s = 0.0;
+    for (long long r = r0; r < r1; ++r) s += static_cast<double>(x[r * d + c]);
+    atomicAdd(acc + c, s);
+  }
+}
+
+__global__ void mean_finalize_kernel(const double* __restrict__ acc, long long n, int d, int center,
+                                     float* __restrict__ mu) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < d) mu[c] = center ? static_cast<float>(acc[c] / static_cast<double>(n)) : 0.0f;
+}
+
+// one warp per index row: x16 = T(fl32(x - mu)); residual against the exact (x - mu); global maxima
+template <class T>
+__global__ void __launch_bounds__(256) index_convert_kernel(const float* __restrict__ x, const float* __restrict__ mu,
+                                                            long long n, int d, T* __restrict__ x16,
+                                                            unsigned int* __restrict__ stats_bits) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* src = x + row * d;
+  T* dst = x16 + row * d;
+  double r2 = 0.0, n2 = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const float v = src[i], m = mu[i];
+    const T h = to16<T>(v - m);
+    dst[i] = h;
+    const double hv = static_cast<double>(from16<T>(h));
+    const double e = (static_cast<double>(v) - static_cast<double>(m)) - hv;
+    r2 = fma(e, e, r2);
+    n2 = fma(hv, hv, n2);
+  }
+  r2 = warp_sum_f64(r2);
+  n2 = warp_sum_f64(n2);
+  if (lane == 0) {
+    // non-negative floats order like their bit patterns
+    atomicMax(stats_bits + 0, __float_as_uint(static_cast<float>(sqrt(r2) * 1.000001) + FLT_MIN));
+    atomicMax(stats_bits + 1, __float_as_uint(static_cast<float>(sqrt(n2) * 1.000001) + FLT_MIN));
+  }
+}
+
+// ================================================================================================
+// 5. exact fallback: full scan with fp64 accumulation for a small batch of queries
+// ================================================================================================
+constexpr int kExactBatch = 8;
+
+__global__ void __launch_bounds__(256) exact_scores_kernel(const float* __restrict__ q, int nf, const float* __restrict__ x,
+                                                           long long n, int d, float* __restrict__ scores) {
+  extern __shared__ float4 ex_q[];  // [nf][d/4]
+  const int d4 = d >> 2;
+  for (int i = threadIdx.x; i < nf * d4; i += blockDim.x) ex_q[i] = reinterpret_cast<const float4*>(q)[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < n; row += static_cast<long long>(gridDim.x) * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+    double acc[kExactBatch];
+#pragma unroll
+    for (int f = 0; f < kExactBatch; ++f) acc[f] = 0.0;
+    for (int i = lane; i < d4; i += 32) {
+      const float4 a = __ldg(xr + i);
+#pragma unroll
+      for (int f = 0; f < kExactBatch; ++f) {
+        if (f < nf) {
+          const float4 b = ex_q[f * d4 + i];
+          acc[f] = fma(static_cast<double>(a.x), static_cast<double>(b.x), acc[f]);
+          acc[f] = fma(static_cast<double>(a.y), static_cast<double>(b.y), acc[f]);
+          acc[f] = fma(static_cast<double>(a.z), static_cast<double>(b.z), acc[f]);
+          acc[f] = fma(static_cast<double>(a.w), static_cast<double>(b.w), acc[f]);
+        }
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < kExactBatch; ++f) {
+      if (f < nf) {
+        const double s = warp_sum_f64(acc[f]);
+        if (lane == 0) scores[static_cast<size_t>(f) * n + row] = static_cast<float>(s);
+      }
+    }
+  }
+}
+
+// one block per query: exact top-k by (score desc, id asc) over all n scores
+__global__ void __launch_bounds__(1024) exact_select_kernel(const float* __restrict__ scores, long long n, int k, int kp_pad,
+                                                            long long id_offset, float* __restrict__ out_scores,
+                                                            long long* __restrict__ out_idx) {
+  extern __shared__ unsigned long long es_keys[];  // [kp_pad]
+  __shared__ int scratch[33];
+  __shared__ int out_pos;
+  const int f = blockIdx.x;
+  const float* s = scores + static_cast<size_t>(f) * n;
+  const int nn = static_cast<int>(n);
+  const int kk = k < nn ? k : nn;
+  if (threadIdx.x == 0) out_pos = 0;
+  for (int i = threadIdx.x; i < kp_pad; i += blockDim.x) es_keys[i] = 0ull;
+  __syncthreads();
+  auto get = [&](int i) { return rank_key(__ldcg(s + i), static_cast<uint32_t>(i)); };
+  const unsigned long long T = block_kth_largest_u64(get, nn, kk, scratch);
+  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+    const unsigned long long e = get(i);
+    if (e >= T) es_keys[atomicAdd(&out_pos, 1)] = e;
+  }
+  __syncthreads();
+  block_bitonic_desc(es_keys, kp_pad);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const unsigned long long e = es_keys[r];
+    const bool ok = e != 0ull;
+    out_scores[static_cast<size_t>(f) * k + r] = ok ? rank_key_score(e) : -FLT_MAX;
+    out_idx[static_cast<size_t>(f) * k + r] = ok ? static_cast<long long>(rank_key_id(e)) + id_offset : -1ll;
+  }
+}
+
+// ================================================================================================
+// multi-GPU: merge W shard results (already exact, global ids) into the global top-k, same ranking rule
+// ================================================================================================
+__global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx,
+                                                    int W, int nq, int k, int pad, float* __restrict__ out_scores,
+                                                    long long* __restrict__ out_idx) {
+  extern __shared__ unsigned long long mg_keys[];  // [pad]
+  const int q = blockIdx.x;
+  const int total = W * k;
+  for (int i = threadIdx.x; i < pad; i += blockDim.x) {
+    unsigned long long e = 0ull;
+    if (i < total) {
+      const int w = i / k, r = i - w * k;
+      const size_t o = (static_cast<size_t>(w) * nq + q) * k + r;
+      const long long id = idx[o];
+      if (id >= 0) e = rank_key(scores[o], static_cast<uint32_t>(id));
+    }
+    mg_keys[i] = e;
+  }
+  __syncthreads();
+  block_bitonic_desc(mg_keys, pad);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const unsigned long long e = mg_keys[r];
+    const bool ok = e != 0ull;
+    out_scores[static_cast<size_t>(q) * k + r] = ok ? rank_key_score(e) : -FLT_MAX;
+    out_idx[static_cast<size_t>(q) * k + r] = ok ? static_cast<long long>(rank_key_id(e)) : -1ll;
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, int coarse_k, int sms) {
+  LDOT_REQUIRE(nq >= 1 && nq <= (1 << 22), "nq=%lld out of range [1, 4194304] (split the query batch)", nq);
+  LDOT_REQUIRE(n >= 1 && n <= 2000000000ll, "n=%lld out of range", n);
+  LDOT_REQUIRE(d >= 8 && d <= 4096 && d % 8 == 0, "d=%d must be a multiple of 8 in [8, 4096]", d);
+  LDOT_REQUIRE(k >= 1 && k <= 1024, "k=%d out of range [1, 1024]", k);
+  int kp = coarse_k > 0 ? coarse_k : k + (k / 4 > 28 ? k / 4 : 28);
+  if (kp < 64) kp = 64;
+  kp = (kp + 31) / 32 * 32;
+  LDOT_REQUIRE(kp >= k && kp <= 1280, "coarse_k=%d must be in [k, 1280]", kp);
+  pl->kprime = kp;
+  pl->epl = kp <= 128 ? 8 : kp <= 256 ? 16 : kp <= 512 ? 32 : 80;
+  pl->cap = pl->epl * 32;
+  pl->kp_pad = next_pow2(kp);
+  pl->m_tiles = static_cast<int>((nq + kBM - 1) / kBM);
+  pl->n_tiles = static_cast<int>((n + kSearchBN - 1) / kSearchBN);
+  const int target_units = 16 * sms;
+  int chunks_wanted = (target_units + pl->m_tiles - 1) / pl->m_tiles;
+  if (chunks_wanted < 1) chunks_wanted = 1;
+  int tpu = (pl->n_tiles + chunks_wanted - 1) / chunks_wanted;
+  if (tpu < 4) tpu = 4;
+  if (tpu > 256) tpu = 256;
+  pl->tiles_per_unit = tpu;
+  pl->chunks = (pl->n_tiles + tpu - 1) / tpu;
+  pl->num_units = pl->m_tiles * pl->chunks;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  pl->off_q16 = take(static_cast<size_t>(nq) * d * 2);
+  pl->off_qstats = take(static_cast<size_t>(nq) * 2 * sizeof(float));
+  pl->off_qmu = take(static_cast<size_t>(nq) * sizeof(double));
+  pl->off_gtau = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(unsigned int));
+  pl->off_flagcnt = take(sizeof(int));
+  pl->off_cnt = take(static_cast<size_t>(pl->num_units) * kBM * sizeof(int));
+  pl->off_sel_idx = take(static_cast<size_t>(nq) * kp * sizeof(int));
+  pl->off_sel_cmin = take(static_cast<size_t>(nq) * sizeof(float));
+  pl->off_cand = take(static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long));
+  pl->total_bytes = off;
+  return kOk;
+}
+
+template <int EPL>
+static int launch_coarse(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSched& s, const TopKParams& p, int sms,
+                         cudaStream_t st) {
+  using SM = GemmSmem<kSearchBN, kSearchStages>;
+  auto kern = gemm_tc_kernel<EpiTopK<EPL>, kSearchBN, kSearchStages>;
+  LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
+  const int grid = s.num_units < sms ? s.num_units : sms;
+  kern<<<grid, kGemmThreads, SM::kDynamic, st>>>(ta, tb, s, p);
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+int search_run(const SearchArgs& a) {
+  int sms = 0;
+  if (int e = device_sm_count(&sms)) return e;
+  SearchPlan pl;
+  if (int e = search_make_plan(&pl, a.nq, a.n, a.d, a.k, a.coarse_k, sms)) return e;
+  LDOT_REQUIRE(a.ws_bytes >= pl.total_bytes, "workspace too small: %zu < %zu", a.ws_bytes, pl.total_bytes);
+  LDOT_REQUIRE(a.coarse_dtype == 0 || a.coarse_dtype == 1, "coarse_dtype must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(a.x16) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.q) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.ws) & 255) == 0,
+               "q, x, x16 must be 16-byte aligned and the workspace 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(a.stream);
+  uint8_t* ws = static_cast<uint8_t*>(a.ws);
+  void* q16 = ws + pl.off_q16;
+  float* qstats = reinterpret_cast<float*>(ws + pl.off_qstats);
+  double* qmu = reinterpret_cast<double*>(ws + pl.off_qmu);
+  unsigned int* gtau = reinterpret_cast<unsigned int*>(ws + pl.off_gtau);
+  int* flagcnt = reinterpret_cast<int*>(ws + pl.off_flagcnt);
+  int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
+  int* sel_idx = reinterpret_cast<int*>(ws + pl.off_sel_idx);
+  float* sel_cmin = reinterpret_cast<float*>(ws + pl.off_sel_cmin);
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
+
+  // gtau and the flag counter are adjacent in the plan: one memset clears both
+  LDOT_CUDA(cudaMemsetAsync(gtau, 0, (pl.off_flagcnt - pl.off_gtau) + sizeof(int), st));
+  const int qblocks = static_cast<int>((a.nq + 7) / 8);
+  if (a.coarse_dtype == 0)
+    query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, static_cast<int>(a.nq), a.d,
+                                                          static_cast<__half*>(q16), qstats, qmu);
+  else
+    query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, static_cast<int>(a.nq), a.d,
+                                                                 static_cast<__nv_bfloat16*>(q16), qstats, qmu);
+  LDOT_CHECK_LAUNCH();
+
+  CUtensorMap ta, tb;
+  if (int e = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e;
+  if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, kSearchBN)) return e;
+  GemmSched s;
+  s.m_tiles = pl.m_tiles;
+  s.n_tiles = pl.n_tiles;
+  s.tiles_per_unit = pl.tiles_per_unit;
+  s.chunks = pl.chunks;
+  s.num_units = pl.num_units;
+  s.k_blocks = (a.d + kBK - 1) / kBK;
+  s.idesc = ptx::make_idesc_f16(a.coarse_dtype == 0 ? 0u : 1u, kBM, kSearchBN);
+  TopKParams tp;
+  tp.nq = static_cast<int>(a.nq);
+  tp.n = static_cast<int>(a.n);
+  tp.kprime = pl.kprime;
+  tp.cap = pl.cap;
+  tp.cand = cand;
+  tp.cand_cnt = cnt;
+  tp.gtau = gtau;
+  int e = kOk;
+  switch (pl.epl) {
+    case 8: e = launch_coarse<8>(ta, tb, s, tp, sms, st); break;
+    case 16: e = launch_coarse<16>(ta, tb, s, tp, sms, st); break;
+    case 32: e = launch_coarse<32>(ta, tb, s, tp, sms, st); break;
+    default: e = launch_coarse<80>(ta, tb, s, tp, sms, st); break;
+  }
+  if (e) return e;
+
+  const size_t sel_smem = kSelStage * sizeof(unsigned long long) + (pl.chunks + 1) * sizeof(int);
+  LDOT_REQUIRE(sel_smem <= 200 * 1024, "too many index chunks (%d)", pl.chunks);
+  LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+  select_kernel<<<static_cast<int>(a.nq), 256, sel_smem, st>>>(cand, cnt, pl.m_tiles, pl.chunks, pl.cap,
+                                                               static_cast<int>(a.nq), pl.kprime, sel_idx, sel_cmin);
+  LDOT_CHECK_LAUNCH();
+
+  RescoreParams rp;
+  rp.q = a.q;
+  rp.x = a.x;
+  rp.sel_idx = sel_idx;
+  rp.sel_cmin = sel_cmin;
+  rp.qstats = qstats;
+  rp.qmu = qmu;
+  rp.xstats = a.xstats;
+  rp.out_scores = a.out_scores;
+  rp.out_idx = a.out_idx;
+  rp.flags = a.out_flags;
+  rp.flag_count = flagcnt;
+  rp.id_offset = a.id_offset;
+  rp.d = a.d;
+  rp.k = a.k;
+  rp.kprime = pl.kprime;
+  rp.kp_pad = pl.kp_pad;
+  const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
+  rescore_kernel<<<static_cast<int>(a.nq), 256, rs_smem, st>>>(rp);
+  LDOT_CHECK_LAUNCH();
+  if (a.out_flag_count)
+    LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  return kOk;
+}
+
+size_t index_prepare_workspace_bytes(int d) { return align_up(static_cast<size_t>(d) * sizeof(double), 256); }
+
+int index_prepare_run(const float* x, long long n, int d, int coarse_dtype, int center, void* x16, float* mu,
+                      float* xstats, void* ws, size_t ws_bytes, void* stream) {
+  LDOT_REQUIRE(n >= 1 && d >= 8 && d % 8 == 0, "bad index shape n=%lld d=%d", n, d);
+  LDOT_REQUIRE(coarse_dtype == 0 || coarse_dtype == 1, "coarse_dtype must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE(ws_bytes >= index_prepare_workspace_bytes(d), "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* acc = static_cast<double*>(ws);
+  LDOT_CUDA(cudaMemsetAsync(acc, 0, static_cast<size_t>(d) * sizeof(double), st));
+  LDOT_CUDA(cudaMemsetAsync(xstats, 0, 2 * sizeof(float), st));
+  if (center) {
+    int blocks = static_cast<int>(n < 4096 ? (n + 7) / 8 : 1184);
+    if (blocks < 1) blocks = 1;
+    colsum_kernel<<<blocks, 256, 0, st>>>(x, n, d, acc);
+    LDOT_CHECK_LAUNCH();
+  }
+  mean_finalize_kernel<<<(d + 255) / 256, 256, 0, st>>>(acc, n, d, center, mu);
+  LDOT_CHECK_LAUNCH();
+  const int blocks = static_cast<int>((n + 7) / 8);
+  if (coarse_dtype == 0)
+    index_convert_kernel<__half><<<blocks, 256, 0, st>>>(x, mu, n, d, static_cast<__half*>(x16),
+                                                         reinterpret_cast<unsigned int*>(xstats));
+  else
+    index_convert_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(x, mu, n, d, static_cast<__nv_bfloat16*>(x16),
+                                                                reinterpret_cast<unsigned int*>(xstats));
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+size_t exact_workspace_bytes(long long n) { return align_up(static_cast<size_t>(kExactBatch) * n * sizeof(float), 256); }
+
+int exact_run(const float* q, long long nf, const float* x, long long n, int d, int k, long long id_offset,
+              float* out_scores, long long* out_idx, void* ws, size_t ws_bytes, void* stream) {
+  LDOT_REQUIRE(nf >= 0 && n >= 1 && n <= 2000000000ll && d >= 8 && d % 8 == 0 && d <= 4096, "bad shape");
+  LDOT_REQUIRE(k >= 1 && k <= 1024, "k=%d out of range [1, 1024]", k);
+  LDOT_REQUIRE(ws_bytes >= exact_workspace_bytes(n), "workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int sms = 0;
+  if (int e = device_sm_count(&sms)) return e;
+  float* scores = static_cast<float*>(ws);
+  const int kp_pad = next_pow2(k);
+  const size_t q_smem = static_cast<size_t>(kExactBatch) * d * sizeof(float);
+  LDOT_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(q_smem)));
+  for (long long f0 = 0; f0 < nf; f0 += kExactBatch) {
+    const int nb = static_cast<int>(nf - f0 < kExactBatch ? nf - f0 : kExactBatch);
+    long long blocks = (n + 7) / 8;
+    if (blocks > sms * 8) blocks = sms * 8;
+    exact_scores_kernel<<<static_cast<int>(blocks), 256, static_cast<size_t>(nb) * d * sizeof(float), st>>>(
+        q + f0 * d, nb, x, n, d, scores);
+    LDOT_CHECK_LAUNCH();
+    exact_select_kernel<<<nb, 1024, kp_pad * sizeof(unsigned long long), st>>>(
+        scores, n, k, kp_pad, id_offset, out_scores + f0 * k, out_idx + f0 * k);
+    LDOT_CHECK_LAUNCH();
+  }
+  return kOk;
+}
+
+int merge_run(const float* scores, const long long* idx, int W, long long nq, int k, float* out_scores,
+              long long* out_idx, void* stream) {
+  LDOT_REQUIRE(W >= 1 && W <= 64 && nq >= 0 && k >= 1 && k <= 1024, "bad merge shape W=%d nq=%lld k=%d", W, nq, k);
+  if (nq == 0) return kOk;
+  const int pad = next_pow2(W * k);
+  const size_t smem = static_cast<size_t>(pad) * sizeof(unsigned long long);
+  LDOT_REQUIRE(smem <= 200 * 1024, "W*k=%d too large for the merge kernel", W * k);
+  LDOT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  merge_kernel<<<static_cast<int>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      scores, idx, W, static_cast<int>(nq), k, pad, out_scores, out_idx);
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+}  // namespace ldot

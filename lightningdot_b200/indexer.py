@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference's index classes (dvl/indexer/faiss_indexers.py) over libldot_sm100a.
+
+  DenseIndexer / DenseFlatIndexer   same constructor, attributes (index, index_id_to_db_id, buffer_size) and methods
+                                    (index_data, search_knn, serialize, deserialize_from) as faiss_indexers.py:22-87
+  FlatIPIndex                       what `DenseFlatIndexer.index` holds instead of faiss.IndexFlatIP
+                                    (faiss_indexers.py:67): d, ntotal, add(), search(), reset() - device resident
+
+The index lives in HBM as an fp32 master copy [n, d] (exact rescoring reads it) plus a centred 16-bit copy for the
+tensor-core pass.  search() is exact: ids are ranked by (correctly rounded fp32 inner product desc, row id asc);
+queries whose exactness certificate fails are transparently re-run through the exhaustive fp64-accumulated scan.
+There is no CPU path: without the CUDA extension and a B200 every call raises.
+"""
+import logging
+import pickle
+import struct
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+logger = logging.getLogger()
+
+MAX_QUERY_BATCH = 32768  # queries per C-ABI call (bounds the candidate-list workspace)
+
+
+def _as_device_f32(a, device):
+    if isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        return t.to(device, non_blocking=False)
+    if isinstance(a, torch.Tensor):
+        return a.detach().to(device=device, dtype=torch.float32).contiguous()
+    raise TypeError(f"expected numpy array or torch tensor, got {type(a)}")
+
+
+class _Workspace:
+    """Grow-only device scratch buffer handed to the C ABI (the library itself never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        off = (-self.buf.data_ptr()) % 256
+        return self.buf[off:off + nbytes]
+
+
+class FlatIPIndex:
+    """Exact inner-product index, device resident.  Mirrors the slice of faiss.IndexFlatIP the reference uses
+    (add / search / ntotal / d; faiss_indexers.py:67,77,83)."""
+
+    def __init__(self, d, device=None, coarse_dtype="fp16", center=True, coarse_k=0, row_offset=0):
+        if d % 8 != 0 or not 8 <= d <= 4096:
+            raise ValueError(f"vector size must be a multiple of 8 in [8, 4096], got {d}")
+        self.d = int(d)
+        self.device = torch.device(device) if device is not None else None
+        self.coarse_dtype = {"fp16": _lib.COARSE_FP16, "bf16": _lib.COARSE_BF16}[coarse_dtype]
+        self.center = bool(center)
+        self.coarse_k = int(coarse_k)
+        self.row_offset = int(row_offset)   # global id of local row 0 (row-sharded index)
+        self.is_trained = True
+        self._chunks = []
+        self._n = 0
+        self._x = None        # [n, d] fp32 master
+        self._x16 = None      # [n, d] centred 16-bit copy
+        self._mu = None       # [d]
+        self._xstats = None   # [2]
+        self._ws = _Workspace()
+        self.last_flagged = 0  # queries of the last search() that needed the exhaustive fallback
+
+    # -- faiss-like surface -------------------------------------------------------------------------------------
+    @property
+    def ntotal(self):
+        return self._n
+
+    def reset(self):
+        self._chunks, self._n = [], 0
+        self._x = self._x16 = self._mu = self._xstats = None
+
+    def add(self, x):
+        dev = self._device()
+        t = _as_device_f32(x, dev)
+        if t.dim() != 2 or t.shape[1] != self.d:
+            raise ValueError(f"add() expects [n, {self.d}], got {tuple(t.shape)}")
+        if t.shape[0] == 0:
+            return
+        if self._x is not None:
+            self._chunks = [self._x]
+        self._chunks.append(t)
+        self._n += t.shape[0]
+        self._x = self._x16 = None
+
+    def search(self, q, k):
+        """-> (scores float32 [nq, k], labels int64 [nq, k]) as numpy arrays (the faiss return convention)."""
+        dev = self._device()
+        qd = _as_device_f32(q, dev)
+        scores, idx = self.search_device(qd, k)
+        return scores.cpu().numpy(), idx.cpu().numpy()
+
+    # -- device-level API (used by the eval loop and the benchmark to avoid host round trips) -------------------
+    def search_device(self, qd, k, resolve_flags=True):
+        """qd: cuda fp32 [nq, d].  -> (scores [nq, k] fp32, labels [nq, k] int64) cuda tensors.
+        With resolve_flags (default) flagged queries are re-run exhaustively (one 4-byte D2H sync per call)."""
+        lib = _lib.load()
+        self._finalize()
+        if qd.dim() != 2 or qd.shape[1] != self.d:
+            raise ValueError(f"search() expects [nq, {self.d}], got {tuple(qd.shape)}")
+        if not 1 <= k <= 1024:
+            raise ValueError(f"top_docs must be in [1, 1024], got {k}")
+        nq = qd.shape[0]
+        dev = qd.device
+        scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if nq == 0:
+            return scores, idx
+        if self._n == 0:
+            scores.fill_(-3.4028235e38)
+            idx.fill_(-1)
+            return scores, idx
+        flags = torch.empty((nq,), dtype=torch.int32, device=dev)
+        counts = torch.zeros(((nq + MAX_QUERY_BATCH - 1) // MAX_QUERY_BATCH,), dtype=torch.int32, device=dev)
+        stream = _lib.stream_ptr()
+        for bi, b in enumerate(range(0, nq, MAX_QUERY_BATCH)):
+            e = min(nq, b + MAX_QUERY_BATCH)
+            nb = e - b
+            need = lib.ldot_flatip_search_workspace_bytes(nb, self._n, self.d, k, self.coarse_k)
+            if need == 0:
+                raise _lib.LdotError(f"invalid search shape: {lib.ldot_last_error().decode()}")
+            ws = self._ws.get(need, dev)
+            _lib.check(lib.ldot_flatip_search(
+                _lib.ptr(qd[b:e]), nb, _lib.ptr(self._x), _lib.ptr(self._x16), _lib.ptr(self._mu),
+                _lib.ptr(self._xstats), self._n, self.d, k, self.coarse_k, self.coarse_dtype, self.row_offset,
+                _lib.ptr(scores[b:e]), _lib.ptr(idx[b:e]), _lib.ptr(flags[b:e]), _lib.ptr(counts[bi:bi + 1]),
+                _lib.ptr(ws), need, stream))
+        self.last_flagged = 0
+        if resolve_flags:
+            n_flag = int(counts.sum().item())
+            self.last_flagged = n_flag
+            if n_flag:
+                rows = torch.nonzero(flags, as_tuple=False).flatten()
+                es, ei = self.exact_search_device(qd.index_select(0, rows).contiguous(), k)
+                scores.index_copy_(0, rows, es)
+                idx.index_copy_(0, rows, ei)
+        return scores, idx
+
+    def exact_search_device(self, qd, k):
+        """Exhaustive fp64-accumulated scan (no tensor cores) - the fallback path, also usable on its own."""
+        lib = _lib.load()
+        self._finalize()
+        nq = qd.shape[0]
+        scores = torch.empty((nq, k), dtype=torch.float32, device=qd.device)
+        idx = torch.empty((nq, k), dtype=torch.int64, device=qd.device)
+        if nq == 0:
+            return scores, idx
+        need = lib.ldot_flatip_exact_workspace_bytes(self._n)
+        ws = self._ws.get(need, qd.device)
+        _lib.check(lib.ldot_flatip_exact(_lib.ptr(qd), nq, _lib.ptr(self._x), self._n, self.d, k, self.row_offset,
+                                         _lib.ptr(scores), _lib.ptr(idx), _lib.ptr(ws), need, _lib.stream_ptr()))
+        return scores, idx
+
+    # -- internals ----------------------------------------------------------------------------------------------
+    def _device(self):
+        if self.device is None:
+            if not torch.cuda.is_available():
+                raise _lib.LdotError("FlatIPIndex needs a CUDA device (B200); there is no CPU fallback")
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        return self.device
+
+    def _finalize(self):
+        """Concatenate pending adds and (re)build the centred 16-bit copy + certificate statistics."""
+        if self._x16 is not None or self._n == 0:
+            return
+        lib = _lib.load()
+        _lib.check(lib.ldot_device_check())
+        dev = self._device()
+        if self._x is None:
+            self._x = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks, dim=0)
+            self._chunks = []
+        x16_dtype = torch.float16 if self.coarse_dtype == _lib.COARSE_FP16 else torch.bfloat16
+        self._x16 = torch.empty((self._n, self.d), dtype=x16_dtype, device=dev)
+        self._mu = torch.empty((self.d,), dtype=torch.float32, device=dev)
+        self._xstats = torch.empty((2,), dtype=torch.float32, device=dev)
+        need = lib.ldot_index_prepare_workspace_bytes(self._n, self.d)
+        ws = self._ws.get(need, dev)
+        _lib.check(lib.ldot_index_prepare(_lib.ptr(self._x), self._n, self.d, self.coarse_dtype, int(self.center),
+                                          _lib.ptr(self._x16), _lib.ptr(self._mu), _lib.ptr(self._xstats),
+                                          _lib.ptr(ws), need, _lib.stream_ptr()))
+
+    def vectors(self):
+        """fp32 master copy as a cuda tensor [ntotal, d]."""
+        self._finalize()
+        return self._x
+
+
+# faiss on-disk layout of an IndexFlatIP (faiss/impl/index_write.cpp, faiss 1.6.x) [external, unverified here: faiss
+# is not installable offline]: fourcc "IxFI", int32 d, int64 ntotal, int64 dummy, int64 dummy, uint8 is_trained,
+# int32 metric_type (0 = inner product), uint64 len(xb), float32 xb[ntotal * d].
+_FAISS_FLAT_IP_FOURCC = b"IxFI"
+_FAISS_HEADER = struct.Struct("<iqqqBi")
+
+
+def write_flat_ip_index(index: "FlatIPIndex", path: str):
+    x = index.vectors().cpu().numpy() if index.ntotal else np.zeros((0, index.d), np.float32)
+    with open(path, "wb") as f:
+        f.write(_FAISS_FLAT_IP_FOURCC)
+        f.write(_FAISS_HEADER.pack(index.d, index.ntotal, 1 << 20, 1 << 20, 1, 0))
+        f.write(struct.pack("<Q", x.size))
+        f.write(np.ascontiguousarray(x, np.float32).tobytes())
+
+
+def read_flat_ip_index(path: str, **kw) -> "FlatIPIndex":
+    with open(path, "rb") as f:
+        if f.read(4) != _FAISS_FLAT_IP_FOURCC:
+            raise ValueError(f"{path}: not a faiss IndexFlatIP file")
+        d, ntotal, _, _, _, metric = _FAISS_HEADER.unpack(f.read(_FAISS_HEADER.size))
+        if metric != 0:
+            raise ValueError(f"{path}: metric_type {metric} is not inner product")
+        (size,) = struct.unpack("<Q", f.read(8))
+        if size != ntotal * d:
+            raise ValueError(f"{path}: vector payload {size} != ntotal * d")
+        x = np.frombuffer(f.read(size * 4), dtype=np.float32).reshape(ntotal, d)
+    idx = FlatIPIndex(d, **kw)
+    if ntotal:
+        idx.add(x)
+    return idx
+
+
+class DenseIndexer(object):
+    """dvl/indexer/faiss_indexers.py:22-60."""
+
+    def __init__(self, buffer_size: int = 50000):
+        self.buffer_size = buffer_size
+        self.index_id_to_db_id = []
+        self.index = None
+
+    def index_data(self, data: List[Tuple[object, np.array]]):
+        raise NotImplementedError
+
+    def search_knn(self, query_vectors: np.array, top_docs: int) -> List[Tuple[List[object], List[float]]]:
+        raise NotImplementedError
+
+    def serialize(self, file: str):
+        logger.info('Serializing index to %s', file)
+        index_file = file + '.index.dpr'
+        meta_file = file + '.index_meta.dpr'
+        write_flat_ip_index(self.index, index_file)
+        with open(meta_file, mode='wb') as f:
+            pickle.dump(self.index_id_to_db_id, f)
+
+    def deserialize_from(self, file: str):
+        logger.info('Loading index from %s', file)
+        index_file = file + '.index.dpr'
+        meta_file = file + '.index_meta.dpr'
+        self.index = read_flat_ip_index(index_file)
+        logger.info('Loaded index of type %s and size %d', type(self.index), self.index.ntotal)
+        with open(meta_file, "rb") as reader:
+            self.index_id_to_db_id = pickle.load(reader)
+        assert len(self.index_id_to_db_id) == self.index.ntotal, \
+            'Deserialized index_id_to_db_id should match faiss index size'
+
+    def _update_id_mapping(self, db_ids: List):
+        self.index_id_to_db_id.extend(db_ids)
+
+
+class DenseFlatIndexer(DenseIndexer):
+    """dvl/indexer/faiss_indexers.py:63-87 with the flat index resident on the B200."""
+
+    def __init__(self, vector_sz: int, buffer_size: int = 50000, **index_kw):
+        super(DenseFlatIndexer, self).__init__(buffer_size=buffer_size)
+        self.index = FlatIPIndex(vector_sz, **index_kw)
+
+    def index_data(self, data: List[Tuple[object, np.array]]):
+        n = len(data)
+        for i in range(0, n, self.buffer_size):
+            chunk = data[i:i + self.buffer_size]
+            db_ids = [t[0] for t in chunk]
+            if isinstance(chunk[0][1], torch.Tensor):
+                vectors = torch.stack([t[1].reshape(-1) for t in chunk], dim=0)
+            else:
+                vectors = np.concatenate([np.reshape(t[1], (1, -1)) for t in chunk], axis=0)
+            self._update_id_mapping(db_ids)
+            self.index.add(vectors)
+        indexed_cnt = len(self.index_id_to_db_id)
+        logger.info('Total data indexed %d', indexed_cnt)
+
+    def index_matrix(self, db_ids: List[object], vectors):
+        """Bulk variant of index_data for embeddings that are already one [n, d] matrix (numpy or cuda tensor)."""
+        assert len(db_ids) == vectors.shape[0]
+        self._update_id_mapping(list(db_ids))
+        self.index.add(vectors)
+
+    def search_knn(self, query_vectors: np.array, top_docs: int) -> List[Tuple[List[object], List[float]]]:
+        scores, indexes = self.index.search(query_vectors, top_docs)
+        # convert to external ids (a label of -1 - index shorter than top_docs - maps to the LAST id through
+        # Python's negative indexing, exactly like faiss_indexers.py:85)
+        id_map = self.index_id_to_db_id
+        db_ids = [[id_map[i] for i in query_top_idxs] for query_top_idxs in indexes.tolist()]
+        result = [(db_ids[i], scores[i]) for i in range(len(db_ids))]
+        return result
+
+
+class DenseHNSWFlatIndexer(DenseIndexer):
+    """Approximate HNSW search (faiss_indexers.py:90-154) is outside the exact-search hot path; the name stays
+    importable because dvl/trainer.py:14 imports it."""
+
+    def __init__(self, *a, **kw):
+        raise NotImplementedError("DenseHNSWFlatIndexer (--hnsw_index) is not part of the B200 exact-search path; "
+                                  "use DenseFlatIndexer")

@@ -1,0 +1,185 @@
+"""TEST INFRASTRUCTURE - mint tests/golden/* by running the UNMODIFIED reference from /root/reference.
+
+Run here (the container that has /root/reference):   python -m oracle.make_golden
+It (1) drives the reference's own classes / functions on seeded weights and inputs, (2) asserts that the oracle
+restatement (oracle/towers.py, loss.py, flatip.py, evalloop.py) reproduces them, (3) stores the REFERENCE outputs
+as small fixtures.  Weights are never stored: lightningdot_b200.synth regenerates them from the seed.
+"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims  # noqa: E402
+
+ref_shims.install()
+
+from lightningdot_b200 import synth  # noqa: E402
+from oracle import evalloop, flatip, loss as oloss, towers  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TOWER_CASES = [
+    # name, kind, layers, seed, batch, ragged
+    ("txt_l2", "txt", 2, 101, 6, True),
+    ("img_l2", "img", 2, 102, 5, True),
+    ("txt_l12", "txt", 12, 42, 4, True),
+    ("img_l12", "img", 12, 42, 4, True),
+]
+
+
+def build_reference_tower(kind, layers, sd):
+    from dvl.models.bi_encoder import BertEncoder, UniterEncoder
+    from transformers import BertConfig
+    from uniter_model.model.model import UniterConfig
+    if kind == "txt":
+        cfg = BertConfig(vocab_size=synth.VOCAB, num_hidden_layers=layers, hidden_dropout_prob=0.1,
+                         attention_probs_dropout_prob=0.1)
+        m = BertEncoder(cfg, project_dim=768)
+    else:
+        cfg = UniterConfig.from_json_file(os.path.join(ref_shims.REFERENCE_ROOT, "config", "img_base.json"))
+        cfg.num_hidden_layers = layers
+        m = UniterEncoder(cfg, project_dim=768)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("position_ids" in k or "token_type_ids" in k for k in missing), missing
+    return m.eval()
+
+
+def tower_case(name, kind, layers, seed, batch, ragged):
+    sd = synth.random_tower_state(kind, seed=seed, perturb=True, layers=layers)
+    model = build_reference_tower(kind, layers, sd)
+    if kind == "txt":
+        b = synth.text_batch(batch, 32, seed=seed, ragged=ragged)
+        with torch.no_grad():
+            seq, pooled, _ = model(b["input_ids"], b["attention_mask"], b["position_ids"])
+            oseq, opooled = towers.text_tower(sd, b["input_ids"], b["attention_mask"], b["position_ids"])
+    else:
+        b = synth.image_batch(batch, 36, seed=seed, ragged=ragged)
+        with torch.no_grad():
+            seq, pooled, _ = model(b["input_ids"], b["attention_mask"], b["position_ids"], b["img_feat"],
+                                   b["img_pos_feat"], None, b["gather_index"])
+            oseq, opooled = towers.image_tower(sd, b["input_ids"], b["attention_mask"], b["position_ids"],
+                                               b["img_feat"], b["img_pos_feat"], b["gather_index"])
+    err_p = (pooled - opooled).abs().max().item()
+    err_s = (seq[:, 0] - oseq[:, 0]).abs().max().item()
+    print(f"[tower {name}] oracle vs reference: pooled max-abs {err_p:.3e}, cls-hidden max-abs {err_s:.3e}")
+    assert err_p < 2e-5 and err_s < 2e-5
+    np.savez_compressed(os.path.join(GOLD, f"tower_{name}.npz"), pooled=pooled.numpy(), cls_hidden=seq[:, 0].numpy(),
+                        meta=np.array([layers, seed, batch, int(ragged)]))
+
+
+def loss_case():
+    from dvl.models.bi_encoder import BiEncoderNllLoss
+    from dvl.utils import _calc_loss
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(24, 768, generator=g) * 0.06
+    ctx = torch.randn(24, 768, generator=g) * 0.06 + q * 0.45
+    cap = torch.randn(24, 768, generator=g) * 0.06
+    pos = list(range(24))
+    args = types.SimpleNamespace(caption_score_weight=0.0)
+    l0, c0, s0 = _calc_loss(args, BiEncoderNllLoss(), q, ctx, None, pos, None)
+    args2 = types.SimpleNamespace(caption_score_weight=0.1)
+    l1, c1, s1 = _calc_loss(args2, BiEncoderNllLoss(), q, ctx, cap, pos, None)
+    ol0, oc0, os0 = oloss.nll(q, ctx, pos)
+    ol1, oc1, os1 = oloss.nll(q, ctx, pos, cap, 0.1)
+    assert torch.allclose(l0, ol0, atol=1e-6) and int(c0) == int(oc0) and torch.allclose(s0, os0, atol=1e-5)
+    assert torch.allclose(l1, ol1, atol=1e-6) and int(c1) == int(oc1) and torch.allclose(s1, os1, atol=1e-5)
+    print(f"[loss] reference loss {l0.item():.6f}/{l1.item():.6f} correct {int(c0)}/{int(c1)}: oracle matches")
+    np.savez_compressed(os.path.join(GOLD, "loss_inbatch.npz"), loss0=l0.numpy(), correct0=np.array(int(c0)),
+                        loss1=l1.numpy(), correct1=np.array(int(c1)), scores0=s0.numpy(), scores1=s1.numpy())
+
+
+def indexer_case():
+    """The reference's DenseFlatIndexer Python logic (buffering, id remap, result format) over the faiss stand-in."""
+    from dvl.indexer.faiss_indexers import DenseFlatIndexer
+    x = synth.gaussian_index(300, 768, seed=5)
+    q, gt = synth.planted_queries(x, 17, sigma=1.0, seed=6)
+    ids = [f"img_{i:07d}.npz" for i in range(300)]
+    ref = DenseFlatIndexer(768, buffer_size=128)
+    ref.index_data(list(zip(ids, x)))
+    res = ref.search_knn(q, 10)
+    mine = flatip.FlatIndexer(768, buffer_size=128, scorer=flatip.scores_f32)
+    mine.index_data(list(zip(ids, x)))
+    res2 = mine.search_knn(q, 10)
+    for (a_ids, a_s), (b_ids, b_s) in zip(res, res2):
+        assert list(a_ids) == list(b_ids)
+        assert np.allclose(a_s, b_s, rtol=1e-6)
+    # fp64-accumulated scorer must rank identically on this fixture (no near-ties at 1e-7)
+    res3 = flatip.FlatIndexer(768, buffer_size=128)
+    res3.index_data(list(zip(ids, x)))
+    for (a_ids, _), (b_ids, _) in zip(res, res3.search_knn(q, 10)):
+        assert list(a_ids) == list(b_ids)
+    print("[indexer] reference DenseFlatIndexer (faiss stand-in) == oracle FlatIndexer")
+    with open(os.path.join(GOLD, "indexer_small.json"), "w") as f:
+        json.dump({"ids": [list(r[0]) for r in res], "scores": [[float(v) for v in r[1]] for r in res],
+                   "gt": [int(v) for v in gt]}, f)
+
+
+def evalloop_case():
+    """The reference's eval_model_on_dataloader (dvl/trainer.py:113-190) driven by a stub encoder that returns
+    planted embeddings, so the loop / dict / recall logic is pinned without the towers."""
+    from dvl.trainer import eval_model_on_dataloader
+    n_img, cap_per_img, bs = 200, 5, 16
+    x = synth.gaussian_index(n_img, 768, seed=11)
+    n_cap = n_img * cap_per_img
+    rng = np.random.default_rng(12)
+    txt = (x[np.arange(n_cap) // cap_per_img] + 12.0 * rng.standard_normal((n_cap, 768), dtype=np.float32) / np.sqrt(768)).astype(np.float32)
+    # each image is re-encoded once per caption with a tiny perturbation (batch-composition noise)
+    img_per_cap = (x[np.arange(n_cap) // cap_per_img] + 1e-6 * rng.standard_normal((n_cap, 768), dtype=np.float32)).astype(np.float32)
+    txt_ids = [str(j) for j in range(n_cap)]
+    img_ids = [f"img_{j // cap_per_img:07d}.npz" for j in range(n_cap)]
+    img2txt = {f"img_{i:07d}.npz": [str(i * cap_per_img + c) for c in range(cap_per_img)] for i in range(n_img)}
+
+    batches = []
+    for b in range(0, n_cap, bs):
+        sl = slice(b, min(n_cap, b + bs))
+        batches.append({"txts": {"input_ids": torch.zeros(sl.stop - sl.start, 4, dtype=torch.long)},
+                        "txt_index": txt_ids[sl], "img_fname": img_ids[sl], "_slice": sl})
+
+    class StubEncoder:
+        def eval(self):
+            return self
+
+        def __call__(self, batch):
+            sl = batch["_slice"]
+            return torch.from_numpy(txt[sl]), torch.from_numpy(img_per_cap[sl]), None
+
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    loss, acc, _, (recall_txt, recall_img), (rank_txt, rank_img) = eval_model_on_dataloader(
+        StubEncoder(), batches, args, img2txt, num_tops=100)
+    o_rt, o_ri, o_rank_txt, o_rank_img = evalloop.recall_from_embeddings(
+        txt, img_per_cap, txt_ids, img_ids, img2txt, 100, scorer=flatip.scores_f32)
+    assert o_rt == recall_txt and o_ri == recall_img, (o_rt, recall_txt, o_ri, recall_img)
+    assert all(list(rank_txt[k]) == list(o_rank_txt[k]) for k in rank_txt)
+    assert all(list(rank_img[k]) == list(o_rank_img[k]) for k in rank_img)
+    o2 = evalloop.recall_from_embeddings(txt, img_per_cap, txt_ids, img_ids, img2txt, 100)
+    assert o2[0] == recall_txt and o2[1] == recall_img
+    print(f"[evalloop] reference recall_txt {recall_txt} recall_img {recall_img}: oracle matches")
+    with open(os.path.join(GOLD, "evalloop_small.json"), "w") as f:
+        json.dump({"recall_txt": {str(k): v for k, v in recall_txt.items()},
+                   "recall_img": {str(k): v for k, v in recall_img.items()},
+                   "loss": float(loss), "acc": float(acc),
+                   "rank_txt_top10": {k: list(v[:10]) for k, v in list(rank_txt.items())[:20]},
+                   "rank_img_top10": {k: list(v[:10]) for k, v in list(rank_img.items())[:20]}}, f)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(os.cpu_count())
+    for case in TOWER_CASES:
+        tower_case(*case)
+    loss_case()
+    indexer_case()
+    evalloop_case()
+    print("golden fixtures written to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
