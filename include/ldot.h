@@ -81,6 +81,30 @@ int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, cons
                 const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
                 int32_t dtype, int32_t act, int32_t out_f32, void* stream);
 
+/* ---- the rest of the tower arithmetic (16-bit activations of `dtype`, fp32 statistics) -------------------------
+ * ldot_layernorm   out[rows, H] = LayerNorm(in[rows, H]) * gamma + beta, eps 1e-12 (layer.py:108-115,149-156);
+ *                  `in` is fp32 when in_f32 != 0, else 16-bit; ld_* are row pitches in elements; H = 256 * {1,2,3,4,6,8}
+ * ldot_embed_text  out[b * out_seq + l, :] = LN(word[ids[b, l]] + pos[pos_ids[b * pos_batch_stride + l]] + type0)
+ *                  (model.py:233-246); ids / pos_ids int64; tables 16-bit [vocab, H] / [max_pos, H] / [H]
+ * ldot_embed_image out[b * out_seq + row_offset + r, :] = LN(LN_img(lin[b, r]) + LN_pos(W_pos box[b, r] + b_pos) + type1)
+ *                  (model.py:262-273,328-336); lin = img_linear(feat) + bias as fp32 [B * R, H] (from ldot_linear)
+ * ldot_attention   ctx = softmax(Q K^T / 8 + (1 - mask) * -10000) V per (sequence, head), head dim 64
+ *                  (layer.py:80-101, model.py:362-365); qkv [B * S, 3 H] = Q | K | V; mask int64 [B, S]; S <= 128
+ * ldot_cast_f32    fp32 -> 16-bit, n elements (n % 8 == 0)                                                          */
+int ldot_layernorm(const void* d_in, int64_t ld_in, int32_t in_f32, const float* d_gamma, const float* d_beta,
+                   void* d_out, int64_t ld_out, int64_t rows, int32_t H, int32_t dtype, void* stream);
+int ldot_embed_text(const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride, const void* d_word,
+                    const void* d_pos, const void* d_type0, const float* d_gamma, const float* d_beta, void* d_out,
+                    int32_t B, int32_t L, int32_t out_seq, int32_t H, int32_t vocab, int32_t max_pos, int32_t dtype,
+                    void* stream);
+int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_g, const float* d_img_b,
+                     const float* d_pos_w, const float* d_pos_bias, const float* d_pos_g, const float* d_pos_b,
+                     const float* d_type1, const float* d_ln_g, const float* d_ln_b, void* d_out, int32_t B, int32_t R,
+                     int32_t out_seq, int32_t row_offset, int32_t H, int32_t dtype, void* stream);
+int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
+                   int32_t heads, int32_t dtype, void* stream);
+int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

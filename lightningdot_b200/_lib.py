@@ -34,6 +34,13 @@ SIGNATURES = {
     "ldot_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "ldot_linear": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                               c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_layernorm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                                 c_int32, c_void_p]),
+    "ldot_embed_text": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_embed_image": (c_int32, [c_void_p] * 12 + [c_int32] * 6 + [c_void_p]),
+    "ldot_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_cast_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
 }
 
 

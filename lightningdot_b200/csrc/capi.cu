@@ -69,6 +69,20 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
                void* stream);
 }
 
+namespace ldot {
+}  // namespace ldot
+#include "encoder_params.h"
+namespace ldot {
+int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int fmt, void* stream);
+int layernorm_run(const void* in, long long ld_in, int in_f32, const float* gamma, const float* beta, void* out,
+                  long long ld_out, long long rows, int H, int fmt, void* stream);
+int embed_text_run(const long long* ids, const long long* pos_ids, long long pos_batch_stride, const void* word,
+                   const void* pos, const void* type0, const float* gamma, const float* beta, void* out, int B, int L,
+                   int out_seq, int H, int vocab, int max_pos, int fmt, void* stream);
+int embed_image_run(const EmbedImageParams& p, int H, int fmt, void* stream);
+int cast_run(const float* in, void* out, long long n, int fmt, void* stream);
+}
+
 using namespace ldot;
 
 extern "C" {
@@ -157,6 +171,51 @@ int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, cons
                 int32_t dtype, int32_t act, int32_t out_f32, void* stream) {
   LDOT_REQUIRE(d_a && d_w && d_out, "null pointer argument");
   return linear_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_out, ldo, M, N, K, dtype, act, out_f32, stream);
+}
+
+int ldot_layernorm(const void* d_in, int64_t ld_in, int32_t in_f32, const float* d_gamma, const float* d_beta,
+                   void* d_out, int64_t ld_out, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_in && d_gamma && d_beta && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return layernorm_run(d_in, ld_in, in_f32, d_gamma, d_beta, d_out, ld_out, rows, H, dtype, stream);
+}
+
+int ldot_embed_text(const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride, const void* d_word,
+                    const void* d_pos, const void* d_type0, const float* d_gamma, const float* d_beta, void* d_out,
+                    int32_t B, int32_t L, int32_t out_seq, int32_t H, int32_t vocab, int32_t max_pos, int32_t dtype,
+                    void* stream) {
+  LDOT_REQUIRE(d_ids && d_pos_ids && d_word && d_pos && d_type0 && d_gamma && d_beta && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return embed_text_run(reinterpret_cast<const long long*>(d_ids), reinterpret_cast<const long long*>(d_pos_ids),
+                        pos_batch_stride, d_word, d_pos, d_type0, d_gamma, d_beta, d_out, B, L, out_seq, H, vocab,
+                        max_pos, dtype, stream);
+}
+
+int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_g, const float* d_img_b,
+                     const float* d_pos_w, const float* d_pos_bias, const float* d_pos_g, const float* d_pos_b,
+                     const float* d_type1, const float* d_ln_g, const float* d_ln_b, void* d_out, int32_t B, int32_t R,
+                     int32_t out_seq, int32_t row_offset, int32_t H, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_lin && d_box && d_img_g && d_img_b && d_pos_w && d_pos_bias && d_pos_g && d_pos_b && d_type1 &&
+                   d_ln_g && d_ln_b && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  EmbedImageParams p;
+  p.lin = d_lin; p.box = d_box; p.img_g = d_img_g; p.img_b = d_img_b; p.pos_w = d_pos_w; p.pos_bias = d_pos_bias;
+  p.pos_g = d_pos_g; p.pos_b = d_pos_b; p.type1 = d_type1; p.ln_g = d_ln_g; p.ln_b = d_ln_b;
+  p.out = static_cast<uint16_t*>(d_out); p.B = B; p.R = R; p.out_seq = out_seq; p.row_offset = row_offset;
+  return embed_image_run(p, H, dtype, stream);
+}
+
+int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
+                   int32_t heads, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_qkv && d_mask && d_ctx, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, dtype, stream);
+}
+
+int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_in && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return cast_run(d_in, d_out, n, dtype, stream);
 }
 
 }  // extern "C"

@@ -36,16 +36,21 @@ struct TopKParams {
   unsigned int* gtau;         // [m_tiles * 128] best known lower bound of the k'-th coarse key, shared by all units
 };
 
-// The list of lane `owner` is full: keep its k' largest entries (in place), return the k'-th key.
+// The list of one lane is (nearly) full: keep its k' largest entries (in place), return the k'-th key.
+// Whole-warp cooperative: entry i of the list is handled by lane i % 32.
 template <int EPL>
 __device__ __noinline__ uint32_t warp_compact(unsigned long long* buf, int n, int kprime, int lane, int& new_cnt) {
+  constexpr bool kInRegs = EPL <= 16;  // small lists: one load round, entries stay in registers
   const unsigned lt = (1u << lane) - 1u;
   __syncwarp();
   uint32_t key[EPL];
+  unsigned long long ent[kInRegs ? EPL : 1];
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
     const int idx = i * 32 + lane;
-    key[i] = idx < n ? static_cast<uint32_t>(__ldcg(buf + idx) >> 32) : 0u;
+    const unsigned long long e = idx < n ? __ldcg(buf + idx) : 0ull;
+    key[i] = static_cast<uint32_t>(e >> 32);
+    if (kInRegs) ent[i] = e;
   }
   uint32_t T = 0;
   for (int bit = 31; bit >= 0; --bit) {
@@ -64,12 +69,14 @@ __device__ __noinline__ uint32_t warp_compact(unsigned long long* buf, int n, in
   for (int i = 0; i < EPL; ++i) {
     const int idx = i * 32 + lane;
     const bool valid = idx < n;
-    const unsigned long long e = valid ? __ldcg(buf + idx) : 0ull;
+    unsigned long long e;
+    if (kInRegs) e = ent[i];
+    else e = valid ? __ldcg(buf + idx) : 0ull;
     const bool is_eq = valid && key[i] == T;
     const unsigned m_eq = __ballot_sync(0xFFFFFFFFu, is_eq);
     const bool take = (key[i] > T) || (is_eq && (eq_seen + __popc(m_eq & lt)) < need_eq);
     const unsigned m_take = __ballot_sync(0xFFFFFFFFu, take);
-    __syncwarp();  // every lane has read chunk i before anyone overwrites positions <= i*32+31
+    if (!kInRegs) __syncwarp();  // every lane has read chunk i before anyone overwrites positions <= i*32+31
     if (take) buf[base + __popc(m_take & lt)] = e;
     base += __popc(m_take);
     eq_seen += __popc(m_eq);
@@ -130,25 +137,31 @@ struct EpiTopK {
         }
       }
       // a list that could overflow in the next 32 columns is compacted now, by the whole warp
-      unsigned need = __ballot_sync(0xFFFFFFFFu, st.cnt > p.cap - 32);
-      while (need) {
-        const int owner = __ffs(need) - 1;
-        need &= need - 1;
-        unsigned long long* obuf =
-            reinterpret_cast<unsigned long long*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(st.buf), owner));
-        const int ocnt = __shfl_sync(0xFFFFFFFFu, st.cnt, owner);
-        int new_cnt;
-        const uint32_t T = warp_compact<EPL>(obuf, ocnt, p.kprime, lane, new_cnt);
-        if (lane == owner) {
-          st.cnt = new_cnt;
-          st.tau = fmaxf(st.tau, fkey_inv(T));
-          atomicMax(p.gtau + st.q, T);
-        }
+      compact_where(st, p, lane, st.cnt > p.cap - 32);
+    }
+  }
+
+  static __device__ __forceinline__ void compact_where(State& st, const Params& p, int lane, bool mine) {
+    unsigned need = __ballot_sync(0xFFFFFFFFu, mine);
+    while (need) {
+      const int owner = __ffs(need) - 1;
+      need &= need - 1;
+      unsigned long long* obuf = reinterpret_cast<unsigned long long*>(
+          __shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(st.buf), owner));
+      const int ocnt = __shfl_sync(0xFFFFFFFFu, st.cnt, owner);
+      int new_cnt;
+      const uint32_t T = warp_compact<EPL>(obuf, ocnt, p.kprime, lane, new_cnt);
+      if (lane == owner) {
+        st.cnt = new_cnt;
+        st.tau = fmaxf(st.tau, fkey_inv(T));
+        atomicMax(p.gtau + st.q, T);
       }
     }
   }
 
   static __device__ __forceinline__ void unit_end(State& st, const Params& p, const UnitInfo& u, int row) {
+    // leave at most k' entries behind: bounds the union the select kernel has to look at (chunks x k')
+    compact_where(st, p, threadIdx.x & 31, st.cnt > p.kprime);
     p.cand_cnt[static_cast<size_t>(u.unit) * kBM + row] = st.cnt;
   }
 };
@@ -156,66 +169,93 @@ struct EpiTopK {
 // ================================================================================================
 // 3. select: merge the per-chunk lists of one query into its k' best coarse candidates
 // ================================================================================================
-constexpr int kSelStage = 4096;  // entries staged in shared memory; larger unions are read from global
+constexpr int kSelStage = 8192;  // entries staged in shared memory (64 KB); larger unions are streamed from L2
 
+// One block per query.  The union of its per-chunk lists holds every row that can be in the coarse top-k'; find the
+// k'-th largest coarse key T by bisection on the key bits (entries staged in shared memory, or streamed from the
+// L2-resident lists when the union is larger), then emit the k' survivors.
 __global__ void __launch_bounds__(256) select_kernel(const unsigned long long* __restrict__ cand,
-                                                     const int* __restrict__ cand_cnt, int m_tiles, int chunks,
+                                                     const int* __restrict__ cand_cnt,
+                                                     const unsigned int* __restrict__ gtau, int m_tiles, int chunks,
                                                      int cap, int nq, int kprime, int* __restrict__ sel_idx,
                                                      float* __restrict__ sel_cmin) {
   extern __shared__ unsigned long long sel_smem[];
   unsigned long long* stage = sel_smem;                             // [kSelStage]
-  int* prefix = reinterpret_cast<int*>(sel_smem + kSelStage);       // [chunks + 1]
+  int* cnts = reinterpret_cast<int*>(sel_smem + kSelStage);         // [chunks]
   __shared__ int scratch[33];
-  __shared__ int out_pos;
+  __shared__ int n_stage, out_pos, eq_pos;
 
   const int q = blockIdx.x;
   const int m_tile = q / kBM, row = q % kBM;
-  for (int c = threadIdx.x; c < chunks; c += blockDim.x)
-    prefix[c + 1] = cand_cnt[(static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row];
-  if (threadIdx.x == 0) {
-    prefix[0] = 0;
-    out_pos = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int mine = 0;
+  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
+    const int v = cand_cnt[(static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row];
+    cnts[c] = v;
+    mine += v;
   }
-  __syncthreads();
-  if (threadIdx.x == 0)
-    for (int c = 0; c < chunks; ++c) prefix[c + 1] += prefix[c];
-  __syncthreads();
-  const int L = prefix[chunks];
-  const bool staged = L <= kSelStage;
+  if (threadIdx.x == 0) n_stage = out_pos = eq_pos = 0;
+  const int L = block_sum(mine, scratch);  // (contains the barriers that publish cnts / the counters)
   auto list_of = [&](int c) { return cand + ((static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row) * cap; };
-  if (staged) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int c = warp; c < chunks; c += 8) {
-      const unsigned long long* src = list_of(c);
-      const int b = prefix[c], cnt = prefix[c + 1] - b;
-      for (int i = lane; i < cnt; i += 32) stage[b + i] = __ldcg(src + i);
-    }
-    __syncthreads();
-  }
-  auto get = [&](int i) -> unsigned long long {
-    if (staged) return stage[i];
-    int lo = 0, hi = chunks;  // largest c with prefix[c] <= i
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (prefix[mid] <= i) lo = mid; else hi = mid;
-    }
-    return __ldcg(list_of(lo) + (i - prefix[lo]));
-  };
-
   int* out = sel_idx + static_cast<size_t>(q) * kprime;
+
   if (L < kprime) {
     // Fewer than k' entries in total: no list was ever compacted (a compaction leaves k' entries behind), so the
     // threshold never rose above -inf and no row of the index was dropped for this query.
-    for (int i = threadIdx.x; i < kprime; i += blockDim.x) out[i] = i < L ? static_cast<int>(get(i) & 0xFFFFFFFFu) : -1;
+    for (int c = warp; c < chunks; c += 8) {
+      const unsigned long long* src = list_of(c);
+      for (int i = lane; i < cnts[c]; i += 32) out[atomicAdd(&out_pos, 1)] = static_cast<int>(__ldcg(src + i) & 0xFFFFFFFFu);
+    }
+    __syncthreads();
+    for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) out[i] = -1;
     if (threadIdx.x == 0) sel_cmin[q] = -INFINITY;
     return;
   }
-  const unsigned long long T = block_kth_largest_u64(get, L, kprime, scratch);
-  for (int i = threadIdx.x; i < L; i += blockDim.x) {
-    const unsigned long long e = get(i);
-    if (e >= T) out[atomicAdd(&out_pos, 1)] = static_cast<int>(e & 0xFFFFFFFFu);
+  // keys below the shared lower bound of the k'-th key cannot be among the k' best
+  const uint32_t floor_key = gtau[q];
+  const bool staged = L <= kSelStage;
+  if (staged) {
+    for (int c = warp; c < chunks; c += 8) {
+      const unsigned long long* src = list_of(c);
+      for (int i = lane; i < cnts[c]; i += 32) {
+        const unsigned long long e = __ldcg(src + i);
+        if (static_cast<uint32_t>(e >> 32) >= floor_key) stage[atomicAdd(&n_stage, 1)] = e;
+      }
+    }
+    __syncthreads();
   }
-  if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(static_cast<uint32_t>(T >> 32));
+  const int ns = n_stage;
+  auto for_each = [&](auto&& f) {
+    if (staged) {
+      for (int i = threadIdx.x; i < ns; i += blockDim.x) f(stage[i]);
+    } else {
+      for (int c = warp; c < chunks; c += 8) {
+        const unsigned long long* src = list_of(c);
+        for (int i = lane; i < cnts[c]; i += 32) f(__ldcg(src + i));
+      }
+    }
+  };
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t candk = T | (1u << bit);
+    int c = 0;
+    for_each([&](unsigned long long e) { c += (static_cast<uint32_t>(e >> 32) >= candk); });
+    if (block_sum(c, scratch) >= kprime) T = candk;
+  }
+  int c = 0;
+  for_each([&](unsigned long long e) { c += (static_cast<uint32_t>(e >> 32) > T); });
+  const int n_gt = block_sum(c, scratch);
+  const int need_eq = kprime - n_gt;
+  for_each([&](unsigned long long e) {
+    const uint32_t key = static_cast<uint32_t>(e >> 32);
+    if (key > T) {
+      out[atomicAdd(&out_pos, 1)] = static_cast<int>(e & 0xFFFFFFFFu);
+    } else if (key == T) {
+      const int r = atomicAdd(&eq_pos, 1);
+      if (r < need_eq) out[n_gt + r] = static_cast<int>(e & 0xFFFFFFFFu);
+    }
+  });
+  if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(T);
 }
 
 // ================================================================================================
@@ -647,9 +687,10 @@ int search_run(const SearchArgs& a) {
   if (e) return e;
 
   const size_t sel_smem = kSelStage * sizeof(unsigned long long) + (pl.chunks + 1) * sizeof(int);
+  static_assert(kSelStage * sizeof(unsigned long long) <= 64 * 1024, "select staging");
   LDOT_REQUIRE(sel_smem <= 200 * 1024, "too many index chunks (%d)", pl.chunks);
   LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
-  select_kernel<<<static_cast<int>(a.nq), 256, sel_smem, st>>>(cand, cnt, pl.m_tiles, pl.chunks, pl.cap,
+  select_kernel<<<static_cast<int>(a.nq), 256, sel_smem, st>>>(cand, cnt, gtau, pl.m_tiles, pl.chunks, pl.cap,
                                                                static_cast<int>(a.nq), pl.kprime, sel_idx, sel_cmin);
   LDOT_CHECK_LAUNCH();
 

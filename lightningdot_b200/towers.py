@@ -1,0 +1,209 @@
+"""Device execution of the two towers: sequences of C-ABI kernel launches over 16-bit activations.
+
+One `TowerEngine` per tower holds the inference copies of the weights (16-bit matrices with Q|K|V fused to one
+[3H, H] operand, fp32 biases / LayerNorm parameters) and runs
+
+    embeddings -> 12 x [ QKV GEMM -> attention -> O GEMM(+bias+residual) -> LN -> FFN-up GEMM(+bias+GELU)
+                         -> FFN-down GEMM(+bias+residual) -> LN ] -> CLS rows -> projection head
+
+exactly as uniter_model/model/model.py:356-387 + layer.py:159-170 + dvl/models/bi_encoder.py:83-88,120-122 do.
+All GEMMs are the tcgen05 kernel (ldot_linear); everything runs on torch's current stream.  No torch math is
+used on this path.
+"""
+import torch
+
+from . import _lib
+
+SEQ_BATCH_TOKENS = 131072   # tokens per engine pass (bounds activation scratch to ~2.5 GB)
+
+
+def _fmt_of(dtype):
+    return {torch.float16: _lib.COARSE_FP16, torch.bfloat16: _lib.COARSE_BF16}[dtype]
+
+
+class TowerEngine:
+    def __init__(self, kind, hidden, heads, ffn, layers, dtype=torch.bfloat16, pre_ln_f32=True):
+        assert kind in ("txt", "img")
+        if hidden != heads * 64:
+            raise ValueError("the attention kernel needs head_dim == 64")
+        self.kind, self.H, self.heads, self.ffn, self.layers = kind, hidden, heads, ffn, layers
+        self.dtype, self.fmt = dtype, _fmt_of(dtype)
+        self.pre_ln_f32 = pre_ln_f32
+        self.w = None
+        self.signature = None
+
+    # ------------------------------------------------------------------------------------------------ weights
+    def load(self, sd, device):
+        """Build the device inference copies from a tower state dict (keys of SURVEY.md Appendix B)."""
+        dt = self.dtype
+
+        def m16(k):
+            return sd[k].detach().to(device=device, dtype=dt).contiguous()
+
+        def f32(k):
+            return sd[k].detach().to(device=device, dtype=torch.float32).contiguous()
+
+        w = {}
+        e = "bert.embeddings."
+        w["word"], w["pos"] = m16(e + "word_embeddings.weight"), m16(e + "position_embeddings.weight")
+        tt = sd[e + "token_type_embeddings.weight"].detach()
+        w["type0"] = tt[0].to(device=device, dtype=dt).contiguous()
+        w["type1_f32"] = tt[1].to(device=device, dtype=torch.float32).contiguous()
+        w["emb_ln_g"], w["emb_ln_b"] = f32(e + "LayerNorm.weight"), f32(e + "LayerNorm.bias")
+        self.vocab, self.max_pos = w["word"].shape[0], w["pos"].shape[0]
+        if self.kind == "img":
+            p = "bert.img_embeddings."
+            w["img_w"], w["img_bias"] = m16(p + "img_linear.weight"), f32(p + "img_linear.bias")
+            w["img_ln_g"], w["img_ln_b"] = f32(p + "img_layer_norm.weight"), f32(p + "img_layer_norm.bias")
+            w["pos_w"], w["pos_bias"] = f32(p + "pos_linear.weight"), f32(p + "pos_linear.bias")
+            w["pos_ln_g"], w["pos_ln_b"] = f32(p + "pos_layer_norm.weight"), f32(p + "pos_layer_norm.bias")
+            w["iemb_ln_g"], w["iemb_ln_b"] = f32(p + "LayerNorm.weight"), f32(p + "LayerNorm.bias")
+            self.img_dim = w["img_w"].shape[1]
+        for i in range(self.layers):
+            p = f"bert.encoder.layer.{i}."
+            a = p + "attention.self."
+            w[f"qkv_w{i}"] = torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0) \
+                .detach().to(device=device, dtype=dt).contiguous()
+            w[f"qkv_b{i}"] = torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0) \
+                .detach().to(device=device, dtype=torch.float32).contiguous()
+            w[f"o_w{i}"], w[f"o_b{i}"] = m16(p + "attention.output.dense.weight"), f32(p + "attention.output.dense.bias")
+            w[f"ln1_g{i}"], w[f"ln1_b{i}"] = f32(p + "attention.output.LayerNorm.weight"), f32(p + "attention.output.LayerNorm.bias")
+            w[f"f1_w{i}"], w[f"f1_b{i}"] = m16(p + "intermediate.dense.weight"), f32(p + "intermediate.dense.bias")
+            w[f"f2_w{i}"], w[f"f2_b{i}"] = m16(p + "output.dense.weight"), f32(p + "output.dense.bias")
+            w[f"ln2_g{i}"], w[f"ln2_b{i}"] = f32(p + "output.LayerNorm.weight"), f32(p + "output.LayerNorm.bias")
+        self.project = "encode_proj.0.weight" in sd
+        if self.project:
+            w["p0_w"], w["p0_b"] = m16("encode_proj.0.weight"), f32("encode_proj.0.bias")
+            w["p_ln_g"], w["p_ln_b"] = f32("encode_proj.2.weight"), f32("encode_proj.2.bias")
+            w["p3_w"], w["p3_b"] = m16("encode_proj.3.weight"), f32("encode_proj.3.bias")
+            self.out_dim = w["p3_w"].shape[0]
+        else:
+            self.out_dim = self.H
+        self.w = w
+        self.device = torch.device(device)
+
+    # ------------------------------------------------------------------------------------------------ kernels
+    def _linear(self, a, lda, wt, bias, out, M, act=0, residual=None, rows_k=None):
+        lib = _lib.load()
+        N, K = wt.shape
+        _lib.check(lib.ldot_linear(_lib.ptr(a), lda, _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(residual),
+                                   0 if residual is None else residual.stride(0), _lib.ptr(out), out.stride(0),
+                                   M, N, K, self.fmt, act, int(out.dtype == torch.float32), _lib.stream_ptr()))
+
+    def _layernorm(self, x, g, b, out, rows, H):
+        lib = _lib.load()
+        _lib.check(lib.ldot_layernorm(_lib.ptr(x), x.stride(0), int(x.dtype == torch.float32), _lib.ptr(g), _lib.ptr(b),
+                                      _lib.ptr(out), out.stride(0), rows, H, self.fmt, _lib.stream_ptr()))
+
+    def _layers(self, h, mask, B, S):
+        """h: [B*S, H] 16-bit (updated in place); mask int64 [B, S]."""
+        lib = _lib.load()
+        T, H, dt, dev = B * S, self.H, self.dtype, h.device
+        w = self.w
+        qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
+        ctx = torch.empty((T, H), dtype=dt, device=dev)
+        pre = torch.empty((T, H), dtype=torch.float32 if self.pre_ln_f32 else dt, device=dev)
+        a = torch.empty((T, H), dtype=dt, device=dev)
+        f = torch.empty((T, self.ffn), dtype=dt, device=dev)
+        stream = _lib.stream_ptr()
+        for i in range(self.layers):
+            self._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
+            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, self.heads, self.fmt, stream))
+            self._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre, T, residual=h)
+            self._layernorm(pre, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
+            self._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f, T, act=1)
+            self._linear(f, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], pre, T, residual=a)
+            self._layernorm(pre, w[f"ln2_g{i}"], w[f"ln2_b{i}"], h, T, H)
+        return h
+
+    def _head(self, h, B, S):
+        """CLS rows (row pitch S*H) -> projection head -> fp32 [B, out_dim]."""
+        w, H, dev = self.w, self.H, h.device
+        if not self.project:
+            return h.view(B, S, H)[:, 0, :].float()
+        x = torch.empty((B, 2 * H), dtype=self.dtype, device=dev)
+        self._linear(h, S * H, w["p0_w"], w["p0_b"], x, B, act=1)
+        y = torch.empty((B, 2 * H), dtype=self.dtype, device=dev)
+        self._layernorm(x, w["p_ln_g"], w["p_ln_b"], y, B, 2 * H)
+        out = torch.empty((B, self.out_dim), dtype=torch.float32, device=dev)
+        self._linear(y, 2 * H, w["p3_w"], w["p3_b"], out, B)
+        return out
+
+    # ------------------------------------------------------------------------------------------------ towers
+    def _embed_text(self, ids, pos_ids, out, B, L, out_seq):
+        lib = _lib.load()
+        w = self.w
+        stride = 0 if pos_ids.shape[0] == 1 else pos_ids.stride(0)
+        _lib.check(lib.ldot_embed_text(_lib.ptr(ids), _lib.ptr(pos_ids), stride, _lib.ptr(w["word"]), _lib.ptr(w["pos"]),
+                                       _lib.ptr(w["type0"]), _lib.ptr(w["emb_ln_g"]), _lib.ptr(w["emb_ln_b"]),
+                                       _lib.ptr(out), B, L, out_seq, self.H, self.vocab, self.max_pos, self.fmt,
+                                       _lib.stream_ptr()))
+
+    @staticmethod
+    def _i64(t, dev):
+        return t.to(device=dev, dtype=torch.int64).contiguous()
+
+    def encode_text(self, input_ids, attention_mask, position_ids, want_seq=False):
+        """-> (sequence_output [B, L, H] 16-bit or None, pooled [B, D] fp32)"""
+        dev = self.device
+        ids, mask, pos = self._i64(input_ids, dev), self._i64(attention_mask, dev), self._i64(position_ids, dev)
+        B, L = ids.shape
+        if L > 128:
+            raise ValueError(f"sequence length {L} > 128 is not supported by the attention kernel")
+        if pos.dim() == 1:
+            pos = pos[None, :]
+        step = max(1, SEQ_BATCH_TOKENS // L)
+        pooled, seqs = [], []
+        for b0 in range(0, B, step):
+            b1 = min(B, b0 + step)
+            nb = b1 - b0
+            h = torch.empty((nb * L, self.H), dtype=self.dtype, device=dev)
+            self._embed_text(ids[b0:b1], pos if pos.shape[0] == 1 else pos[b0:b1], h, nb, L, L)
+            h = self._layers(h, mask[b0:b1], nb, L)
+            pooled.append(self._head(h, nb, L))
+            if want_seq:
+                seqs.append(h.view(nb, L, self.H))
+        return (torch.cat(seqs, 0) if want_seq else None), (pooled[0] if len(pooled) == 1 else torch.cat(pooled, 0))
+
+    def encode_image(self, input_ids, attention_mask, position_ids, img_feat, img_pos_feat, gather_index=None,
+                     want_seq=False):
+        """-> (sequence_output [B, Lt + R, H] 16-bit or None, pooled [B, D] fp32)"""
+        lib = _lib.load()
+        dev, w, H = self.device, self.w, self.H
+        ids, mask, pos = self._i64(input_ids, dev), self._i64(attention_mask, dev), self._i64(position_ids, dev)
+        feat = img_feat.to(device=dev, dtype=torch.float32).contiguous()
+        box = img_pos_feat.to(device=dev, dtype=torch.float32).contiguous()
+        B, Lt = ids.shape
+        R = feat.shape[1]
+        S = Lt + R
+        if S > 128:
+            raise ValueError(f"sequence length {S} > 128 is not supported by the attention kernel")
+        if mask.shape[1] != S:
+            raise ValueError(f"attention_mask has {mask.shape[1]} positions, expected {S}")
+        if gather_index is not None:
+            gi = gather_index.to(dev)
+            if not torch.equal(gi, torch.arange(S, device=dev)[None, :].expand(B, S)):
+                raise NotImplementedError("only the identity gather_index of dvl/data/itm.py is supported")
+        if pos.dim() == 1:
+            pos = pos[None, :]
+        step = max(1, SEQ_BATCH_TOKENS // S)
+        pooled, seqs = [], []
+        stream = _lib.stream_ptr()
+        for b0 in range(0, B, step):
+            b1 = min(B, b0 + step)
+            nb = b1 - b0
+            h = torch.empty((nb * S, H), dtype=self.dtype, device=dev)
+            self._embed_text(ids[b0:b1], pos if pos.shape[0] == 1 else pos[b0:b1], h, nb, Lt, S)
+            f16 = torch.empty((nb * R, self.img_dim), dtype=self.dtype, device=dev)
+            _lib.check(lib.ldot_cast_f32(_lib.ptr(feat[b0:b1]), _lib.ptr(f16), nb * R * self.img_dim, self.fmt, stream))
+            lin = torch.empty((nb * R, H), dtype=torch.float32, device=dev)
+            self._linear(f16, self.img_dim, w["img_w"], w["img_bias"], lin, nb * R)
+            _lib.check(lib.ldot_embed_image(
+                _lib.ptr(lin), _lib.ptr(box[b0:b1]), _lib.ptr(w["img_ln_g"]), _lib.ptr(w["img_ln_b"]), _lib.ptr(w["pos_w"]),
+                _lib.ptr(w["pos_bias"]), _lib.ptr(w["pos_ln_g"]), _lib.ptr(w["pos_ln_b"]), _lib.ptr(w["type1_f32"]),
+                _lib.ptr(w["iemb_ln_g"]), _lib.ptr(w["iemb_ln_b"]), _lib.ptr(h), nb, R, S, Lt, H, self.fmt, stream))
+            h = self._layers(h, mask[b0:b1], nb, S)
+            pooled.append(self._head(h, nb, S))
+            if want_seq:
+                seqs.append(h.view(nb, S, H))
+        return (torch.cat(seqs, 0) if want_seq else None), (pooled[0] if len(pooled) == 1 else torch.cat(pooled, 0))

@@ -140,3 +140,53 @@ if __name__ == "__main__":
         probe_search()
     if "time" in what:
         probe_time()
+
+
+def probe_towers():
+    from lightningdot_b200.towers import TowerEngine
+    from oracle import towers as otowers
+    for dtype in (torch.bfloat16, torch.float16):
+        for kind, layers in (("txt", 2), ("img", 2), ("txt", 12), ("img", 12)):
+            sd = synth.random_tower_state(kind, seed=42, perturb=True, layers=layers)
+            eng = TowerEngine(kind, 768, 12, 3072, layers, dtype=dtype)
+            eng.load(sd, "cuda")
+            if kind == "txt":
+                b = synth.text_batch(6, 32, seed=1, ragged=True)
+                seq, pooled = eng.encode_text(b["input_ids"], b["attention_mask"], b["position_ids"], want_seq=True)
+                with torch.no_grad():
+                    oseq, opooled = otowers.text_tower(sd, b["input_ids"], b["attention_mask"], b["position_ids"])
+            else:
+                b = synth.image_batch(5, 36, seed=1, ragged=True)
+                seq, pooled = eng.encode_image(b["input_ids"], b["attention_mask"], b["position_ids"], b["img_feat"],
+                                               b["img_pos_feat"], b["gather_index"], want_seq=True)
+                with torch.no_grad():
+                    oseq, opooled = otowers.image_tower(sd, b["input_ids"], b["attention_mask"], b["position_ids"],
+                                                        b["img_feat"], b["img_pos_feat"], b["gather_index"])
+            torch.cuda.synchronize()
+            got = pooled.float().cpu()
+            cos = torch.nn.functional.cosine_similarity(got, opooled, dim=-1).min().item()
+            err = (got - opooled).abs().max().item() / opooled.abs().max().item()
+            herr = (seq[:, 0].float().cpu() - oseq[:, 0]).abs().max().item()
+            print(f"tower {kind} L{layers} {dtype}: pooled cos_min={cos:.6f} rel_max_err={err:.3e} cls_hidden_abs_err={herr:.3e} "
+                  f"nan={int(torch.isnan(got).sum())}", flush=True)
+    # throughput: 10k captions, L=32
+    sd = synth.random_tower_state("txt", seed=42, layers=12)
+    eng = TowerEngine("txt", 768, 12, 3072, 12, dtype=torch.bfloat16)
+    eng.load(sd, "cuda")
+    b = synth.text_batch(10000, 32, seed=3)
+    ids, mask, pos = b["input_ids"].cuda(), b["attention_mask"].cuda(), b["position_ids"].cuda()
+    for _ in range(2):
+        eng.encode_text(ids, mask, pos)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(3):
+        eng.encode_text(ids, mask, pos)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 3
+    print(f"text tower 10000 x 32: {ms:.2f} ms  {10000 / ms * 1e3:.0f} captions/s  {10000 * 5.48e9 / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__" and "towers" in sys.argv[1:]:
+    probe_towers()

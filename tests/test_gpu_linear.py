@@ -1,0 +1,51 @@
+"""tcgen05 Linear (ldot_linear) against a plain PyTorch fp32 reference of the same op."""
+import pytest
+import torch
+
+from lightningdot_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def run_linear(M, N, K, fmt, act=0, bias=True, res=False, out_f32=True, seed=0):
+    lib = _lib.load()
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dt)
+    b = torch.randn(N, device="cuda", generator=g) if bias else None
+    r = torch.randn(M, N, device="cuda", generator=g).to(dt) if res else None
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32 if out_f32 else dt)
+    _lib.check(lib.ldot_linear(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(r), N, _lib.ptr(out), N, M, N, K,
+                               fmt, act, int(out_f32), _lib.stream_ptr()))
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b
+    if act:
+        ref = torch.nn.functional.gelu(ref)  # erf form
+    if res:
+        ref = ref + r.float()
+    return out.float(), ref
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 768), (1000, 3072, 768), (4096, 768, 3072),
+                                   (77, 1536, 768), (130, 200, 72), (1, 768, 1536)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_linear_fp32_out(cuda_lib, M, N, K, fmt):
+    out, ref = run_linear(M, N, K, fmt)
+    # inputs are exactly representable 16-bit values, accumulation is fp32: only summation-order noise remains
+    torch.testing.assert_close(out, ref, atol=1e-4, rtol=1e-5)
+
+
+def test_linear_gelu_16bit_out(cuda_lib):
+    out, ref = run_linear(512, 3072, 768, 1, act=1, out_f32=False)
+    torch.testing.assert_close(out, ref, atol=2e-2, rtol=8e-3)   # bf16 output rounding: 2^-8 relative
+    out, ref = run_linear(512, 3072, 768, 0, act=1, out_f32=False)
+    torch.testing.assert_close(out, ref, atol=2e-3, rtol=1e-3)   # fp16 output: 2^-11 relative
+
+
+def test_linear_residual(cuda_lib):
+    out, ref = run_linear(512, 768, 3072, 1, res=True, out_f32=True)
+    torch.testing.assert_close(out, ref, atol=2e-4, rtol=1e-5)
+    out, ref = run_linear(640, 768, 768, 1, res=True, out_f32=False, bias=False)
+    torch.testing.assert_close(out, ref, atol=4e-2, rtol=8e-3)
