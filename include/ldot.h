@@ -105,6 +105,19 @@ int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_
                    int32_t heads, int32_t dtype, void* stream);
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream);
 
+/* ---- in-batch-negative NLL: replaces BiEncoderNllLoss.calc (dvl/models/bi_encoder.py:615-656) -------------------
+ * ldot_split16     fp32 [rows, K] -> fp16 [rows, 3 K] hi/lo split, side 0: [hi | lo | hi], side 1: [hi | hi | lo];
+ *                  ldot_linear(split(Q, 0), split(C, 1), K = 3 K, fp32 out) then yields Q . C^T to ~2^-22 relative
+ *                  (dot_product_scores, bi_encoder.py:54-68) on the 16-bit tensor cores
+ * ldot_inbatch_nll scores = d_scores (mixed with d_scores_cap: (1 - w) s + w s_cap when d_scores_cap != NULL,
+ *                  bi_encoder.py:625-627) -> d_scores_out [bq, bc] (may alias d_scores);
+ *                  d_row_loss[i] = logsumexp_j s[i, j] - s[i, pos[i]]; d_loss = mean (reduction 0) or sum (1);
+ *                  d_correct = #{ i : argmax_j s[i, j] == pos[i] } (first maximal index); d_row_correct [bq] scratch */
+int ldot_split16(const float* d_in, int64_t rows, int32_t K, int32_t side, void* d_out, void* stream);
+int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap_weight, const int64_t* d_pos,
+                     int64_t bq, int64_t bc, int32_t reduction, float* d_scores_out, float* d_row_loss,
+                     int32_t* d_row_correct, float* d_loss, int64_t* d_correct, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

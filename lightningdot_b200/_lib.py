@@ -41,6 +41,9 @@ SIGNATURES = {
     "ldot_embed_image": (c_int32, [c_void_p] * 12 + [c_int32] * 6 + [c_void_p]),
     "ldot_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_cast_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "ldot_split16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "ldot_inbatch_nll": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -81,6 +81,9 @@ int embed_text_run(const long long* ids, const long long* pos_ids, long long pos
                    int out_seq, int H, int vocab, int max_pos, int fmt, void* stream);
 int embed_image_run(const EmbedImageParams& p, int H, int fmt, void* stream);
 int cast_run(const float* in, void* out, long long n, int fmt, void* stream);
+int split16_run(const float* in, long long rows, int K, int side, void* out, void* stream);
+int nll_run(const float* s1, const float* s2, float w, const long long* pos, long long bq, long long bc, int reduction,
+            float* s_out, float* row_loss, int* row_correct, float* loss, long long* correct, void* stream);
 }
 
 using namespace ldot;
@@ -216,6 +219,20 @@ int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void
   LDOT_REQUIRE(d_in && d_out, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
   return cast_run(d_in, d_out, n, dtype, stream);
+}
+
+int ldot_split16(const float* d_in, int64_t rows, int32_t K, int32_t side, void* d_out, void* stream) {
+  LDOT_REQUIRE(d_in && d_out, "null pointer argument");
+  return split16_run(d_in, rows, K, side, d_out, stream);
+}
+
+int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap_weight, const int64_t* d_pos,
+                     int64_t bq, int64_t bc, int32_t reduction, float* d_scores_out, float* d_row_loss,
+                     int32_t* d_row_correct, float* d_loss, int64_t* d_correct, void* stream) {
+  LDOT_REQUIRE(d_scores && d_pos && d_scores_out && d_row_loss && d_row_correct && d_loss && d_correct,
+               "null pointer argument");
+  return nll_run(d_scores, d_scores_cap, cap_weight, reinterpret_cast<const long long*>(d_pos), bq, bc, reduction,
+                 d_scores_out, d_row_loss, d_row_correct, d_loss, reinterpret_cast<long long*>(d_correct), stream);
 }
 
 }  // extern "C"

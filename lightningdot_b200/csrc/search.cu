@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 #include <cfloat>
 #include <cmath>
+#include "coarse_ts.cuh"
 #include "gemm_tc.cuh"
 #include "host_common.h"
 #include "search_plan.h"
@@ -86,7 +87,7 @@ __device__ __noinline__ uint32_t warp_compact(unsigned long long* buf, int n, in
   return T;
 }
 
-template <int EPL>
+template <int EPL, int BN>
 struct EpiTopK {
   using Params = TopKParams;
   struct State {
@@ -110,10 +111,10 @@ struct EpiTopK {
       const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.gtau + st.q);
       if (g > kKeyNegInf) st.tau = fmaxf(st.tau, fkey_inv(g));
     }
-    const int col0 = nt * kSearchBN;
-    const bool full_tile = col0 + kSearchBN <= p.n;
+    const int col0 = nt * BN;
+    const bool full_tile = col0 + BN <= p.n;
 #pragma unroll 1
-    for (int c = 0; c < kSearchBN; c += 32) {
+    for (int c = 0; c < BN; c += 32) {
       uint32_t v[32];
       ptx::tmem_ld32(taddr + c, v);
       ptx::tmem_ld_wait();
@@ -169,53 +170,78 @@ struct EpiTopK {
 // ================================================================================================
 // 3. select: merge the per-chunk lists of one query into its k' best coarse candidates
 // ================================================================================================
-constexpr int kSelStage = 8192;  // entries staged in shared memory (64 KB); larger unions are streamed from L2
+constexpr int kSelStage = 8192;    // entries staged in shared memory (64 KB)
+constexpr int kSelGroup = 64;      // lists merged by one block: 64 lists x k' <= 128 entries fit the stage
 
-// One block per query.  The union of its per-chunk lists holds every row that can be in the coarse top-k'; find the
-// k'-th largest coarse key T by bisection on the key bits (entries staged in shared memory, or streamed from the
-// L2-resident lists when the union is larger), then emit the k' survivors.
-__global__ void __launch_bounds__(256) select_kernel(const unsigned long long* __restrict__ cand,
-                                                     const int* __restrict__ cand_cnt,
-                                                     const unsigned int* __restrict__ gtau, int m_tiles, int chunks,
-                                                     int cap, int nq, int kprime, int* __restrict__ sel_idx,
+// Where the candidate lists of a query live.  List c of query q holds cnt[c * cnt_sc + q * cnt_sq] entries at
+// ent + c * ent_sc + q * ent_sq.   Level 1 reads the per-unit lists of the coarse pass (c = index chunk), level 2
+// reads the per-group survivors of level 1.
+struct SelLists {
+  const unsigned long long* ent;
+  const int* cnt;
+  long long ent_sc, ent_sq, cnt_sc, cnt_sq;
+  int num_lists;
+};
+
+// grid (nq, groups).  Block (q, g) merges lists [g * kSelGroup, (g + 1) * kSelGroup) of query q into their k'
+// largest coarse keys (bisection on the key bits over entries staged in shared memory, or streamed from the
+// L2-resident lists when the union is larger).  final == 0: survivors (packed entries) go to out_ent / out_cnt for a
+// second level; final == 1: survivor row ids go to sel_idx and the k'-th key to sel_cmin.
+// Invariant kept at every level: an entry that is dropped has at least k' entries above it, so every row outside the
+// final list has a coarse score <= c_min.
+__global__ void __launch_bounds__(256) select_kernel(const SelLists in, const unsigned int* __restrict__ gtau, int kprime,
+                                                     int final, unsigned long long* __restrict__ out_ent,
+                                                     int* __restrict__ out_cnt, int* __restrict__ sel_idx,
                                                      float* __restrict__ sel_cmin) {
   extern __shared__ unsigned long long sel_smem[];
-  unsigned long long* stage = sel_smem;                             // [kSelStage]
-  int* cnts = reinterpret_cast<int*>(sel_smem + kSelStage);         // [chunks]
+  unsigned long long* stage = sel_smem;  // [kSelStage]
+  __shared__ int cnts[kSelGroup];
   __shared__ int scratch[33];
   __shared__ int n_stage, out_pos, eq_pos;
 
-  const int q = blockIdx.x;
-  const int m_tile = q / kBM, row = q % kBM;
+  const int q = blockIdx.x, g = blockIdx.y, groups = gridDim.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = g * kSelGroup;
+  const int nl = in.num_lists - c0 < kSelGroup ? in.num_lists - c0 : kSelGroup;
   int mine = 0;
-  for (int c = threadIdx.x; c < chunks; c += blockDim.x) {
-    const int v = cand_cnt[(static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row];
-    cnts[c] = v;
-    mine += v;
+  if (threadIdx.x < kSelGroup) {
+    const int v = threadIdx.x < nl ? in.cnt[(c0 + threadIdx.x) * in.cnt_sc + q * in.cnt_sq] : 0;
+    cnts[threadIdx.x] = v;
+    mine = v;
   }
   if (threadIdx.x == 0) n_stage = out_pos = eq_pos = 0;
-  const int L = block_sum(mine, scratch);  // (contains the barriers that publish cnts / the counters)
-  auto list_of = [&](int c) { return cand + ((static_cast<size_t>(c) * m_tiles + m_tile) * kBM + row) * cap; };
-  int* out = sel_idx + static_cast<size_t>(q) * kprime;
+  const int L = block_sum(mine, scratch);  // (its barriers also publish cnts and the counters)
+  auto list_of = [&](int c) { return in.ent + (c0 + c) * in.ent_sc + q * in.ent_sq; };
+  unsigned long long* oent = final ? nullptr : out_ent + (static_cast<size_t>(q) * groups + g) * kprime;
+  int* oidx = final ? sel_idx + static_cast<size_t>(q) * kprime : nullptr;
+  auto emit = [&](int pos, unsigned long long e) {
+    if (final) oidx[pos] = static_cast<int>(e & 0xFFFFFFFFu);
+    else oent[pos] = e;
+  };
 
   if (L < kprime) {
-    // Fewer than k' entries in total: no list was ever compacted (a compaction leaves k' entries behind), so the
-    // threshold never rose above -inf and no row of the index was dropped for this query.
-    for (int c = warp; c < chunks; c += 8) {
+    // Fewer than k' entries: everything survives.  (At the final level this also means that no list was ever
+    // compacted anywhere - a compaction leaves k' entries behind - so no row of the index was dropped: c_min = -inf.)
+    for (int c = warp; c < nl; c += 8) {
       const unsigned long long* src = list_of(c);
-      for (int i = lane; i < cnts[c]; i += 32) out[atomicAdd(&out_pos, 1)] = static_cast<int>(__ldcg(src + i) & 0xFFFFFFFFu);
+      for (int i = lane; i < cnts[c]; i += 32) emit(atomicAdd(&out_pos, 1), __ldcg(src + i));
     }
-    __syncthreads();
-    for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) out[i] = -1;
-    if (threadIdx.x == 0) sel_cmin[q] = -INFINITY;
+    if (final) {
+      __syncthreads();
+      for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
+      if (threadIdx.x == 0) sel_cmin[q] = -INFINITY;
+    } else if (threadIdx.x == 0) {
+      out_cnt[q * groups + g] = L;
+    }
     return;
   }
-  // keys below the shared lower bound of the k'-th key cannot be among the k' best
+  // keys below the shared lower bound of the k'-th key cannot be among the k' best (at least k' entries of one
+  // list are >= gtau, so the filter never leaves fewer than k' entries in the union that contains that list;
+  // groups that do not contain it may shrink below k' - then they simply keep everything that is left)
   const uint32_t floor_key = gtau[q];
   const bool staged = L <= kSelStage;
   if (staged) {
-    for (int c = warp; c < chunks; c += 8) {
+    for (int c = warp; c < nl; c += 8) {
       const unsigned long long* src = list_of(c);
       for (int i = lane; i < cnts[c]; i += 32) {
         const unsigned long long e = __ldcg(src + i);
@@ -229,12 +255,22 @@ __global__ void __launch_bounds__(256) select_kernel(const unsigned long long* _
     if (staged) {
       for (int i = threadIdx.x; i < ns; i += blockDim.x) f(stage[i]);
     } else {
-      for (int c = warp; c < chunks; c += 8) {
+      for (int c = warp; c < nl; c += 8) {
         const unsigned long long* src = list_of(c);
         for (int i = lane; i < cnts[c]; i += 32) f(__ldcg(src + i));
       }
     }
   };
+  if (staged && ns < kprime) {
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) emit(i, stage[i]);
+    // only possible in a non-final group that does not hold the list that set gtau: nothing >= gtau was dropped
+    if (!final && threadIdx.x == 0) out_cnt[q * groups + g] = ns;
+    if (final) {  // cannot happen (the union holds the list that set gtau); keep the output well-formed anyway
+      for (int i = ns + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
+      if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(floor_key);
+    }
+    return;
+  }
   uint32_t T = 0;
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t candk = T | (1u << bit);
@@ -249,13 +285,16 @@ __global__ void __launch_bounds__(256) select_kernel(const unsigned long long* _
   for_each([&](unsigned long long e) {
     const uint32_t key = static_cast<uint32_t>(e >> 32);
     if (key > T) {
-      out[atomicAdd(&out_pos, 1)] = static_cast<int>(e & 0xFFFFFFFFu);
+      emit(atomicAdd(&out_pos, 1), e);
     } else if (key == T) {
       const int r = atomicAdd(&eq_pos, 1);
-      if (r < need_eq) out[n_gt + r] = static_cast<int>(e & 0xFFFFFFFFu);
+      if (r < need_eq) emit(n_gt + r, e);
     }
   });
-  if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(T);
+  if (threadIdx.x == 0) {
+    if (final) sel_cmin[q] = fkey_inv(T);
+    else out_cnt[q * groups + g] = kprime;
+  }
 }
 
 // ================================================================================================
@@ -583,17 +622,38 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->epl = kp <= 128 ? 8 : kp <= 256 ? 16 : kp <= 512 ? 32 : 80;
   pl->cap = pl->epl * 32;
   pl->kp_pad = next_pow2(kp);
+  // queries parked in TMEM (A-stationary kernel) whenever the vector fits 384 TMEM columns
+  pl->a_in_tmem = d <= kTsMaxD ? 1 : 0;
+  pl->bn = pl->a_in_tmem ? kTsBN : kSearchBN;
   pl->m_tiles = static_cast<int>((nq + kBM - 1) / kBM);
-  pl->n_tiles = static_cast<int>((n + kSearchBN - 1) / kSearchBN);
-  const int target_units = 16 * sms;
-  int chunks_wanted = (target_units + pl->m_tiles - 1) / pl->m_tiles;
-  if (chunks_wanted < 1) chunks_wanted = 1;
-  int tpu = (pl->n_tiles + chunks_wanted - 1) / chunks_wanted;
-  if (tpu < 4) tpu = 4;
-  if (tpu > 256) tpu = 256;
-  pl->tiles_per_unit = tpu;
-  pl->chunks = (pl->n_tiles + tpu - 1) / tpu;
+  pl->n_tiles = static_cast<int>((n + pl->bn - 1) / pl->bn);
+  // Units = m_tiles x chunks, dealt round-robin to one persistent CTA per SM.  Pick the chunk count that fills the
+  // last wave best; prefer long chunks (>= 4096 index rows: fewer candidate lists, fewer list compactions) and, on
+  // ties, fewer chunks.
+  const int min_tpu = 4096 / pl->bn;
+  int max_chunks = pl->n_tiles / min_tpu;
+  if (max_chunks < 1) max_chunks = 1;
+  if (max_chunks > 2048) max_chunks = 2048;
+  int best_chunks = 1;
+  double best_eff = -1.0;
+  for (int c = 1; c <= max_chunks; ++c) {
+    const int tpu_c = (pl->n_tiles + c - 1) / c;
+    const int chunks_c = (pl->n_tiles + tpu_c - 1) / tpu_c;
+    const long long units = static_cast<long long>(pl->m_tiles) * chunks_c;
+    const long long waves = (units + sms - 1) / sms;
+    // cost of the busiest CTA in tiles vs the perfectly balanced share
+    const double eff = (static_cast<double>(pl->m_tiles) * pl->n_tiles / sms) / (static_cast<double>(waves) * tpu_c);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_chunks = chunks_c;
+    }
+    if (units >= 32ll * sms) break;
+  }
+  pl->tiles_per_unit = (pl->n_tiles + best_chunks - 1) / best_chunks;
+  pl->chunks = (pl->n_tiles + pl->tiles_per_unit - 1) / pl->tiles_per_unit;
   pl->num_units = pl->m_tiles * pl->chunks;
+  pl->groups = (pl->chunks + kSelGroup - 1) / kSelGroup;  // > 1: two-level select
+  LDOT_REQUIRE(pl->groups <= kSelGroup, "index too large for one search call (chunks=%d)", pl->chunks);
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -608,19 +668,32 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->off_cnt = take(static_cast<size_t>(pl->num_units) * kBM * sizeof(int));
   pl->off_sel_idx = take(static_cast<size_t>(nq) * kp * sizeof(int));
   pl->off_sel_cmin = take(static_cast<size_t>(nq) * sizeof(float));
+  pl->off_l2_ent = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * kp * sizeof(unsigned long long) : 0);
+  pl->off_l2_cnt = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * sizeof(int) : 0);
   pl->off_cand = take(static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long));
   pl->total_bytes = off;
   return kOk;
 }
 
 template <int EPL>
-static int launch_coarse(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSched& s, const TopKParams& p, int sms,
-                         cudaStream_t st) {
+static int launch_coarse_ss(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSched& s, const TopKParams& p, int sms,
+                            cudaStream_t st) {
   using SM = GemmSmem<kSearchBN, kSearchStages>;
-  auto kern = gemm_tc_kernel<EpiTopK<EPL>, kSearchBN, kSearchStages>;
+  auto kern = gemm_tc_kernel<EpiTopK<EPL, kSearchBN>, kSearchBN, kSearchStages>;
   LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
   const int grid = s.num_units < sms ? s.num_units : sms;
   kern<<<grid, kGemmThreads, SM::kDynamic, st>>>(ta, tb, s, p);
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+template <int EPL>
+static int launch_coarse_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TopKParams& p, int sms,
+                            cudaStream_t st) {
+  auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>>;
+  LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+  const int grid = s.num_units < sms ? s.num_units : sms;
+  kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
   LDOT_CHECK_LAUNCH();
   return kOk;
 }
@@ -645,22 +718,21 @@ int search_run(const SearchArgs& a) {
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int* sel_idx = reinterpret_cast<int*>(ws + pl.off_sel_idx);
   float* sel_cmin = reinterpret_cast<float*>(ws + pl.off_sel_cmin);
+  unsigned long long* l2_ent = reinterpret_cast<unsigned long long*>(ws + pl.off_l2_ent);
+  int* l2_cnt = reinterpret_cast<int*>(ws + pl.off_l2_cnt);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
+  const int nq = static_cast<int>(a.nq);
 
   // gtau and the flag counter are adjacent in the plan: one memset clears both
   LDOT_CUDA(cudaMemsetAsync(gtau, 0, (pl.off_flagcnt - pl.off_gtau) + sizeof(int), st));
-  const int qblocks = static_cast<int>((a.nq + 7) / 8);
+  const int qblocks = (nq + 7) / 8;
   if (a.coarse_dtype == 0)
-    query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, static_cast<int>(a.nq), a.d,
-                                                          static_cast<__half*>(q16), qstats, qmu);
+    query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__half*>(q16), qstats, qmu);
   else
-    query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, static_cast<int>(a.nq), a.d,
-                                                                 static_cast<__nv_bfloat16*>(q16), qstats, qmu);
+    query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__nv_bfloat16*>(q16),
+                                                                 qstats, qmu);
   LDOT_CHECK_LAUNCH();
 
-  CUtensorMap ta, tb;
-  if (int e = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e;
-  if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, kSearchBN)) return e;
   GemmSched s;
   s.m_tiles = pl.m_tiles;
   s.n_tiles = pl.n_tiles;
@@ -668,31 +740,68 @@ int search_run(const SearchArgs& a) {
   s.chunks = pl.chunks;
   s.num_units = pl.num_units;
   s.k_blocks = (a.d + kBK - 1) / kBK;
-  s.idesc = ptx::make_idesc_f16(a.coarse_dtype == 0 ? 0u : 1u, kBM, kSearchBN);
+  s.idesc = ptx::make_idesc_f16(a.coarse_dtype == 0 ? 0u : 1u, kBM, pl.bn);
   TopKParams tp;
-  tp.nq = static_cast<int>(a.nq);
+  tp.nq = nq;
   tp.n = static_cast<int>(a.n);
   tp.kprime = pl.kprime;
   tp.cap = pl.cap;
   tp.cand = cand;
   tp.cand_cnt = cnt;
   tp.gtau = gtau;
+  CUtensorMap ta, tb;
+  if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, pl.bn)) return e;
   int e = kOk;
-  switch (pl.epl) {
-    case 8: e = launch_coarse<8>(ta, tb, s, tp, sms, st); break;
-    case 16: e = launch_coarse<16>(ta, tb, s, tp, sms, st); break;
-    case 32: e = launch_coarse<32>(ta, tb, s, tp, sms, st); break;
-    default: e = launch_coarse<80>(ta, tb, s, tp, sms, st); break;
+  if (pl.a_in_tmem) {
+    TsQueries tq;
+    tq.q16 = static_cast<const uint16_t*>(q16);
+    tq.nq = nq;
+    tq.d = a.d;
+    switch (pl.epl) {
+      case 8: e = launch_coarse_ts<8>(tb, s, tq, tp, sms, st); break;
+      case 16: e = launch_coarse_ts<16>(tb, s, tq, tp, sms, st); break;
+      case 32: e = launch_coarse_ts<32>(tb, s, tq, tp, sms, st); break;
+      default: e = launch_coarse_ts<80>(tb, s, tq, tp, sms, st); break;
+    }
+  } else {
+    if (int e2 = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e2;
+    switch (pl.epl) {
+      case 8: e = launch_coarse_ss<8>(ta, tb, s, tp, sms, st); break;
+      case 16: e = launch_coarse_ss<16>(ta, tb, s, tp, sms, st); break;
+      case 32: e = launch_coarse_ss<32>(ta, tb, s, tp, sms, st); break;
+      default: e = launch_coarse_ss<80>(ta, tb, s, tp, sms, st); break;
+    }
   }
   if (e) return e;
 
-  const size_t sel_smem = kSelStage * sizeof(unsigned long long) + (pl.chunks + 1) * sizeof(int);
+  const size_t sel_smem = kSelStage * sizeof(unsigned long long);
   static_assert(kSelStage * sizeof(unsigned long long) <= 64 * 1024, "select staging");
-  LDOT_REQUIRE(sel_smem <= 200 * 1024, "too many index chunks (%d)", pl.chunks);
   LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
-  select_kernel<<<static_cast<int>(a.nq), 256, sel_smem, st>>>(cand, cnt, gtau, pl.m_tiles, pl.chunks, pl.cap,
-                                                               static_cast<int>(a.nq), pl.kprime, sel_idx, sel_cmin);
-  LDOT_CHECK_LAUNCH();
+  SelLists l1;
+  l1.ent = cand;
+  l1.cnt = cnt;
+  l1.ent_sc = static_cast<long long>(pl.m_tiles) * kBM * pl.cap;  // list (chunk c, query q) = unit (c * m_tiles + q / 128), row q % 128
+  l1.ent_sq = pl.cap;
+  l1.cnt_sc = static_cast<long long>(pl.m_tiles) * kBM;
+  l1.cnt_sq = 1;
+  l1.num_lists = pl.chunks;
+  if (pl.groups == 1) {
+    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+    LDOT_CHECK_LAUNCH();
+  } else {
+    select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr);
+    LDOT_CHECK_LAUNCH();
+    SelLists l2;
+    l2.ent = l2_ent;
+    l2.cnt = l2_cnt;
+    l2.ent_sc = pl.kprime;
+    l2.ent_sq = static_cast<long long>(pl.groups) * pl.kprime;
+    l2.cnt_sc = 1;
+    l2.cnt_sq = pl.groups;
+    l2.num_lists = pl.groups;
+    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+    LDOT_CHECK_LAUNCH();
+  }
 
   RescoreParams rp;
   rp.q = a.q;
@@ -712,7 +821,7 @@ int search_run(const SearchArgs& a) {
   rp.kprime = pl.kprime;
   rp.kp_pad = pl.kp_pad;
   const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
-  rescore_kernel<<<static_cast<int>(a.nq), 256, rs_smem, st>>>(rp);
+  rescore_kernel<<<nq, 256, rs_smem, st>>>(rp);
   LDOT_CHECK_LAUNCH();
   if (a.out_flag_count)
     LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDeviceToDevice, st));

@@ -5,7 +5,7 @@
 
 namespace ldot {
 
-constexpr int kSearchBN = 256;     // index rows per MMA tile (UMMA N)
+constexpr int kSearchBN = 256;     // index rows per MMA tile (UMMA N) of the streamed kernel (d > 768)
 constexpr int kSearchStages = 4;   // smem ring depth: 4 x (16 KB queries + 32 KB index rows)
 
 struct SearchPlan {
@@ -13,8 +13,12 @@ struct SearchPlan {
   int epl;             // list entries per lane in the compaction (cap = epl * 32 >= 2 * kprime)
   int cap;
   int kp_pad;          // kprime rounded up to a power of two (bitonic sort width)
+  int a_in_tmem;       // 1: A-stationary kernel (queries in tensor memory, 64-row index tiles); 0: streamed 128 x 256
+  int bn;              // index rows per MMA tile
   int m_tiles, n_tiles, tiles_per_unit, chunks, num_units;
-  size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_cand;
+  int groups;          // candidate-list groups of the select stage (> 1: two-level select)
+  size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_l2_ent,
+      off_l2_cnt, off_cand;
   size_t total_bytes;
 };
 
