@@ -37,6 +37,19 @@ const char* ldot_last_error(void);
 /* 0 when the current device is an sm_100 part the kernels can run on, LDOT_ERR_ARCH / LDOT_ERR_CUDA otherwise */
 int ldot_device_check(void);
 
+/* ---- launch accounting (measurement support; no reference counterpart) ------------------------------------------
+ * The library counts every kernel it launches per kernel class (always) and, between ldot_prof_enable(1) and
+ * ldot_prof_enable(0), brackets each launch with CUDA events on the launching stream.  ldot_prof_read waits for
+ * the recorded events and returns, per class: launches, launches that were timed, summed device milliseconds, and
+ * the algorithmic FLOPs / bytes of those launches (DESIGN.md states the per-unit figures).  These three calls are
+ * the only entry points that synchronise (on their own events only).                                             */
+int ldot_prof_num_classes(void);
+const char* ldot_prof_class_name(int32_t cls);
+int ldot_prof_enable(int32_t on);
+int ldot_prof_reset(void);
+int ldot_prof_read(int32_t n_classes, int64_t* launches, int64_t* timed_launches, double* ms, double* flops,
+                   double* bytes);
+
 /* ---- index build: replaces faiss.IndexFlatIP.add (dvl/indexer/faiss_indexers.py:77) -------------------------
  * d_x      [n, d] fp32 master copy of the index (kept by the caller; the search reads it for exact rescoring)
  * d_x16    [n, d] out: centred 16-bit copy (x - mean row) for the tensor-core pass

@@ -21,6 +21,11 @@ SIGNATURES = {
     "ldot_abi_version": (c_int32, []),
     "ldot_last_error": (c_char_p, []),
     "ldot_device_check": (c_int32, []),
+    "ldot_prof_num_classes": (c_int32, []),
+    "ldot_prof_class_name": (c_char_p, [c_int32]),
+    "ldot_prof_enable": (c_int32, [c_int32]),
+    "ldot_prof_reset": (c_int32, []),
+    "ldot_prof_read": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ldot_index_prepare_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "ldot_index_prepare": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
@@ -85,3 +90,23 @@ def ptr(t):
 def stream_ptr():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_enable(on=True):
+    """Start / stop bracketing every kernel launch of the library with CUDA events (measurement support)."""
+    check(load().ldot_prof_enable(1 if on else 0))
+
+
+def prof_reset():
+    check(load().ldot_prof_reset())
+
+
+def prof_read():
+    """-> {kernel class: dict(launches, timed, ms, flops, bytes)} accumulated since the last prof_reset()."""
+    lib = load()
+    n = lib.ldot_prof_num_classes()
+    i64, f64 = ctypes.c_int64 * n, ctypes.c_double * n
+    launches, timed, ms, flops, nbytes = i64(), i64(), f64(), f64(), f64()
+    check(lib.ldot_prof_read(n, launches, timed, ms, flops, nbytes))
+    return {lib.ldot_prof_class_name(c).decode(): dict(launches=launches[c], timed=timed[c], ms=ms[c], flops=flops[c],
+                                                       bytes=nbytes[c]) for c in range(n)}

@@ -1,7 +1,10 @@
 // extern "C" surface of libldot_sm100a.so (declared in include/ldot.h) + shared host helpers.
 #include "../../include/ldot.h"
 #include <cstring>
+#include <mutex>
+#include <vector>
 #include "host_common.h"
+#include "prof.h"
 #include "search_plan.h"
 
 namespace ldot {
@@ -43,6 +46,85 @@ int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(kErrCuda, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return kOk;
+}
+
+// ---------------------------------------------------------------------------------------------- launch accounting
+namespace {
+struct ProfRecord {
+  int cls;
+  cudaEvent_t e0, e1;
+};
+struct ProfState {
+  std::mutex mu;
+  bool enabled = false;
+  long long launches[kKcCount] = {0};
+  double flops[kKcCount] = {0};
+  double bytes[kKcCount] = {0};
+  double ms[kKcCount] = {0};            // folded in by prof_collect
+  long long timed[kKcCount] = {0};      // launches that carry an event pair
+  std::vector<ProfRecord> open;         // recorded, not yet folded
+  std::vector<cudaEvent_t> pool;        // reusable events
+};
+ProfState& prof_state() {
+  static ProfState s;
+  return s;
+}
+}  // namespace
+
+const char* kernel_class_name(int c) {
+  static const char* names[kKcCount] = {"coarse_score_topk", "select", "rescore", "query_prepare", "index_prepare",
+                                        "exact_scan", "merge", "linear_tcgen05", "attention", "layernorm", "embed",
+                                        "cast", "nll"};
+  return c >= 0 && c < kKcCount ? names[c] : "?";
+}
+
+void prof_begin(int cls, cudaStream_t st, double flops, double bytes, void** token) {
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  S.launches[cls] += 1;
+  *token = nullptr;
+  if (!S.enabled) return;
+  S.flops[cls] += flops;   // work totals cover exactly the timed launches
+  S.bytes[cls] += bytes;
+  ProfRecord r;
+  r.cls = cls;
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    if (!S.pool.empty()) {
+      ev[i] = S.pool.back();
+      S.pool.pop_back();
+    } else if (cudaEventCreate(&ev[i]) != cudaSuccess) {
+      return;
+    }
+  }
+  r.e0 = ev[0];
+  r.e1 = ev[1];
+  cudaEventRecord(r.e0, st);
+  S.open.push_back(r);
+  *token = reinterpret_cast<void*>(static_cast<uintptr_t>(S.open.size()));  // index + 1
+}
+
+void prof_end(void* token, cudaStream_t st) {
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  const size_t i = static_cast<size_t>(reinterpret_cast<uintptr_t>(token)) - 1;
+  if (i < S.open.size()) cudaEventRecord(S.open[i].e1, st);
+}
+
+static int prof_collect() {
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  for (const ProfRecord& r : S.open) {
+    LDOT_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    LDOT_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    S.ms[r.cls] += ms;
+    S.timed[r.cls] += 1;
+    S.pool.push_back(r.e0);
+    S.pool.push_back(r.e1);
+  }
+  S.open.clear();
   return kOk;
 }
 
@@ -100,6 +182,45 @@ int ldot_device_check(void) {
   LDOT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   LDOT_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   if (major != 10) return set_error(kErrArch, "libldot_sm100a needs an sm_100 device, found sm_%d%d", major, minor);
+  return kOk;
+}
+
+int ldot_prof_num_classes(void) { return kKcCount; }
+
+const char* ldot_prof_class_name(int32_t cls) { return kernel_class_name(cls); }
+
+int ldot_prof_enable(int32_t on) {
+  if (int e = prof_collect()) return e;
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  S.enabled = on != 0;
+  return kOk;
+}
+
+int ldot_prof_reset(void) {
+  if (int e = prof_collect()) return e;
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  for (int c = 0; c < kKcCount; ++c) {
+    S.launches[c] = S.timed[c] = 0;
+    S.flops[c] = S.bytes[c] = S.ms[c] = 0.0;
+  }
+  return kOk;
+}
+
+int ldot_prof_read(int32_t n_classes, int64_t* launches, int64_t* timed_launches, double* ms, double* flops,
+                   double* bytes) {
+  LDOT_REQUIRE(n_classes >= 0 && launches && timed_launches && ms && flops && bytes, "null pointer argument");
+  if (int e = prof_collect()) return e;
+  ProfState& S = prof_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  for (int c = 0; c < n_classes && c < kKcCount; ++c) {
+    launches[c] = S.launches[c];
+    timed_launches[c] = S.timed[c];
+    ms[c] = S.ms[c];
+    flops[c] = S.flops[c];
+    bytes[c] = S.bytes[c];
+  }
   return kOk;
 }
 

@@ -12,6 +12,7 @@
 #include <cuda_fp16.h>
 #include <cmath>
 #include "host_common.h"
+#include "prof.h"
 #include "encoder_params.h"
 
 namespace ldot {
@@ -382,6 +383,7 @@ int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int 
   LDOT_REQUIRE(H == heads * kHeadDim && H % 8 == 0, "attention: hidden %d must be heads (%d) x 64", H, heads);
   LDOT_REQUIRE(B <= 65535, "attention: batch %d > 65535 (split the batch)", B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope ks(kKcAttention, st, 4.0 * B * static_cast<double>(S) * S * H, static_cast<double>(B) * S * H * 8.0);
   return fmt == 1 ? attention_launch<1>(qkv, mask, ctx, B, S, H, heads, st) : attention_launch<0>(qkv, mask, ctx, B, S, H, heads, st);
 }
 
@@ -402,6 +404,7 @@ int layernorm_run(const void* in, long long ld_in, int in_f32, const float* gamm
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
   uint16_t* o = static_cast<uint16_t*>(out);
+  KernelScope ks(kKcLayerNorm, st, 0.0, static_cast<double>(rows) * H * (in_f32 ? 6.0 : 4.0));
   if (fmt == 1) {
     if (in_f32) { LDOT_NV_DISPATCH(H, (layernorm_kernel<NV, 1, true><<<blocks, 256, 0, st>>>(in, ld_in, gamma, beta, o, ld_out, rows))) }
     else { LDOT_NV_DISPATCH(H, (layernorm_kernel<NV, 1, false><<<blocks, 256, 0, st>>>(in, ld_in, gamma, beta, o, ld_out, rows))) }
@@ -423,6 +426,7 @@ int embed_text_run(const long long* ids, const long long* pos_ids, long long pos
   const uint16_t* p = static_cast<const uint16_t*>(pos);
   const uint16_t* t = static_cast<const uint16_t*>(type0);
   uint16_t* o = static_cast<uint16_t*>(out);
+  KernelScope ks(kKcEmbed, st, 0.0, static_cast<double>(B) * L * H * 6.0);
   if (fmt == 1) { LDOT_NV_DISPATCH(H, (embed_text_kernel<NV, 1><<<blocks, 256, 0, st>>>(ids, pos_ids, pos_batch_stride, w, p, t, gamma, beta, o, B, L, out_seq, vocab, max_pos))) }
   else { LDOT_NV_DISPATCH(H, (embed_text_kernel<NV, 0><<<blocks, 256, 0, st>>>(ids, pos_ids, pos_batch_stride, w, p, t, gamma, beta, o, B, L, out_seq, vocab, max_pos))) }
   LDOT_CHECK_LAUNCH();
@@ -433,6 +437,7 @@ int embed_image_run(const EmbedImageParams& p, int H, int fmt, void* stream) {
   LDOT_REQUIRE(p.B >= 1 && p.R >= 1 && H % 256 == 0 && p.out_seq >= p.row_offset + p.R, "embed_image: bad shape");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned blocks = static_cast<unsigned>((static_cast<long long>(p.B) * p.R + 7) / 8);
+  KernelScope ks(kKcEmbed, st, 0.0, static_cast<double>(p.B) * p.R * H * 6.0);
   if (fmt == 1) { LDOT_NV_DISPATCH(H, (embed_image_kernel<NV, 1><<<blocks, 256, 0, st>>>(p))) }
   else { LDOT_NV_DISPATCH(H, (embed_image_kernel<NV, 0><<<blocks, 256, 0, st>>>(p))) }
   LDOT_CHECK_LAUNCH();
@@ -447,6 +452,7 @@ int cast_run(const float* in, void* out, long long n, int fmt, void* stream) {
   long long blocks = (n8 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope ks(kKcCast, st, 0.0, static_cast<double>(n) * 6.0);
   if (fmt == 1) cast_kernel<1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, static_cast<uint16_t*>(out), n8);
   else cast_kernel<0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, static_cast<uint16_t*>(out), n8);
   LDOT_CHECK_LAUNCH();

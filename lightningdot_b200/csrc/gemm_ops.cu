@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 #include "host_common.h"
+#include "prof.h"
 
 namespace ldot {
 
@@ -181,7 +182,12 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   auto kern = gemm_tc_kernel<EpiStore, kLinBN, kLinStages>;
   LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
   const int grid = s.num_units < sms ? s.num_units : sms;
-  kern<<<grid, kGemmThreads, SM::kDynamic, static_cast<cudaStream_t>(stream)>>>(ta, tb, s, p);
+  {
+    KernelScope ks(kKcLinear, static_cast<cudaStream_t>(stream), 2.0 * M * static_cast<double>(N) * K,
+                   (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 +
+                       static_cast<double>(M) * N * (out_f32 ? 4.0 : 2.0) + (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
+    kern<<<grid, kGemmThreads, SM::kDynamic, static_cast<cudaStream_t>(stream)>>>(ta, tb, s, p);
+  }
   LDOT_CHECK_LAUNCH();
   return kOk;
 }

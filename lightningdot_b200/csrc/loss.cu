@@ -13,6 +13,7 @@
 #include <cfloat>
 #include <cmath>
 #include "host_common.h"
+#include "prof.h"
 
 namespace ldot {
 
@@ -118,8 +119,11 @@ int split16_run(const float* in, long long rows, int K, int side, void* out, voi
   LDOT_REQUIRE(rows >= 1 && K >= 1 && (side == 0 || side == 1), "split16: bad arguments");
   long long blocks = (rows * K + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, rows, K, side,
-                                                                                               static_cast<__half*>(out));
+  {
+    KernelScope ks(kKcCast, static_cast<cudaStream_t>(stream), 0.0, static_cast<double>(rows) * K * 10.0);
+    split16_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, rows, K, side,
+                                                                                                 static_cast<__half*>(out));
+  }
   LDOT_CHECK_LAUNCH();
   return kOk;
 }
@@ -129,9 +133,15 @@ int nll_run(const float* s1, const float* s2, float w, const long long* pos, lon
   LDOT_REQUIRE(bq >= 1 && bc >= 1 && bc < (1ll << 31) && bq < (1ll << 31), "nll: bad shape %lld x %lld", bq, bc);
   LDOT_REQUIRE(reduction == 0 || reduction == 1, "nll: reduction must be 0 (mean) or 1 (sum)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  nll_rows_kernel<<<static_cast<unsigned>(bq), 256, 0, st>>>(s1, s2, w, pos, bc, s_out, row_loss, row_correct);
+  {
+    KernelScope ks(kKcNll, st, 0.0, static_cast<double>(bq) * bc * (s2 ? 12.0 : 8.0));
+    nll_rows_kernel<<<static_cast<unsigned>(bq), 256, 0, st>>>(s1, s2, w, pos, bc, s_out, row_loss, row_correct);
+  }
   LDOT_CHECK_LAUNCH();
-  nll_finalize_kernel<<<1, 256, 0, st>>>(row_loss, row_correct, bq, reduction, loss, correct);
+  {
+    KernelScope ks(kKcNll, st);
+    nll_finalize_kernel<<<1, 256, 0, st>>>(row_loss, row_correct, bq, reduction, loss, correct);
+  }
   LDOT_CHECK_LAUNCH();
   return kOk;
 }

@@ -19,6 +19,7 @@
 #include "coarse_ts.cuh"
 #include "gemm_tc.cuh"
 #include "host_common.h"
+#include "prof.h"
 #include "search_plan.h"
 #include "topk_common.cuh"
 
@@ -726,11 +727,14 @@ int search_run(const SearchArgs& a) {
   // gtau and the flag counter are adjacent in the plan: one memset clears both
   LDOT_CUDA(cudaMemsetAsync(gtau, 0, (pl.off_flagcnt - pl.off_gtau) + sizeof(int), st));
   const int qblocks = (nq + 7) / 8;
+  {
+    KernelScope ks(kKcQueryPrep, st, 0.0, static_cast<double>(nq) * a.d * 6.0);
   if (a.coarse_dtype == 0)
     query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__half*>(q16), qstats, qmu);
   else
     query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__nv_bfloat16*>(q16),
                                                                  qstats, qmu);
+  }
   LDOT_CHECK_LAUNCH();
 
   GemmSched s;
@@ -752,6 +756,12 @@ int search_run(const SearchArgs& a) {
   CUtensorMap ta, tb;
   if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, pl.bn)) return e;
   int e = kOk;
+  // algorithmic work of the coarse pass: every (query, row) pair once; the 16-bit index and queries read once
+  if (!pl.a_in_tmem)
+    if (int e2 = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e2;
+  {
+  KernelScope coarse_scope(kKcCoarse, st, 2.0 * nq * static_cast<double>(a.n) * a.d,
+                           (static_cast<double>(a.n) + nq) * a.d * 2.0);
   if (pl.a_in_tmem) {
     TsQueries tq;
     tq.q16 = static_cast<const uint16_t*>(q16);
@@ -764,13 +774,13 @@ int search_run(const SearchArgs& a) {
       default: e = launch_coarse_ts<80>(tb, s, tq, tp, sms, st); break;
     }
   } else {
-    if (int e2 = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e2;
     switch (pl.epl) {
       case 8: e = launch_coarse_ss<8>(ta, tb, s, tp, sms, st); break;
       case 16: e = launch_coarse_ss<16>(ta, tb, s, tp, sms, st); break;
       case 32: e = launch_coarse_ss<32>(ta, tb, s, tp, sms, st); break;
       default: e = launch_coarse_ss<80>(ta, tb, s, tp, sms, st); break;
     }
+  }
   }
   if (e) return e;
 
@@ -786,10 +796,14 @@ int search_run(const SearchArgs& a) {
   l1.cnt_sq = 1;
   l1.num_lists = pl.chunks;
   if (pl.groups == 1) {
+    KernelScope ks(kKcSelect, st);
     select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
     LDOT_CHECK_LAUNCH();
   } else {
-    select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr);
+    {
+      KernelScope ks(kKcSelect, st);
+      select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr);
+    }
     LDOT_CHECK_LAUNCH();
     SelLists l2;
     l2.ent = l2_ent;
@@ -799,7 +813,10 @@ int search_run(const SearchArgs& a) {
     l2.cnt_sc = 1;
     l2.cnt_sq = pl.groups;
     l2.num_lists = pl.groups;
-    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+    {
+      KernelScope ks(kKcSelect, st);
+      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+    }
     LDOT_CHECK_LAUNCH();
   }
 
@@ -821,7 +838,10 @@ int search_run(const SearchArgs& a) {
   rp.kprime = pl.kprime;
   rp.kp_pad = pl.kp_pad;
   const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
-  rescore_kernel<<<nq, 256, rs_smem, st>>>(rp);
+  {
+    KernelScope ks(kKcRescore, st, 2.0 * nq * pl.kprime * a.d, static_cast<double>(nq) * pl.kprime * a.d * 4.0);
+    rescore_kernel<<<nq, 256, rs_smem, st>>>(rp);
+  }
   LDOT_CHECK_LAUNCH();
   if (a.out_flag_count)
     LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -842,12 +862,19 @@ int index_prepare_run(const float* x, long long n, int d, int coarse_dtype, int 
   if (center) {
     int blocks = static_cast<int>(n < 4096 ? (n + 7) / 8 : 1184);
     if (blocks < 1) blocks = 1;
-    colsum_kernel<<<blocks, 256, 0, st>>>(x, n, d, acc);
+    {
+      KernelScope ks(kKcIndexPrep, st, 0.0, static_cast<double>(n) * d * 4.0);
+      colsum_kernel<<<blocks, 256, 0, st>>>(x, n, d, acc);
+    }
     LDOT_CHECK_LAUNCH();
   }
-  mean_finalize_kernel<<<(d + 255) / 256, 256, 0, st>>>(acc, n, d, center, mu);
+  {
+    KernelScope ks(kKcIndexPrep, st);
+    mean_finalize_kernel<<<(d + 255) / 256, 256, 0, st>>>(acc, n, d, center, mu);
+  }
   LDOT_CHECK_LAUNCH();
   const int blocks = static_cast<int>((n + 7) / 8);
+  KernelScope ks_conv(kKcIndexPrep, st, 0.0, static_cast<double>(n) * d * 6.0);
   if (coarse_dtype == 0)
     index_convert_kernel<__half><<<blocks, 256, 0, st>>>(x, mu, n, d, static_cast<__half*>(x16),
                                                          reinterpret_cast<unsigned int*>(xstats));
@@ -876,11 +903,17 @@ int exact_run(const float* q, long long nf, const float* x, long long n, int d, 
     const int nb = static_cast<int>(nf - f0 < kExactBatch ? nf - f0 : kExactBatch);
     long long blocks = (n + 7) / 8;
     if (blocks > sms * 8) blocks = sms * 8;
-    exact_scores_kernel<<<static_cast<int>(blocks), 256, static_cast<size_t>(nb) * d * sizeof(float), st>>>(
-        q + f0 * d, nb, x, n, d, scores);
+    {
+      KernelScope ks(kKcExactScan, st, 2.0 * nb * static_cast<double>(n) * d, static_cast<double>(n) * d * 4.0);
+      exact_scores_kernel<<<static_cast<int>(blocks), 256, static_cast<size_t>(nb) * d * sizeof(float), st>>>(
+          q + f0 * d, nb, x, n, d, scores);
+    }
     LDOT_CHECK_LAUNCH();
-    exact_select_kernel<<<nb, 1024, kp_pad * sizeof(unsigned long long), st>>>(
-        scores, n, k, kp_pad, id_offset, out_scores + f0 * k, out_idx + f0 * k);
+    {
+      KernelScope ks(kKcExactScan, st, 0.0, static_cast<double>(nb) * n * 4.0);
+      exact_select_kernel<<<nb, 1024, kp_pad * sizeof(unsigned long long), st>>>(
+          scores, n, k, kp_pad, id_offset, out_scores + f0 * k, out_idx + f0 * k);
+    }
     LDOT_CHECK_LAUNCH();
   }
   return kOk;
@@ -894,8 +927,11 @@ int merge_run(const float* scores, const long long* idx, int W, long long nq, in
   const size_t smem = static_cast<size_t>(pad) * sizeof(unsigned long long);
   LDOT_REQUIRE(smem <= 200 * 1024, "W*k=%d too large for the merge kernel", W * k);
   LDOT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  merge_kernel<<<static_cast<int>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      scores, idx, W, static_cast<int>(nq), k, pad, out_scores, out_idx);
+  {
+    KernelScope ks(kKcMerge, static_cast<cudaStream_t>(stream), 0.0, static_cast<double>(nq) * k * 12.0 * (W + 1));
+    merge_kernel<<<static_cast<int>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        scores, idx, W, static_cast<int>(nq), k, pad, out_scores, out_idx);
+  }
   LDOT_CHECK_LAUNCH();
   return kOk;
 }

@@ -293,12 +293,23 @@ class DenseFlatIndexer(DenseIndexer):
 
     def search_knn(self, query_vectors: np.array, top_docs: int) -> List[Tuple[List[object], List[float]]]:
         scores, indexes = self.index.search(query_vectors, top_docs)
+        return self._format_result(scores, indexes)
+
+    def _format_result(self, scores, indexes):
         # convert to external ids (a label of -1 - index shorter than top_docs - maps to the LAST id through
-        # Python's negative indexing, exactly like faiss_indexers.py:85)
-        id_map = self.index_id_to_db_id
-        db_ids = [[id_map[i] for i in query_top_idxs] for query_top_idxs in indexes.tolist()]
-        result = [(db_ids[i], scores[i]) for i in range(len(db_ids))]
-        return result
+        # negative indexing, exactly like faiss_indexers.py:85).  One vectorised gather over an object array
+        # instead of nq * k Python list look-ups.
+        id_map = self._id_array()
+        db_ids = id_map[indexes].tolist() if len(id_map) else [[] for _ in range(len(indexes))]
+        return [(db_ids[i], scores[i]) for i in range(len(db_ids))]
+
+    def _id_array(self):
+        cache = getattr(self, "_id_cache", None)
+        if cache is None or cache[0] != len(self.index_id_to_db_id):
+            arr = np.fromiter(self.index_id_to_db_id, dtype=object, count=len(self.index_id_to_db_id))
+            cache = (len(self.index_id_to_db_id), arr)
+            self._id_cache = cache
+        return cache[1]
 
 
 class DenseHNSWFlatIndexer(DenseIndexer):

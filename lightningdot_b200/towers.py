@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-SEQ_BATCH_TOKENS = 131072   # tokens per engine pass (bounds activation scratch to ~2.5 GB)
+SEQ_BATCH_TOKENS = 524288   # tokens per engine pass (bounds activation scratch to ~10 GB)
 
 
 def _fmt_of(dtype):

@@ -1,0 +1,96 @@
+"""Host-side mirror of the slice of dvl/utils.py the retrieval path uses.
+
+  _calc_loss        dvl/utils.py:114-169   in-batch-negative loss wrapper (world size 1 in the reference: its
+                                           cross-rank branch is dead code, :121; here the gather is live when a
+                                           torch.distributed group is initialised and args.distributed_world_size > 1)
+  retrieve_query    dvl/utils.py:204-211   free-text query -> txt tower -> search_knn(., 100)
+  is_main_process / get_rank / get_world_size   dvl/utils.py:18-23,187-188 (horovod there; env / torch.distributed here)
+  print_args, num_of_parameters, compare_models dvl/utils.py:26-38,172-184
+"""
+import logging
+import os
+
+import torch
+import torch.distributed as dist
+
+logger = logging.getLogger()
+
+
+def get_rank():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank()
+    return int(os.environ.get("RANK", "0"))
+
+
+def get_world_size():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def is_main_process():
+    return get_rank() == 0
+
+
+def print_args(args):
+    logger.info(" **************** CONFIGURATION **************** ")
+    for key, val in sorted(vars(args).items()):
+        logger.info("%s -->   %s", f"{key:<30}", val)
+    logger.info(" **************** CONFIGURATION **************** ")
+
+
+def num_of_parameters(model, requires_grad=False):
+    return sum(p.numel() for p in model.parameters() if p.requires_grad or not requires_grad)
+
+
+def compare_models(model_1, model_2):
+    differ = [k1 for (k1, v1), (k2, v2) in zip(model_1.state_dict().items(), model_2.state_dict().items())
+              if k1 != k2 or not torch.equal(v1, v2)]
+    for k in differ:
+        print('Mismtach found at', k)
+    if not differ:
+        print('Models match perfectly! :)')
+    return len(differ)
+
+
+def gather_embeddings(local, group=None):
+    """All-gather a [b, D] embedding block over the ranks (equal b on every rank) -> [W * b, D]; the local slice is
+    the caller's own tensor (dvl/utils.py:143-152: only local embeddings would carry grad)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.detach().contiguous(), group=group)
+    parts[rank] = local
+    return torch.cat(parts, dim=0)
+
+
+def _calc_loss(args, loss_function, local_q_vector, local_ctx_vectors, local_caption_vectors, local_positive_idxs,
+               local_hard_negatives_idxs: list = None, experiment=None):
+    """In-batch-negatives loss (dvl/utils.py:114-169).  With one process this is loss_function.calc on the local
+    batch; with a process group and args.distributed_world_size > 1 the embeddings of all ranks are gathered and
+    positives are shifted by the rank's context offset, which is what the reference's (disabled) branch sketches."""
+    world = int(getattr(args, "distributed_world_size", 1) or 1)
+    if world > 1 and dist.is_available() and dist.is_initialized():
+        rank = dist.get_rank()
+        n_ctx = local_ctx_vectors.shape[0]
+        q = local_q_vector
+        ctx = gather_embeddings(local_ctx_vectors)
+        cap = gather_embeddings(local_caption_vectors) if local_caption_vectors is not None else None
+        positives = [p + rank * n_ctx for p in local_positive_idxs]
+        hard = None if local_hard_negatives_idxs is None else \
+            [[v + rank * n_ctx for v in row] for row in local_hard_negatives_idxs]
+    else:
+        q, ctx, cap = local_q_vector, local_ctx_vectors, local_caption_vectors
+        positives, hard = local_positive_idxs, local_hard_negatives_idxs
+    return loss_function.calc(q, ctx, cap, positives, hard, getattr(args, "caption_score_weight", 0.0), experiment)
+
+
+def retrieve_query(model, query, indexer, args, top=10):
+    """dvl/utils.py:204-211 (the reference ignores `top` and always asks for 100; kept)."""
+    input_ids = torch.as_tensor(args.tokenizer.encode(query), dtype=torch.long, device=args.device).unsqueeze(0)
+    n = input_ids.shape[1]
+    attn_mask = torch.ones((1, n), dtype=torch.long, device=args.device)
+    pos_ids = torch.arange(n, dtype=torch.long, device=args.device).unsqueeze(0)
+    with torch.no_grad():
+        _, query_vector, _ = model.txt_model(input_ids=input_ids, attention_mask=attn_mask, position_ids=pos_ids)
+    return indexer.search_knn(query_vector, 100)

@@ -1,0 +1,201 @@
+"""GPU parity of the pieces around the two kernels families: in-batch NLL, the BiEncoder / eval-loop mirrors, the
+multi-shard merge, and the launch accounting - all through the C ABI, checked against the oracle and the fixtures
+minted from the reference."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lightningdot_b200 import _lib, sharded, synth, trainer
+from lightningdot_b200.bi_encoder import BertEncoder, BiEncoder, BiEncoderNllLoss, TowerConfig, UniterEncoder, \
+    dot_product_scores
+from lightningdot_b200.indexer import DenseFlatIndexer
+from lightningdot_b200.utils import _calc_loss
+from oracle import flatip, loss as oloss, towers as otowers
+
+from test_host_logic import StubEncoder, check_evalloop_against_golden, evalloop_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_inbatch_nll_matches_reference_fixture(cuda_lib, golden_dir):
+    """Tolerance: scores 2e-6 absolute (fp16 hi/lo split products, fp32 accumulation), loss 1e-5."""
+    gold = np.load(os.path.join(golden_dir, "loss_inbatch.npz"))
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(24, 768, generator=g) * 0.06
+    ctx = torch.randn(24, 768, generator=g) * 0.06 + q * 0.45
+    cap = torch.randn(24, 768, generator=g) * 0.06
+    pos = list(range(24))
+    with torch.no_grad():
+        l0, c0, s0 = _calc_loss(types.SimpleNamespace(caption_score_weight=0.0), BiEncoderNllLoss(), q.cuda(), ctx.cuda(),
+                                None, pos, None)
+        l1, c1, s1 = _calc_loss(types.SimpleNamespace(caption_score_weight=0.1), BiEncoderNllLoss(), q.cuda(), ctx.cuda(),
+                                cap.cuda(), pos, None)
+    assert abs(float(l0) - float(gold["loss0"])) < 1e-5 and int(c0) == int(gold["correct0"])
+    assert abs(float(l1) - float(gold["loss1"])) < 1e-5 and int(c1) == int(gold["correct1"])
+    np.testing.assert_allclose(s0.cpu().numpy(), gold["scores0"], atol=2e-6)
+    np.testing.assert_allclose(s1.cpu().numpy(), gold["scores1"], atol=2e-6)
+
+
+@pytest.mark.parametrize("bq,bc", [(1, 1), (7, 13), (96, 96), (300, 1000), (4096, 4096)])
+def test_inbatch_nll_vs_oracle_shapes(cuda_lib, bq, bc):
+    g = torch.Generator().manual_seed(bq * 31 + bc)
+    q = torch.randn(bq, 768, generator=g) * 0.2
+    ctx = torch.randn(bc, 768, generator=g) * 0.2
+    pos = torch.randint(0, bc, (bq,), generator=g).tolist()
+    with torch.no_grad():
+        for red in ("mean", "sum"):
+            l, c, s = BiEncoderNllLoss().calc(q.cuda(), ctx.cuda(), None, pos, reduction=red)
+            ol, oc, os_ = oloss.nll(q.double(), ctx.double(), pos, reduction=red)
+            assert abs(float(l) - float(ol)) <= 2e-5 * max(1.0, abs(float(ol)))
+            assert int(c) == int(oc)
+            assert torch.allclose(s.cpu().double(), os_, atol=5e-6)
+    # cosine flag of dot_product_scores (bi_encoder.py:63-67)
+    cs = dot_product_scores(q.cuda(), ctx.cuda(), cosine=True).cpu()
+    want = torch.nn.functional.normalize(q, dim=1) @ torch.nn.functional.normalize(ctx, dim=1).t()
+    assert torch.allclose(cs, want, atol=1e-5)
+
+
+def test_eval_loop_on_gpu_matches_reference_fixture(cuda_lib, golden_dir):
+    """dvl/trainer.py:113-190 through the CUDA indexer + CUDA loss: recalls, ranked ids, loss and accuracy equal the
+    fixture minted from the reference's own eval_model_on_dataloader."""
+    gold = json.load(open(os.path.join(golden_dir, "evalloop_small.json")))
+    txt, img, batches, img2txt = evalloop_inputs()
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    out = trainer.eval_model_on_dataloader(StubEncoder(txt, img, "cuda"), batches, args, img2txt, num_tops=100)
+    check_evalloop_against_golden(out, gold)
+    ix = trainer.get_indexer(StubEncoder(txt, img, "cuda"), batches, args, hnsw_index=False)
+    assert ix.index_id_to_db_id == [f"img_{i:07d}.npz" for i in range(200)]
+    assert np.array_equal(ix.index.vectors().cpu().numpy(), img[4::5])
+
+
+def _small_biencoder(layers=2):
+    args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(num_hidden_layers=layers),
+                                 img_checkpoint=None, txt_model_type='bert-base',
+                                 txt_model_config=TowerConfig(num_hidden_layers=layers), txt_checkpoint=None)
+    return BiEncoder(args, project_dim=768)
+
+
+def test_biencoder_forward_on_collate_batch(cuda_lib):
+    """BiEncoder.forward on the nested batch of itm_fast_collate (dvl/data/itm.py:203-288): txts / imgs / caps ->
+    three pooled [B, 768] tensors, against the fp32 oracle towers.  Tolerance: bf16 towers, cosine >= 0.999."""
+    model = _small_biencoder()
+    sd_t = synth.random_tower_state("txt", seed=11, perturb=True, layers=2)
+    sd_i = synth.random_tower_state("img", seed=12, perturb=True, layers=2)
+    model.txt_model.load_state_dict(sd_t, strict=True)
+    model.img_model.load_state_dict(sd_i, strict=True)
+    assert set(model.state_dict().keys()) == {"txt_model." + k for k in sd_t} | {"img_model." + k for k in sd_i}
+    model.cuda().eval()
+    tb, ib = synth.text_batch(9, 32, seed=1, ragged=True), synth.image_batch(9, 36, seed=2, ragged=True)
+    batch = {"txts": tb, "imgs": ib, "caps": synth.text_batch(9, 20, seed=3, ragged=True), "sample_size": 9}
+    with torch.no_grad():
+        t, i, c = model(batch)
+        _, ot = otowers.text_tower(sd_t, tb["input_ids"], tb["attention_mask"], tb["position_ids"])
+        _, oi = otowers.image_tower(sd_i, ib["input_ids"], ib["attention_mask"], ib["position_ids"], ib["img_feat"],
+                                    ib["img_pos_feat"], ib["gather_index"])
+        cb = batch["caps"]
+        _, oc = otowers.text_tower(sd_t, cb["input_ids"], cb["attention_mask"], cb["position_ids"])
+    for got, want in ((t, ot), (i, oi), (c, oc)):
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert torch.nn.functional.cosine_similarity(got.cpu(), want, dim=1).min() >= 0.999
+    # caps absent -> None, sequence outputs on request
+    with torch.no_grad():
+        t2, i2, c2 = model({"txts": tb, "imgs": ib, "caps": {"input_ids": None}})
+        seqs = model({"txts": tb, "imgs": ib}, output_all_encoded_layers=True)
+    assert c2 is None and torch.equal(t2, t) and torch.equal(i2, i)
+    assert seqs[0].shape == (9, 32, 768) and seqs[1].shape == (9, 37, 768) and seqs[2] is None
+
+
+def test_training_mode_forward_fails_loudly(cuda_lib):
+    model = _small_biencoder().cuda().train()
+    tb = synth.text_batch(2, 16, seed=1)
+    with pytest.raises(NotImplementedError):
+        model({"txts": tb})
+
+
+def test_towers_refuse_cpu():
+    enc = BertEncoder(TowerConfig(num_hidden_layers=1), project_dim=768).eval()
+    tb = synth.text_batch(2, 16, seed=1)
+    with torch.no_grad(), pytest.raises(_lib.LdotError):
+        enc(tb["input_ids"], tb["attention_mask"], tb["position_ids"])
+
+
+@pytest.mark.parametrize("world,nq,k", [(2, 33, 10), (8, 200, 100), (3, 5, 1000)])
+def test_topk_merge_kernel_vs_oracle(cuda_lib, world, nq, k):
+    """Shard lists built by the oracle from a row-split index; merged on the GPU; equal to the single-index result."""
+    n = 4000
+    x = synth.gaussian_index(n, 64, seed=31)
+    x[2500] = x[17]      # cross-shard duplicate
+    q, _ = synth.planted_queries(x, nq, sigma=2.0, seed=32)
+    b = sharded.shard_bounds(n, world)
+    gs = np.empty((world, nq, k), np.float32)
+    gi = np.empty((world, nq, k), np.int64)
+    for r in range(world):
+        s, i = flatip.search(q, x[b[r]:b[r + 1]], k)
+        gs[r], gi[r] = s, np.where(i >= 0, i + b[r], -1)
+    lib = cuda_lib
+    ds, di = torch.from_numpy(gs).cuda(), torch.from_numpy(gi).cuda()
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    _lib.check(lib.ldot_topk_merge(_lib.ptr(ds), _lib.ptr(di), world, nq, k, _lib.ptr(out_s), _lib.ptr(out_i),
+                                   _lib.stream_ptr()))
+    os_, oi = flatip.search(q, x, k)
+    assert np.array_equal(out_i.cpu().numpy(), oi) and np.array_equal(out_s.cpu().numpy(), os_)
+
+
+def test_sharded_indexer_single_rank_and_offsets(cuda_lib):
+    """world = 1 path of ShardedFlatIndexer, and a hand-made 3-shard search (row_offset + merge) in one process."""
+    n, k = 9000, 50
+    x = synth.gaussian_index(n, 768, seed=41)
+    q, _ = synth.planted_queries(x, 70, sigma=2.0, seed=42)
+    ids = [f"d{i}" for i in range(n)]
+    ix = sharded.ShardedFlatIndexer(768)
+    ix.index_matrix(ids, x)
+    res = ix.search_knn(q, k)
+    os_, oi = flatip.search(q, x, k)
+    assert [r[0] for r in res] == [[ids[j] for j in row] for row in oi]
+    b = sharded.shard_bounds(n, 3)
+    qd = torch.from_numpy(q).cuda()
+    gs, gi = [], []
+    for r in range(3):
+        shard = sharded.FlatIPIndex(768, row_offset=b[r])
+        shard.add(x[b[r]:b[r + 1]])
+        s, i = shard.search_device(qd, k)
+        gs.append(s)
+        gi.append(i)
+    ms, mi = ix._merge(torch.stack(gs), torch.stack(gi), k)
+    assert np.array_equal(mi.cpu().numpy(), oi) and np.array_equal(ms.cpu().numpy(), os_)
+
+
+def test_search_knn_accepts_device_tensors_and_remaps_ids(cuda_lib):
+    x = synth.gaussian_index(50, 768, seed=51)
+    ids = [("tuple", i) for i in range(50)]           # arbitrary hashable ids, as the reference allows
+    ix = DenseFlatIndexer(768)
+    ix.index_data(list(zip(ids, x)))
+    a = ix.search_knn(x[:4], 60)                      # k > ntotal: label -1 maps to the LAST id (faiss_indexers.py:85)
+    b = ix.search_knn(torch.from_numpy(x[:4]).cuda(), 60)
+    assert [r[0] for r in a] == [r[0] for r in b]
+    assert a[0][0][0] == ("tuple", 0) and a[0][0][50:] == [("tuple", 49)] * 10
+
+
+def test_launch_accounting(cuda_lib):
+    x = synth.gaussian_index(20000, 768, seed=61)
+    q, _ = synth.planted_queries(x, 256, sigma=2.0, seed=62)
+    ix = DenseFlatIndexer(768)
+    ix.index_matrix(list(range(20000)), x)
+    qd = torch.from_numpy(q).cuda()
+    ix.index.search_device(qd, 100)
+    torch.cuda.synchronize()
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    for _ in range(3):
+        ix.index.search_device(qd, 100)
+    _lib.prof_enable(False)
+    p = _lib.prof_read()
+    c = p["coarse_score_topk"]
+    assert c["launches"] == 3 and c["timed"] == 3 and c["ms"] > 0
+    assert c["flops"] == 3 * 2.0 * 256 * 20000 * 768
+    assert p["rescore"]["launches"] == 3 and p["select"]["launches"] >= 3 and p["linear_tcgen05"]["launches"] == 0

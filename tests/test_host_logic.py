@@ -1,0 +1,234 @@
+"""Host-side logic that needs no GPU: the eval loop mirror (dvl/trainer.py:113-190) against the fixture minted from
+the reference, shard arithmetic, and the row-sharded search protocol over a 2-rank gloo group (device kernels
+replaced by the oracle so that the exchange / offset / merge plumbing is what is tested)."""
+import json
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lightningdot_b200 import sharded, synth, trainer
+from oracle import flatip, loss as oloss
+
+
+class OracleIndexer:
+    """CPU stand-in with the DenseFlatIndexer surface the eval loop touches."""
+
+    def __init__(self, vector_sz, **kw):
+        self.inner = flatip.FlatIndexer(vector_sz)
+        self.index_id_to_db_id = self.inner.index_id_to_db_id
+
+    def index_matrix(self, ids, vectors):
+        self.inner.index_data(list(zip(ids, vectors.cpu().numpy())))
+
+    def search_knn(self, q, k):
+        return self.inner.search_knn(q.cpu().numpy() if isinstance(q, torch.Tensor) else q, k)
+
+
+class OracleLoss:
+    def calc(self, q, ctx, cap, pos, hard=None, caption_score_weight=0.1, experiment=None, reduction='mean'):
+        return oloss.nll(q, ctx, pos, cap, caption_score_weight, reduction)
+
+
+def evalloop_inputs():
+    n_img, cap_per_img, bs = 200, 5, 16
+    x = synth.gaussian_index(n_img, 768, seed=11)
+    n_cap = n_img * cap_per_img
+    rng = np.random.default_rng(12)
+    txt = (x[np.arange(n_cap) // cap_per_img] + 12.0 * rng.standard_normal((n_cap, 768), dtype=np.float32) / np.sqrt(768)).astype(np.float32)
+    img = (x[np.arange(n_cap) // cap_per_img] + 1e-6 * rng.standard_normal((n_cap, 768), dtype=np.float32)).astype(np.float32)
+    txt_ids = [str(j) for j in range(n_cap)]
+    img_ids = [f"img_{j // cap_per_img:07d}.npz" for j in range(n_cap)]
+    img2txt = {f"img_{i:07d}.npz": [str(i * cap_per_img + c) for c in range(cap_per_img)] for i in range(n_img)}
+    batches = []
+    for b in range(0, n_cap, bs):
+        sl = slice(b, min(n_cap, b + bs))
+        batches.append({"txts": {"input_ids": torch.zeros(sl.stop - sl.start, 4, dtype=torch.long)},
+                        "txt_index": txt_ids[sl], "img_fname": img_ids[sl], "_slice": sl})
+    return txt, img, batches, img2txt
+
+
+class StubEncoder:
+    def __init__(self, txt, img, device="cpu"):
+        self.txt, self.img, self.device = txt, img, device
+
+    def eval(self):
+        return self
+
+    def __call__(self, batch):
+        sl = batch["_slice"]
+        return (torch.from_numpy(self.txt[sl]).to(self.device), torch.from_numpy(self.img[sl]).to(self.device), None)
+
+
+def check_evalloop_against_golden(out, gold):
+    loss, acc, (ix_img, ix_txt), (recall_txt, recall_img), (rank_txt, rank_img) = out
+    assert {str(k): v for k, v in recall_txt.items()} == gold["recall_txt"]
+    assert {str(k): v for k, v in recall_img.items()} == gold["recall_img"]
+    assert abs(loss - gold["loss"]) < 1e-4 and abs(acc - gold["acc"]) < 1e-9
+    for k, v in gold["rank_txt_top10"].items():
+        assert list(rank_txt[k][:10]) == v
+    for k, v in gold["rank_img_top10"].items():
+        assert list(rank_img[k][:10]) == v
+    assert len(ix_img.index_id_to_db_id) == 200 and len(ix_txt.index_id_to_db_id) == 1000
+
+
+def test_eval_loop_mirror_matches_reference_fixture(golden_dir, monkeypatch):
+    gold = json.load(open(os.path.join(golden_dir, "evalloop_small.json")))
+    txt, img, batches, img2txt = evalloop_inputs()
+    monkeypatch.setattr(trainer, "DenseFlatIndexer", OracleIndexer)
+    monkeypatch.setattr(trainer, "BiEncoderNllLoss", OracleLoss)
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    out = trainer.eval_model_on_dataloader(StubEncoder(txt, img), batches, args, img2txt, num_tops=100)
+    check_evalloop_against_golden(out, gold)
+    # no_eval: indexes only
+    out2 = trainer.eval_model_on_dataloader(StubEncoder(txt, img), batches, args, img2txt, no_eval=True)
+    assert out2[3] == (None, None) and out2[4] == (None, None)
+
+
+def test_get_indexer_keeps_last_encoding_in_first_seen_order(monkeypatch):
+    txt, img, batches, _ = evalloop_inputs()
+    monkeypatch.setattr(trainer, "DenseFlatIndexer", OracleIndexer)
+    args = types.SimpleNamespace(vector_size=768)
+    ix = trainer.get_indexer(StubEncoder(txt, img), batches, args, hnsw_index=False, img_retrieval=True)
+    assert ix.index_id_to_db_id == [f"img_{i:07d}.npz" for i in range(200)]
+    # image i was encoded by captions 5i .. 5i+4: the LAST one (row 5i + 4) is what the index holds (trainer.py:151)
+    assert np.array_equal(ix.inner.xb, img[4::5])
+
+
+def test_checkpoint_state_roundtrip(tmp_path):
+    model = torch.nn.Linear(4, 3)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    args = types.SimpleNamespace(output_dir=str(tmp_path))
+    cp = trainer._save_checkpoint(args, model, opt, sched, epoch=3, offset=0, cp_name="best")
+    assert cp.endswith("biencoder.best.pt")
+    assert trainer._save_checkpoint(args, model, opt, sched, epoch=3, offset=7).endswith("biencoder.3.7.pt")
+    st = trainer.load_states_from_checkpoint(cp)
+    assert set(st._fields) == {'model_dict', 'optimizer_dict', 'scheduler_dict', 'offset', 'epoch', 'encoder_params'}
+    model2 = torch.nn.Linear(4, 3)
+    trainer.load_saved_state(model2, saved_state=st)
+    assert all(torch.equal(a, b) for a, b in zip(model.state_dict().values(), model2.state_dict().values()))
+
+
+def test_shard_bounds():
+    assert sharded.shard_bounds(1_000_000, 8) == [i * 125000 for i in range(9)]
+    assert sharded.shard_bounds(10, 4) == [0, 3, 6, 8, 10]
+    assert sharded.shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    b = sharded.shard_bounds(123287, 8)
+    assert b[0] == 0 and b[-1] == 123287 and max(np.diff(b)) - min(np.diff(b)) <= 1
+
+
+class _OracleLocalIndex:
+    """FlatIPIndex stand-in on CPU tensors (row_offset semantics included)."""
+
+    def __init__(self, d, row_offset=0, **kw):
+        self.d, self.row_offset, self.x = d, row_offset, np.zeros((0, d), np.float32)
+        self.last_flagged = 0
+
+    @property
+    def ntotal(self):
+        return len(self.x)
+
+    def add(self, v):
+        v = v.numpy() if isinstance(v, torch.Tensor) else v
+        self.x = np.concatenate([self.x, np.asarray(v, np.float32)], 0)
+
+    def search_device(self, q, k):
+        s, i = flatip.search(q.numpy(), self.x, k)
+        i = np.where(i >= 0, i + self.row_offset, -1)
+        return torch.from_numpy(s), torch.from_numpy(i)
+
+    def _device(self):
+        return torch.device("cpu")
+
+
+class _CpuSharded(sharded.ShardedFlatIndexer):
+    def _make_local_index(self, row_offset):
+        return _OracleLocalIndex(self.vector_sz, row_offset=row_offset)
+
+    def _merge(self, gs, gi, k):
+        # (score desc, id asc) over the W * k gathered candidates of every query - what ldot_topk_merge does
+        world, nq, _ = gs.shape
+        s = gs.permute(1, 0, 2).reshape(nq, world * k).numpy()
+        i = gi.permute(1, 0, 2).reshape(nq, world * k).numpy()
+        out_s = np.full((nq, k), np.float32(-3.4028235e38), np.float32)
+        out_i = np.full((nq, k), -1, np.int64)
+        for r in range(nq):
+            valid = np.nonzero(i[r] >= 0)[0]
+            order = valid[np.lexsort((i[r, valid], -s[r, valid].astype(np.float64)))][:k]
+            out_s[r, :len(order)] = s[r, order]
+            out_i[r, :len(order)] = i[r, order]
+        return torch.from_numpy(out_s), torch.from_numpy(out_i)
+
+
+def _sharded_worker(rank, world, port, n, nq, k, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x = synth.gaussian_index(n, 64, seed=21)
+        if n > 16:
+            x[n // 2 + 3] = x[5]        # a cross-shard exact duplicate: tie broken by the global row id
+        q, _ = synth.planted_queries(x, nq, sigma=2.0, seed=22)
+        ids = [f"doc{i}" for i in range(n)]
+        ix = _CpuSharded(64)
+        ix.index_matrix(ids, x)
+        assert ix.index.ntotal == ix.bounds[rank + 1] - ix.bounds[rank] and ix.index.row_offset == ix.bounds[rank]
+        # queries arrive sharded (each rank "encoded" its slice) and are gathered in rank order
+        qb = sharded.shard_bounds(nq, world)
+        q_all = ix.gather_queries(torch.from_numpy(q[qb[rank]:qb[rank + 1]]))
+        assert np.array_equal(q_all.numpy(), q)
+        res = ix.search_knn(q_all, k)
+        os_, oi = flatip.search(q, x, k)
+        want = [[ids[j] if j >= 0 else ids[-1] for j in row] for row in oi]
+        assert [r[0] for r in res] == want
+        assert np.array_equal(np.stack([r[1] for r in res]), os_)
+        # already-partitioned build path
+        ix2 = _CpuSharded(64)
+        ix2.index_shard(ids, x[ix.bounds[rank]:ix.bounds[rank + 1]], ix.bounds)
+        s2, i2 = ix2.search_device(q_all, k)
+        assert np.array_equal(i2.numpy(), oi) and np.array_equal(s2.numpy(), os_)
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,nq,k", [(1001, 37, 10), (3, 5, 4)])
+def test_sharded_search_protocol_two_ranks_gloo(tmp_path, n, nq, k):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_worker, args=(2, port, n, nq, k, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def _loss_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lightningdot_b200 import utils
+        g = torch.Generator().manual_seed(5)
+        q = torch.randn(16, 32, generator=g)
+        ctx = torch.randn(16, 32, generator=g) + q
+        lo, hi = rank * 8, rank * 8 + 8
+        args = types.SimpleNamespace(distributed_world_size=world, caption_score_weight=0.0)
+        loss, correct, scores = utils._calc_loss(args, OracleLoss(), q[lo:hi], ctx[lo:hi], None, list(range(8)), None)
+        # the global-batch loss restricted to this rank's query rows
+        want_l, want_c, want_s = oloss.nll(q[lo:hi], ctx, list(range(lo, hi)))
+        assert torch.allclose(loss, want_l) and int(correct) == int(want_c) and torch.allclose(scores, want_s)
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_inbatch_loss_global_negatives_two_ranks_gloo(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_loss_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
