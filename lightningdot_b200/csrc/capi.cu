@@ -49,6 +49,26 @@ int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint
   return kOk;
 }
 
+int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(kErrCuda, "cuTensorMapEncodeTiled entry point not available");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride_bytes % 16 == 0,
+               "TMA store target must be 16-byte aligned with a 16-byte multiple row pitch");
+  const uint32_t inner = box_cols * elt_bytes;
+  LDOT_REQUIRE((elt_bytes == 2 || elt_bytes == 4) && (inner == 64 || inner == 128), "unsupported TMA store box");
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {row_stride_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = fn(out, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+                        const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(kErrCuda, "cuTensorMapEncodeTiled (store) failed with CUresult %d", (int)r);
+  return kOk;
+}
+
 // ---------------------------------------------------------------------------------------------- launch accounting
 namespace {
 struct ProfRecord {

@@ -90,7 +90,7 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
             ptx::mbar_arrive_expect_tx(&full[stage], nkb * TsSmem::kKbBytes);
             for (int j = 0; j < nkb; ++j)
               ptx::tma_load_2d(smem + stage * TsSmem::kStageBytes + j * TsSmem::kKbBytes, &tmap_b, &full[stage],
-                               (kb0 + j) * kBK, nt * kTsBN, ptx::kEvictNormal);
+                               (kb0 + j) * kBK, nt * sched.tile_stride * kTsBN, ptx::kEvictNormal);
             if (++stage == kTsStages) {
               stage = 0;
               phase ^= 1;
@@ -179,7 +179,7 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
       for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
         ptx::mbar_wait(&tfull[as], aphase);
         ptx::tc_fence_after();
-        Epi::tile(st, ep, u, row, nt, lane_base + kTsACols + static_cast<uint32_t>(as * kTsBN));
+        Epi::tile(st, ep, u, row, nt * sched.tile_stride, lane_base + kTsACols + static_cast<uint32_t>(as * kTsBN));
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty[as]);
         as ^= 1;

@@ -44,6 +44,7 @@ struct GemmSched {
   int chunks;          // ceil(n_tiles / tiles_per_unit)
   int num_units;       // m_tiles * chunks
   int k_blocks;        // ceil(K / 64)
+  int tile_stride;     // N tile t of the schedule is tile t * tile_stride of B (> 1: strided sample of the index)
   uint32_t idesc;      // tcgen05 instruction descriptor (dtype, M=128, N=BN)
 };
 
@@ -132,8 +133,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
             ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, u.m_tile * kBM,
                              ptx::kEvictLast);
-            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_b, &full[stage], kb * kBK, nt * BN,
-                             ptx::kEvictNormal);
+            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_b, &full[stage], kb * kBK,
+                             nt * sched.tile_stride * BN, ptx::kEvictNormal);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -193,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
         ptx::mbar_wait(&tfull[as], aphase);
         ptx::tc_fence_after();
-        Epi::tile(st, ep, u, row, nt, lane_base + static_cast<uint32_t>(as * BN));
+        Epi::tile(st, ep, u, row, nt * sched.tile_stride, lane_base + static_cast<uint32_t>(as * BN));
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tempty[as]);
         as ^= 1;

@@ -48,6 +48,11 @@ inline int set_error(int code, const char* fmt, ...) {
 int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t row_stride_bytes, uint32_t box_rows);
 
+// 2-D tensor map of a row-major [rows, cols] matrix of `elt_bytes`-wide elements for TMA stores of
+// [box_rows, box_cols] boxes whose inner extent (box_cols * elt_bytes) is 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B).
+int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows);
+
 int device_sm_count(int* out);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

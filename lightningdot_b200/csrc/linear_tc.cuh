@@ -1,0 +1,312 @@
+// Encoder Linear on tcgen05:  out[M, N] = act(A[M, K] . W[N, K]^T + bias) (+ residual)
+//
+// Persistent, warp-specialised, one CTA per SM, 320 threads:
+//   warp 0      TMA producer: A (activations) 128 x 64 and W 256 x 64 K-major boxes, SWIZZLE_128B, 4-stage ring
+//   warp 1      TMEM owner + tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accumulate, 2 accumulators)
+//   warps 2..9  epilogue: warp w reads TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the 128 x 256 tile in
+//               32-column chunks.  Per chunk: tcgen05.ld (async) | bias + residual prefetch | wait | bias, erf-GELU,
+//               residual in registers | swizzled st.shared into the warp's staging buffer | one TMA store
+//               (cp.async.bulk.tensor) of the 32 x 32 box.  Stores are coalesced by the TMA unit and clipped at the
+//               M / N edges of the output, so there is no tail handling on the store side.
+// Tiles are visited n-fastest (tile t = m_tile * n_tiles + n_tile): CTAs that run at the same time share the A row
+// block (the big operand - activations) through L2 while the weights stay L2-resident anyway.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "gemm_tc.cuh"
+
+namespace ldot {
+
+constexpr int kLinBN = 256;
+constexpr int kLinStages = 4;
+constexpr int kLinEpiWarps = 8;
+constexpr int kLinThreads = 32 * (2 + kLinEpiWarps);
+
+struct LinSched {
+  int m_tiles, n_tiles, num_tiles, k_blocks;
+  uint32_t idesc;
+};
+
+struct LinParams {
+  const float* bias;      // [N] or null
+  const void* residual;   // [M, ldr] 16-bit of `fmt`, or null
+  long long ldr;
+  long long M;
+  int N;
+  int fmt;                // 0 = fp16, 1 = bf16 (A, W, residual, 16-bit output)
+};
+
+struct LinSmem {
+  static constexpr int kABytes = kBM * kBK * 2;        // 16 KB
+  static constexpr int kBBytes = kLinBN * kBK * 2;     // 32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingPerWarp = 4096;         // one 32 x 32 fp32 box, or two 32 x 32 16-bit boxes
+  static constexpr int kStagingOffset = kLinStages * kStageBytes;
+  static constexpr int kBarOffset = kStagingOffset + kLinEpiWarps * kStagingPerWarp;
+  static constexpr int kTotal = kBarOffset + (2 * kLinStages + 4) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;       // slack for manual 1024 B alignment
+};
+static_assert(LinSmem::kDynamic <= 227 * 1024, "linear kernel shared memory");
+
+// erf with |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26): far below the 16-bit output resolution, and a third
+// of the instructions of erff() - the FFN-up epilogue is ALU-paced.
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
+  if (fmt == 1) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
+  if (fmt == 1) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+template <int ACT, int OUT_F32>
+__global__ void __launch_bounds__(kLinThreads, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
+  using SM = LinSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kLinStages * SM::kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
+  uint64_t* empty = full + kLinStages;
+  uint64_t* tfull = empty + kLinStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLinStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], kLinEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
+        const int m_tile = t / sched.n_tiles, n_tile = t - m_tile * sched.n_tiles;
+        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
+          ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
+                           ptx::kEvictNormal);
+          ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, n_tile * kLinBN,
+                           ptx::kEvictLast);
+          if (++stage == kLinStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
+        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * SM::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == kLinStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::mma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    uint8_t* staging = smem + SM::kStagingOffset + (warp - 2) * SM::kStagingPerWarp;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t nstore = 0;
+    for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
+      const int m_tile = t / sched.n_tiles, n_tile = t - m_tile * sched.n_tiles;
+      const long long grow = static_cast<long long>(m_tile) * kBM + row;
+      const bool row_ok = grow < p.M;
+      const int col_base = n_tile * kLinBN + half * (kLinBN / 2);
+      // chunks of this warp that hold valid columns (uniform across the warp)
+      int nchunks = (p.N - col_base + 31) / 32;
+      nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
+      if (nchunks == 0) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      }
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int col = col_base + cc * 32;
+        const bool full_chunk = col + 32 <= p.N;
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + cc * 32, v);
+        // operands of the elementwise tail are fetched while the TMEM load is in flight
+        float4 b4[8];
+        if (p.bias != nullptr && full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+        }
+        uint4 r4[4];
+        const bool res_vec = p.residual != nullptr && row_ok && full_chunk;
+        if (res_vec) {
+          const uint4* r = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r4[j] = __ldg(r + j);
+        }
+        ptx::tmem_ld_wait();
+        if (cc == nchunks - 1) {  // accumulator drained: hand it back to the MMA warp before the math
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        }
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[4 * j] += b4[j].x;
+              f[4 * j + 1] += b4[j].y;
+              f[4 * j + 2] += b4[j].z;
+              f[4 * j + 3] += b4[j].w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) f[j] += __ldg(p.bias + col + j);
+          }
+        }
+        if (ACT == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+        }
+        if (p.residual != nullptr && row_ok) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 x = unpack2(w[q], p.fmt);
+                f[j4 * 8 + q * 2] += x.x;
+                f[j4 * 8 + q * 2 + 1] += x.y;
+              }
+            }
+          } else {
+            const uint16_t* r16 = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j < p.N) f[j] += unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
+          }
+        }
+        // stage the 32 x 32 box (swizzled exactly as the output tensor map expects) and hand it to the TMA unit
+        uint8_t* buf = OUT_F32 ? staging : staging + (nstore & 1u) * (SM::kStagingPerWarp / 2);
+        if (lane == 0) {
+          if (OUT_F32) ptx::bulk_wait_group_read<0>();
+          else ptx::bulk_wait_group_read<1>();
+        }
+        __syncwarp();
+        if (OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 w;
+            w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
+            w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
+            w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
+            w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
+            *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
+          ptx::bulk_commit_group();
+        }
+        ++nstore;
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<0>();  // the staging buffers must outlive the TMA reads
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ldot

@@ -193,7 +193,7 @@ struct SelLists {
 __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const unsigned int* __restrict__ gtau, int kprime,
                                                      int final, unsigned long long* __restrict__ out_ent,
                                                      int* __restrict__ out_cnt, int* __restrict__ sel_idx,
-                                                     float* __restrict__ sel_cmin) {
+                                                     float* __restrict__ sel_cmin, unsigned int* __restrict__ tau_out) {
   extern __shared__ unsigned long long sel_smem[];
   unsigned long long* stage = sel_smem;  // [kSelStage]
   __shared__ int cnts[kSelGroup];
@@ -221,8 +221,9 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
   };
 
   if (L < kprime) {
-    // Fewer than k' entries: everything survives.  (At the final level this also means that no list was ever
-    // compacted anywhere - a compaction leaves k' entries behind - so no row of the index was dropped: c_min = -inf.)
+    // Fewer than k' entries: everything survives.  Rows that are in no list were dropped by a threshold, and every
+    // threshold ever applied to this query is <= the final gtau[q] (atomicMax), so c_min = gtau[q]; gtau[q] == 0 means
+    // that nothing was ever dropped (no compaction happened anywhere, no sampled threshold): c_min = -inf.
     for (int c = warp; c < nl; c += 8) {
       const unsigned long long* src = list_of(c);
       for (int i = lane; i < cnts[c]; i += 32) emit(atomicAdd(&out_pos, 1), __ldcg(src + i));
@@ -230,7 +231,11 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
     if (final) {
       __syncthreads();
       for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
-      if (threadIdx.x == 0) sel_cmin[q] = -INFINITY;
+      if (threadIdx.x == 0) {
+        const uint32_t g = gtau[q];
+        sel_cmin[q] = g > kKeyNegInf ? fkey_inv(g) : -INFINITY;
+        if (tau_out) tau_out[q] = 0u;  // sample too small to bound anything
+      }
     } else if (threadIdx.x == 0) {
       out_cnt[q * groups + g] = L;
     }
@@ -268,7 +273,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
     if (!final && threadIdx.x == 0) out_cnt[q * groups + g] = ns;
     if (final) {  // cannot happen (the union holds the list that set gtau); keep the output well-formed anyway
       for (int i = ns + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
-      if (threadIdx.x == 0) sel_cmin[q] = fkey_inv(floor_key);
+      if (threadIdx.x == 0) {
+        sel_cmin[q] = fkey_inv(floor_key);
+        if (tau_out) tau_out[q] = 0u;
+      }
     }
     return;
   }
@@ -293,8 +301,12 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
     }
   });
   if (threadIdx.x == 0) {
-    if (final) sel_cmin[q] = fkey_inv(T);
-    else out_cnt[q * groups + g] = kprime;
+    if (final) {
+      sel_cmin[q] = fkey_inv(T);
+      if (tau_out) tau_out[q] = T;
+    } else {
+      out_cnt[q * groups + g] = kprime;
+    }
   }
 }
 
@@ -402,8 +414,9 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
         const double sk = static_cast<double>(rank_key_score(kk));
         const double nq16 = p.qstats[2 * q], rq = p.qstats[2 * q + 1];
         const double rmax = p.xstats[0], xmax = p.xstats[1];
-        // rounding of x, rounding of q, cross term, tensor-core fp32 accumulation (d terms, <= 2^-22 relative each)
-        const double E = nq16 * rmax + rq * (xmax + rmax) + 2.0 * p.d * 2.384185791015625e-07 * nq16 * xmax;
+        // rounding of x, rounding of q (+ cross term), tensor-core fp32 accumulation: d additions, each within
+        // 2^-22 of the running sum of |products| <= |q16| |x16| (twice the bound of a truncating fp32 adder)
+        const double E = nq16 * rmax + rq * (xmax + rmax) + p.d * 2.384185791015625e-07 * nq16 * xmax;
         const double slack = 1.1920928955078125e-07 * (fabs(sk) + fabs(p.qmu[q])) + 1e-30;
         certified = (sk - p.qmu[q] - slack) > (static_cast<double>(cmin) + E * 1.0001);
       }
@@ -542,25 +555,54 @@ __global__ void __launch_bounds__(256) exact_scores_kernel(const float* __restri
   }
 }
 
-// one block per query: exact top-k by (score desc, id asc) over all n scores
-__global__ void __launch_bounds__(1024) exact_select_kernel(const float* __restrict__ scores, long long n, int k, int kp_pad,
-                                                            long long id_offset, float* __restrict__ out_scores,
-                                                            long long* __restrict__ out_idx) {
+// Level 1 of the exact selection: grid (chunks, queries); the block ranks one chunk of a query's score row in shared
+// memory and emits its k best (rank keys: score desc, row id asc; keys are distinct) to out_keys[f][chunk][0..k),
+// zero padded.
+constexpr int kExactChunk = 6144;  // scores per block: 48 KB of 64-bit rank keys
+
+__global__ void __launch_bounds__(256) exact_chunk_topk_kernel(const float* __restrict__ scores, long long n, int k,
+                                                               unsigned long long* __restrict__ out_keys) {
+  extern __shared__ unsigned long long ec_keys[];  // [kExactChunk]
+  __shared__ int scratch[33];
+  __shared__ int out_pos;
+  const int f = blockIdx.y, c = blockIdx.x, chunks = gridDim.x;
+  const long long off = static_cast<long long>(c) * kExactChunk;
+  const int len = static_cast<int>(n - off < kExactChunk ? n - off : kExactChunk);
+  const float* s = scores + static_cast<size_t>(f) * n + off;
+  unsigned long long* out = out_keys + (static_cast<size_t>(f) * chunks + c) * k;
+  if (threadIdx.x == 0) out_pos = 0;
+  for (int i = threadIdx.x; i < len; i += blockDim.x) ec_keys[i] = rank_key(__ldcg(s + i), static_cast<uint32_t>(off + i));
+  __syncthreads();
+  if (len <= k) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = i < len ? ec_keys[i] : 0ull;
+    return;
+  }
+  auto get = [&](int i) { return ec_keys[i]; };
+  const unsigned long long T = block_kth_largest_u64(get, len, k, scratch);
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    const unsigned long long e = ec_keys[i];
+    if (e >= T) out[atomicAdd(&out_pos, 1)] = e;   // exactly k entries: keys are distinct
+  }
+}
+
+// Level 2: one block per query over the m = chunks * k level-1 keys -> the final ranked top-k.
+__global__ void __launch_bounds__(1024) exact_merge_kernel(const unsigned long long* __restrict__ keys, int m, long long n,
+                                                           int k, int kp_pad, long long id_offset,
+                                                           float* __restrict__ out_scores, long long* __restrict__ out_idx) {
   extern __shared__ unsigned long long es_keys[];  // [kp_pad]
   __shared__ int scratch[33];
   __shared__ int out_pos;
   const int f = blockIdx.x;
-  const float* s = scores + static_cast<size_t>(f) * n;
-  const int nn = static_cast<int>(n);
-  const int kk = k < nn ? k : nn;
+  const unsigned long long* src = keys + static_cast<size_t>(f) * m;
+  const int kk = static_cast<long long>(k) < n ? k : static_cast<int>(n);
   if (threadIdx.x == 0) out_pos = 0;
   for (int i = threadIdx.x; i < kp_pad; i += blockDim.x) es_keys[i] = 0ull;
   __syncthreads();
-  auto get = [&](int i) { return rank_key(__ldcg(s + i), static_cast<uint32_t>(i)); };
-  const unsigned long long T = block_kth_largest_u64(get, nn, kk, scratch);
-  for (int i = threadIdx.x; i < nn; i += blockDim.x) {
+  auto get = [&](int i) { return __ldcg(src + i); };
+  const unsigned long long T = block_kth_largest_u64(get, m, kk, scratch);
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
     const unsigned long long e = get(i);
-    if (e >= T) es_keys[atomicAdd(&out_pos, 1)] = e;
+    if (e >= T && e != 0ull) es_keys[atomicAdd(&out_pos, 1)] = e;
   }
   __syncthreads();
   block_bitonic_desc(es_keys, kp_pad);
@@ -615,12 +657,13 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   LDOT_REQUIRE(n >= 1 && n <= 2000000000ll, "n=%lld out of range", n);
   LDOT_REQUIRE(d >= 8 && d <= 4096 && d % 8 == 0, "d=%d must be a multiple of 8 in [8, 4096]", d);
   LDOT_REQUIRE(k >= 1 && k <= 1024, "k=%d out of range [1, 1024]", k);
-  int kp = coarse_k > 0 ? coarse_k : k + (k / 4 > 28 ? k / 4 : 28);
+  int kp = coarse_k > 0 ? coarse_k : k + (k / 2 > 32 ? k / 2 : 32);
   if (kp < 64) kp = 64;
   kp = (kp + 31) / 32 * 32;
   LDOT_REQUIRE(kp >= k && kp <= 1280, "coarse_k=%d must be in [k, 1280]", kp);
   pl->kprime = kp;
-  pl->epl = kp <= 128 ? 8 : kp <= 256 ? 16 : kp <= 512 ? 32 : 80;
+  // list capacity cap = epl * 32 >= k' + 32 (a list is compacted to its k' best when fewer than 32 slots are left)
+  pl->epl = kp <= 192 ? 8 : kp <= 448 ? 16 : kp <= 960 ? 32 : 80;
   pl->cap = pl->epl * 32;
   pl->kp_pad = next_pow2(kp);
   // queries parked in TMEM (A-stationary kernel) whenever the vector fits 384 TMEM columns
@@ -655,6 +698,29 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->num_units = pl->m_tiles * pl->chunks;
   pl->groups = (pl->chunks + kSelGroup - 1) / kSelGroup;  // > 1: two-level select
   LDOT_REQUIRE(pl->groups <= kSelGroup, "index too large for one search call (chunks=%d)", pl->chunks);
+  // Threshold pre-pass.  Every s_stride-th index tile is scored first and the s_kprime-th best sample score of a
+  // query becomes its initial threshold.  With sample fraction f = 1 / s_stride the threshold cuts the full index
+  // down to ~ s_kprime * s_stride rows per query (>= 3 k'), and it is too high - fewer than k' rows above it, which
+  // the select stage detects and flags - only if >= s_kprime of the k' best rows fell into the sample:
+  // P(Binomial(k', f) >= 32) with k' f <= 10, below 1e-8.
+  pl->sample = 0;
+  pl->s_kprime = 32;
+  pl->s_stride = pl->s_tiles = pl->s_tiles_per_unit = pl->s_chunks = pl->s_units = 0;
+  {
+    int stride = kp / 2;
+    if (stride > pl->n_tiles / 64) stride = pl->n_tiles / 64;  // at least 64 sample tiles (4096 rows)
+    if (stride >= 2 && stride * 10 >= kp) {
+      pl->sample = 1;
+      pl->s_stride = stride;
+      pl->s_tiles = (pl->n_tiles + stride - 1) / stride;
+      int sc = (sms + pl->m_tiles - 1) / pl->m_tiles;
+      if (sc > kSelGroup) sc = kSelGroup;  // single-level select
+      if (sc > pl->s_tiles) sc = pl->s_tiles;
+      pl->s_tiles_per_unit = (pl->s_tiles + sc - 1) / sc;
+      pl->s_chunks = (pl->s_tiles + pl->s_tiles_per_unit - 1) / pl->s_tiles_per_unit;
+      pl->s_units = pl->m_tiles * pl->s_chunks;
+    }
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -665,13 +731,21 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->off_qstats = take(static_cast<size_t>(nq) * 2 * sizeof(float));
   pl->off_qmu = take(static_cast<size_t>(nq) * sizeof(double));
   pl->off_gtau = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(unsigned int));
+  pl->off_gtau_s = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(unsigned int));
   pl->off_flagcnt = take(sizeof(int));
-  pl->off_cnt = take(static_cast<size_t>(pl->num_units) * kBM * sizeof(int));
+  {
+    const int max_units = pl->num_units > pl->s_units ? pl->num_units : pl->s_units;
+    pl->off_cnt = take(static_cast<size_t>(max_units) * kBM * sizeof(int));
+  }
   pl->off_sel_idx = take(static_cast<size_t>(nq) * kp * sizeof(int));
   pl->off_sel_cmin = take(static_cast<size_t>(nq) * sizeof(float));
   pl->off_l2_ent = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * kp * sizeof(unsigned long long) : 0);
   pl->off_l2_cnt = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * sizeof(int) : 0);
-  pl->off_cand = take(static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long));
+  {
+    const size_t main_b = static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long);
+    const size_t samp_b = static_cast<size_t>(pl->s_units) * kBM * 256 * sizeof(unsigned long long);
+    pl->off_cand = take(main_b > samp_b ? main_b : samp_b);
+  }
   pl->total_bytes = off;
   return kOk;
 }
@@ -724,85 +798,114 @@ int search_run(const SearchArgs& a) {
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
   const int nq = static_cast<int>(a.nq);
 
-  // gtau and the flag counter are adjacent in the plan: one memset clears both
+  // gtau, gtau_s and the flag counter are adjacent in the plan: one memset clears them
+  unsigned int* gtau_s = reinterpret_cast<unsigned int*>(ws + pl.off_gtau_s);
   LDOT_CUDA(cudaMemsetAsync(gtau, 0, (pl.off_flagcnt - pl.off_gtau) + sizeof(int), st));
   const int qblocks = (nq + 7) / 8;
   {
     KernelScope ks(kKcQueryPrep, st, 0.0, static_cast<double>(nq) * a.d * 6.0);
-  if (a.coarse_dtype == 0)
-    query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__half*>(q16), qstats, qmu);
-  else
-    query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__nv_bfloat16*>(q16),
-                                                                 qstats, qmu);
+    if (a.coarse_dtype == 0)
+      query_prepare_kernel<__half><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d, static_cast<__half*>(q16), qstats, qmu);
+    else
+      query_prepare_kernel<__nv_bfloat16><<<qblocks, 256, 0, st>>>(a.q, a.mu, nq, a.d,
+                                                                   static_cast<__nv_bfloat16*>(q16), qstats, qmu);
   }
   LDOT_CHECK_LAUNCH();
 
+  CUtensorMap ta, tb;
+  if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, pl.bn)) return e;
+  if (!pl.a_in_tmem)
+    if (int e = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e;
+  TsQueries tq;
+  tq.q16 = static_cast<const uint16_t*>(q16);
+  tq.nq = nq;
+  tq.d = a.d;
+
+  // one coarse pass (tcgen05 score + per-list top-k') over the tiles of schedule `s`
+  auto run_coarse = [&](const GemmSched& s, const TopKParams& tp, int epl, double rows) -> int {
+    // algorithmic work: every (query, row) pair once; the 16-bit rows and queries read once
+    KernelScope coarse_scope(kKcCoarse, st, 2.0 * nq * rows * a.d, (rows + nq) * a.d * 2.0);
+    if (pl.a_in_tmem) {
+      switch (epl) {
+        case 8: return launch_coarse_ts<8>(tb, s, tq, tp, sms, st);
+        case 16: return launch_coarse_ts<16>(tb, s, tq, tp, sms, st);
+        case 32: return launch_coarse_ts<32>(tb, s, tq, tp, sms, st);
+        default: return launch_coarse_ts<80>(tb, s, tq, tp, sms, st);
+      }
+    }
+    switch (epl) {
+      case 8: return launch_coarse_ss<8>(ta, tb, s, tp, sms, st);
+      case 16: return launch_coarse_ss<16>(ta, tb, s, tp, sms, st);
+      case 32: return launch_coarse_ss<32>(ta, tb, s, tp, sms, st);
+      default: return launch_coarse_ss<80>(ta, tb, s, tp, sms, st);
+    }
+  };
+  // where the lists of a coarse pass live: list (chunk c, query q) = unit (c * m_tiles + q / 128), row q % 128
+  auto lists_of = [&](int chunks, int cap) {
+    SelLists l;
+    l.ent = cand;
+    l.cnt = cnt;
+    l.ent_sc = static_cast<long long>(pl.m_tiles) * kBM * cap;
+    l.ent_sq = cap;
+    l.cnt_sc = static_cast<long long>(pl.m_tiles) * kBM;
+    l.cnt_sq = 1;
+    l.num_lists = chunks;
+    return l;
+  };
+  const size_t sel_smem = kSelStage * sizeof(unsigned long long);
+  static_assert(kSelStage * sizeof(unsigned long long) <= 64 * 1024, "select staging");
+  LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+
   GemmSched s;
   s.m_tiles = pl.m_tiles;
-  s.n_tiles = pl.n_tiles;
-  s.tiles_per_unit = pl.tiles_per_unit;
-  s.chunks = pl.chunks;
-  s.num_units = pl.num_units;
   s.k_blocks = (a.d + kBK - 1) / kBK;
   s.idesc = ptx::make_idesc_f16(a.coarse_dtype == 0 ? 0u : 1u, kBM, pl.bn);
   TopKParams tp;
   tp.nq = nq;
   tp.n = static_cast<int>(a.n);
-  tp.kprime = pl.kprime;
-  tp.cap = pl.cap;
   tp.cand = cand;
   tp.cand_cnt = cnt;
-  tp.gtau = gtau;
-  CUtensorMap ta, tb;
-  if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, pl.bn)) return e;
-  int e = kOk;
-  // algorithmic work of the coarse pass: every (query, row) pair once; the 16-bit index and queries read once
-  if (!pl.a_in_tmem)
-    if (int e2 = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e2;
-  {
-  KernelScope coarse_scope(kKcCoarse, st, 2.0 * nq * static_cast<double>(a.n) * a.d,
-                           (static_cast<double>(a.n) + nq) * a.d * 2.0);
-  if (pl.a_in_tmem) {
-    TsQueries tq;
-    tq.q16 = static_cast<const uint16_t*>(q16);
-    tq.nq = nq;
-    tq.d = a.d;
-    switch (pl.epl) {
-      case 8: e = launch_coarse_ts<8>(tb, s, tq, tp, sms, st); break;
-      case 16: e = launch_coarse_ts<16>(tb, s, tq, tp, sms, st); break;
-      case 32: e = launch_coarse_ts<32>(tb, s, tq, tp, sms, st); break;
-      default: e = launch_coarse_ts<80>(tb, s, tq, tp, sms, st); break;
-    }
-  } else {
-    switch (pl.epl) {
-      case 8: e = launch_coarse_ss<8>(ta, tb, s, tp, sms, st); break;
-      case 16: e = launch_coarse_ss<16>(ta, tb, s, tp, sms, st); break;
-      case 32: e = launch_coarse_ss<32>(ta, tb, s, tp, sms, st); break;
-      default: e = launch_coarse_ss<80>(ta, tb, s, tp, sms, st); break;
-    }
-  }
-  }
-  if (e) return e;
 
-  const size_t sel_smem = kSelStage * sizeof(unsigned long long);
-  static_assert(kSelStage * sizeof(unsigned long long) <= 64 * 1024, "select staging");
-  LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
-  SelLists l1;
-  l1.ent = cand;
-  l1.cnt = cnt;
-  l1.ent_sc = static_cast<long long>(pl.m_tiles) * kBM * pl.cap;  // list (chunk c, query q) = unit (c * m_tiles + q / 128), row q % 128
-  l1.ent_sq = pl.cap;
-  l1.cnt_sc = static_cast<long long>(pl.m_tiles) * kBM;
-  l1.cnt_sq = 1;
-  l1.num_lists = pl.chunks;
+  if (pl.sample) {
+    // threshold pre-pass: the s_kprime-th best score of every query over a strided sample of the index tiles
+    s.n_tiles = pl.s_tiles;
+    s.tiles_per_unit = pl.s_tiles_per_unit;
+    s.chunks = pl.s_chunks;
+    s.num_units = pl.s_units;
+    s.tile_stride = pl.s_stride;
+    tp.kprime = pl.s_kprime;
+    tp.cap = 256;
+    tp.gtau = gtau_s;
+    const double s_rows = static_cast<double>(pl.s_tiles) * pl.bn;
+    if (int e = run_coarse(s, tp, 8, s_rows < static_cast<double>(a.n) ? s_rows : static_cast<double>(a.n))) return e;
+    {
+      KernelScope ks(kKcSelect, st);
+      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(lists_of(pl.s_chunks, 256), gtau_s, pl.s_kprime, 1, nullptr,
+                                                        nullptr, sel_idx, sel_cmin, gtau);
+    }
+    LDOT_CHECK_LAUNCH();
+  }
+
+  s.n_tiles = pl.n_tiles;
+  s.tiles_per_unit = pl.tiles_per_unit;
+  s.chunks = pl.chunks;
+  s.num_units = pl.num_units;
+  s.tile_stride = 1;
+  tp.kprime = pl.kprime;
+  tp.cap = pl.cap;
+  tp.gtau = gtau;
+  if (int e = run_coarse(s, tp, pl.epl, static_cast<double>(a.n))) return e;
+
+  const SelLists l1 = lists_of(pl.chunks, pl.cap);
   if (pl.groups == 1) {
     KernelScope ks(kKcSelect, st);
-    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr);
     LDOT_CHECK_LAUNCH();
   } else {
     {
       KernelScope ks(kKcSelect, st);
-      select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr);
+      select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr,
+                                                                nullptr);
     }
     LDOT_CHECK_LAUNCH();
     SelLists l2;
@@ -815,7 +918,7 @@ int search_run(const SearchArgs& a) {
     l2.num_lists = pl.groups;
     {
       KernelScope ks(kKcSelect, st);
-      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin);
+      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr);
     }
     LDOT_CHECK_LAUNCH();
   }
@@ -885,7 +988,13 @@ int index_prepare_run(const float* x, long long n, int d, int coarse_dtype, int 
   return kOk;
 }
 
-size_t exact_workspace_bytes(long long n) { return align_up(static_cast<size_t>(kExactBatch) * n * sizeof(float), 256); }
+static size_t exact_scores_bytes(long long n) { return align_up(static_cast<size_t>(kExactBatch) * n * sizeof(float), 256); }
+static int exact_chunks(long long n) { return static_cast<int>((n + kExactChunk - 1) / kExactChunk); }
+
+size_t exact_workspace_bytes(long long n) {
+  // score rows of one query batch + level-1 keys sized for the largest k (1024)
+  return exact_scores_bytes(n) + align_up(static_cast<size_t>(kExactBatch) * exact_chunks(n) * 1024 * sizeof(unsigned long long), 256);
+}
 
 int exact_run(const float* q, long long nf, const float* x, long long n, int d, int k, long long id_offset,
               float* out_scores, long long* out_idx, void* ws, size_t ws_bytes, void* stream) {
@@ -896,7 +1005,11 @@ int exact_run(const float* q, long long nf, const float* x, long long n, int d, 
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   float* scores = static_cast<float*>(ws);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + exact_scores_bytes(n));
+  const int chunks = exact_chunks(n);
   const int kp_pad = next_pow2(k);
+  LDOT_CUDA(cudaFuncSetAttribute(exact_chunk_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kExactChunk * sizeof(unsigned long long))));
   const size_t q_smem = static_cast<size_t>(kExactBatch) * d * sizeof(float);
   LDOT_CUDA(cudaFuncSetAttribute(exact_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(q_smem)));
   for (long long f0 = 0; f0 < nf; f0 += kExactBatch) {
@@ -911,8 +1024,13 @@ int exact_run(const float* q, long long nf, const float* x, long long n, int d, 
     LDOT_CHECK_LAUNCH();
     {
       KernelScope ks(kKcExactScan, st, 0.0, static_cast<double>(nb) * n * 4.0);
-      exact_select_kernel<<<nb, 1024, kp_pad * sizeof(unsigned long long), st>>>(
-          scores, n, k, kp_pad, id_offset, out_scores + f0 * k, out_idx + f0 * k);
+      exact_chunk_topk_kernel<<<dim3(chunks, nb), 256, kExactChunk * sizeof(unsigned long long), st>>>(scores, n, k, keys);
+    }
+    LDOT_CHECK_LAUNCH();
+    {
+      KernelScope ks(kKcExactScan, st, 0.0, static_cast<double>(nb) * chunks * k * 8.0);
+      exact_merge_kernel<<<nb, 1024, kp_pad * sizeof(unsigned long long), st>>>(
+          keys, chunks * k, n, k, kp_pad, id_offset, out_scores + f0 * k, out_idx + f0 * k);
     }
     LDOT_CHECK_LAUNCH();
   }

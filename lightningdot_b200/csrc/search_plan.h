@@ -17,6 +17,12 @@ struct SearchPlan {
   int bn;              // index rows per MMA tile
   int m_tiles, n_tiles, tiles_per_unit, chunks, num_units;
   int groups;          // candidate-list groups of the select stage (> 1: two-level select)
+  // threshold pre-pass over a strided sample of the index tiles (0 = off, small indexes)
+  int sample;          // 1: run it
+  int s_stride;        // every s_stride-th index tile is sampled
+  int s_tiles, s_tiles_per_unit, s_chunks, s_units;
+  int s_kprime;        // the s_kprime-th best sample score of a query seeds its threshold
+  size_t off_gtau_s;
   size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_l2_ent,
       off_l2_cnt, off_cand;
   size_t total_bytes;

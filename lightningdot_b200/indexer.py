@@ -23,6 +23,7 @@ from . import _lib
 logger = logging.getLogger()
 
 MAX_QUERY_BATCH = 32768  # queries per C-ABI call (bounds the candidate-list workspace)
+WIDE_COARSE_K = 960      # candidate-list width of the second tier (queries whose first certificate failed)
 
 
 def _as_device_f32(a, device):
@@ -68,7 +69,8 @@ class FlatIPIndex:
         self._mu = None       # [d]
         self._xstats = None   # [2]
         self._ws = _Workspace()
-        self.last_flagged = 0  # queries of the last search() that needed the exhaustive fallback
+        self.last_flagged = 0      # queries of the last search() whose first-tier certificate failed
+        self.last_exhaustive = 0   # ... of which the second tier could not certify either (exhaustive scan)
 
     # -- faiss-like surface -------------------------------------------------------------------------------------
     @property
@@ -120,30 +122,60 @@ class FlatIPIndex:
             idx.fill_(-1)
             return scores, idx
         flags = torch.empty((nq,), dtype=torch.int32, device=dev)
+        n_flag = self._search_pass(qd, k, self.coarse_k, scores, idx, flags)
+        self.last_flagged = 0
+        self.last_exhaustive = 0
+        if resolve_flags:
+            n_flag = int(n_flag.sum().item())
+            self.last_flagged = n_flag
+            if n_flag:
+                # tier 2: the same tensor-core pipeline with a much wider candidate list (the certificate margin
+                # grows with k' - k); tier 3: the exhaustive fp64-accumulated scan for whatever is still uncertified
+                rows = torch.nonzero(flags, as_tuple=False).flatten()
+                q2 = qd.index_select(0, rows).contiguous()
+                s2 = torch.empty((n_flag, k), dtype=torch.float32, device=dev)
+                i2 = torch.empty((n_flag, k), dtype=torch.int64, device=dev)
+                wide = min(WIDE_COARSE_K, 1280)
+                if wide >= 2 * k and wide > self._auto_coarse_k(k):
+                    f2 = torch.empty((n_flag,), dtype=torch.int32, device=dev)
+                    n2 = int(self._search_pass(q2, k, wide, s2, i2, f2).sum().item())
+                else:
+                    f2, n2 = torch.ones((n_flag,), dtype=torch.int32, device=dev), n_flag
+                if n2:
+                    sub = torch.nonzero(f2, as_tuple=False).flatten()
+                    es, ei = self.exact_search_device(q2.index_select(0, sub).contiguous(), k)
+                    s2.index_copy_(0, sub, es)
+                    i2.index_copy_(0, sub, ei)
+                    self.last_exhaustive = n2
+                scores.index_copy_(0, rows, s2)
+                idx.index_copy_(0, rows, i2)
+        return scores, idx
+
+    def _auto_coarse_k(self, k):
+        if self.coarse_k:
+            return self.coarse_k
+        kp = max(k + max(k // 2, 32), 64)
+        return (kp + 31) // 32 * 32
+
+    def _search_pass(self, qd, k, coarse_k, scores, idx, flags):
+        """One ldot_flatip_search call per MAX_QUERY_BATCH queries -> per-call flagged counts (cuda int32 tensor)."""
+        lib = _lib.load()
+        nq, dev = qd.shape[0], qd.device
         counts = torch.zeros(((nq + MAX_QUERY_BATCH - 1) // MAX_QUERY_BATCH,), dtype=torch.int32, device=dev)
         stream = _lib.stream_ptr()
         for bi, b in enumerate(range(0, nq, MAX_QUERY_BATCH)):
             e = min(nq, b + MAX_QUERY_BATCH)
             nb = e - b
-            need = lib.ldot_flatip_search_workspace_bytes(nb, self._n, self.d, k, self.coarse_k)
+            need = lib.ldot_flatip_search_workspace_bytes(nb, self._n, self.d, k, coarse_k)
             if need == 0:
                 raise _lib.LdotError(f"invalid search shape: {lib.ldot_last_error().decode()}")
             ws = self._ws.get(need, dev)
             _lib.check(lib.ldot_flatip_search(
                 _lib.ptr(qd[b:e]), nb, _lib.ptr(self._x), _lib.ptr(self._x16), _lib.ptr(self._mu),
-                _lib.ptr(self._xstats), self._n, self.d, k, self.coarse_k, self.coarse_dtype, self.row_offset,
+                _lib.ptr(self._xstats), self._n, self.d, k, coarse_k, self.coarse_dtype, self.row_offset,
                 _lib.ptr(scores[b:e]), _lib.ptr(idx[b:e]), _lib.ptr(flags[b:e]), _lib.ptr(counts[bi:bi + 1]),
                 _lib.ptr(ws), need, stream))
-        self.last_flagged = 0
-        if resolve_flags:
-            n_flag = int(counts.sum().item())
-            self.last_flagged = n_flag
-            if n_flag:
-                rows = torch.nonzero(flags, as_tuple=False).flatten()
-                es, ei = self.exact_search_device(qd.index_select(0, rows).contiguous(), k)
-                scores.index_copy_(0, rows, es)
-                idx.index_copy_(0, rows, ei)
-        return scores, idx
+        return counts
 
     def exact_search_device(self, qd, k):
         """Exhaustive fp64-accumulated scan (no tensor cores) - the fallback path, also usable on its own."""

@@ -49,3 +49,23 @@ def test_linear_residual(cuda_lib):
     torch.testing.assert_close(out, ref, atol=2e-4, rtol=1e-5)
     out, ref = run_linear(640, 768, 768, 1, res=True, out_f32=False, bias=False)
     torch.testing.assert_close(out, ref, atol=4e-2, rtol=8e-3)
+
+
+def test_linear_tails_and_pitches(cuda_lib):
+    """N not a multiple of the 32-column store box, M not a multiple of 32, output / residual pitches wider than N
+    (the TMA store clips at the tensor edges; nothing outside [M, N] may be touched)."""
+    lib = _lib.load()
+    M, N, K, ld = 77, 200, 72, 264
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, ld, device="cuda", generator=g).to(torch.bfloat16)
+    for out_f32, dt in ((1, torch.float32), (0, torch.bfloat16)):
+        out = torch.full((M + 3, ld), 7.0, device="cuda", dtype=dt)
+        _lib.check(lib.ldot_linear(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(r), ld, _lib.ptr(out), ld, M, N, K,
+                                   1, 0, out_f32, _lib.stream_ptr()))
+        ref = a.float() @ w.float().t() + b + r[:, :N].float()
+        tol = dict(atol=1e-4, rtol=1e-5) if out_f32 else dict(atol=4e-2, rtol=8e-3)
+        torch.testing.assert_close(out[:M, :N].float(), ref, **tol)
+        assert (out[M:] == 7.0).all() and (out[:, N:] == 7.0).all()

@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 
 
 def test_inbatch_nll_matches_reference_fixture(cuda_lib, golden_dir):
-    """Tolerance: scores 2e-6 absolute (fp16 hi/lo split products, fp32 accumulation), loss 1e-5."""
+    """Tolerance: scores 1e-5 relative + 2e-6 absolute (fp16 hi/lo split products drop the lo*lo term, ~2^-21
+    relative per operand pair, plus fp32 accumulation), loss 1e-5."""
     gold = np.load(os.path.join(golden_dir, "loss_inbatch.npz"))
     g = torch.Generator().manual_seed(7)
     q = torch.randn(24, 768, generator=g) * 0.06
@@ -36,8 +37,8 @@ def test_inbatch_nll_matches_reference_fixture(cuda_lib, golden_dir):
                                 cap.cuda(), pos, None)
     assert abs(float(l0) - float(gold["loss0"])) < 1e-5 and int(c0) == int(gold["correct0"])
     assert abs(float(l1) - float(gold["loss1"])) < 1e-5 and int(c1) == int(gold["correct1"])
-    np.testing.assert_allclose(s0.cpu().numpy(), gold["scores0"], atol=2e-6)
-    np.testing.assert_allclose(s1.cpu().numpy(), gold["scores1"], atol=2e-6)
+    np.testing.assert_allclose(s0.cpu().numpy(), gold["scores0"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(s1.cpu().numpy(), gold["scores1"], atol=2e-6, rtol=1e-5)
 
 
 @pytest.mark.parametrize("bq,bc", [(1, 1), (7, 13), (96, 96), (300, 1000), (4096, 4096)])
@@ -52,7 +53,7 @@ def test_inbatch_nll_vs_oracle_shapes(cuda_lib, bq, bc):
             ol, oc, os_ = oloss.nll(q.double(), ctx.double(), pos, reduction=red)
             assert abs(float(l) - float(ol)) <= 2e-5 * max(1.0, abs(float(ol)))
             assert int(c) == int(oc)
-            assert torch.allclose(s.cpu().double(), os_, atol=5e-6)
+            assert torch.allclose(s.cpu().double(), os_, atol=5e-6, rtol=1e-5)
     # cosine flag of dot_product_scores (bi_encoder.py:63-67)
     cs = dot_product_scores(q.cuda(), ctx.cuda(), cosine=True).cpu()
     want = torch.nn.functional.normalize(q, dim=1) @ torch.nn.functional.normalize(ctx, dim=1).t()
