@@ -67,7 +67,7 @@ int ldot_index_prepare(const float* d_x, int64_t n, int32_t d, int32_t coarse_dt
  * d_out_scores [nq, k] fp32, d_out_idx [nq, k] int64 (-1 / -FLT_MAX past the end of a short index)
  * d_out_flags  [nq] int32: 0 = result proven exact; 1 = certificate failed - the caller must re-run that query
  *              through ldot_flatip_exact (DenseFlatIndexer.search_knn does)
- * d_out_flag_count [1] int32 number of flagged queries (may be NULL)                                            */
+ * d_out_flag_count [1] int32 number of flagged queries: device or PINNED HOST memory (UVA copy), may be NULL     */
 size_t ldot_flatip_search_workspace_bytes(int64_t nq, int64_t n, int32_t d, int32_t k, int32_t coarse_k);
 int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const void* d_x16, const float* d_mu,
                        const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,

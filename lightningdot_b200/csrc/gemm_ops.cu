@@ -15,7 +15,11 @@ template <int ACT, int OUT_F32>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
   auto kern = linear_tc_kernel<ACT, OUT_F32>;
-  LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LinSmem::kDynamic));
+  static bool configured = false;  // (one device per process)
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LinSmem::kDynamic));
+    configured = true;
+  }
   const int grid = s.num_tiles < sms ? s.num_tiles : sms;
   kern<<<grid, kLinThreads, LinSmem::kDynamic, st>>>(ta, tw, to, s, p);
   LDOT_CHECK_LAUNCH();

@@ -32,7 +32,7 @@ struct TopKParams {
   int nq;                     // valid queries
   int n;                      // valid index rows
   int kprime;                 // entries kept by a compaction
-  int cap;                    // list capacity per (unit, query) = EPL * 32  (>= 2 * kprime)
+  int cap;                    // list capacity per (unit, query) = EPL * 32  (>= kprime + 64)
   unsigned long long* cand;   // [num_units][128][cap] packed (coarse key, row id)
   int* cand_cnt;              // [num_units][128]
   unsigned int* gtau;         // [m_tiles * 128] best known lower bound of the k'-th coarse key, shared by all units
@@ -51,7 +51,7 @@ __device__ __noinline__ uint32_t warp_compact(unsigned long long* buf, int n, in
   for (int i = 0; i < EPL; ++i) {
     const int idx = i * 32 + lane;
     const unsigned long long e = idx < n ? __ldcg(buf + idx) : 0ull;
-    key[i] = static_cast<uint32_t>(e >> 32);
+    key[i] = idx < n ? entry_key(e) : 0u;
     if (kInRegs) ent[i] = e;
   }
   uint32_t T = 0;
@@ -105,41 +105,57 @@ struct EpiTopK {
     st.tau = st.q < p.nq ? -INFINITY : INFINITY;  // padded query rows never collect anything
   }
 
+  // Append entry (s, id) to the list at `ptr` when s > tau: one compare and three predicated instructions, no branch.
+  static __device__ __forceinline__ void append_if(unsigned long long*& ptr, float s, float tau, uint32_t id) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.gt.f32 p, %1, %2;\n"
+        "@p st.global.v2.b32 [%0], {%3, %4};\n"
+        "@p add.u64 %0, %0, 8;\n"
+        "}\n"
+        : "+l"(ptr)
+        : "f"(s), "f"(tau), "r"(id), "r"(__float_as_uint(s))
+        : "memory");
+  }
+
   static __device__ __forceinline__ void tile(State& st, const Params& p, const UnitInfo& u, int row, int nt,
                                               uint32_t taddr) {
     const int lane = threadIdx.x & 31;
-    if (st.q < p.nq) {
+    // the shared lower bound only moves when some list is compacted: poll it every 8th tile
+    if (((nt - u.n_tile_begin) & 7) == 0 && st.q < p.nq) {
       const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.gtau + st.q);
       if (g > kKeyNegInf) st.tau = fmaxf(st.tau, fkey_inv(g));
     }
     const int col0 = nt * BN;
     const bool full_tile = col0 + BN <= p.n;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld32(taddr + c, v);
+    for (int c = 0; c < BN; c += 64) {
+      // both 32-column loads of this 64-column slab are in flight before the wait
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(taddr + c, v0);
+      ptx::tmem_ld32(taddr + c + 32, v1);
       ptx::tmem_ld_wait();
       if (full_tile) {
+        unsigned long long* ptr = st.buf + st.cnt;
+        const uint32_t id0 = static_cast<uint32_t>(col0 + c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]);
-          if (s > st.tau) {
-            st.buf[st.cnt] = pack_entry(fkey(s), static_cast<uint32_t>(col0 + c + j));
-            ++st.cnt;
-          }
-        }
+        for (int j = 0; j < 32; ++j) append_if(ptr, __uint_as_float(v0[j]), st.tau, id0 + j);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) append_if(ptr, __uint_as_float(v1[j]), st.tau, id0 + 32 + j);
+        st.cnt = static_cast<int>(ptr - st.buf);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float s = __uint_as_float(v[j]);
+        for (int j = 0; j < 64; ++j) {
+          const float s = __uint_as_float(j < 32 ? v0[j] : v1[j - 32]);
           if (s > st.tau && col0 + c + j < p.n) {
-            st.buf[st.cnt] = pack_entry(fkey(s), static_cast<uint32_t>(col0 + c + j));
+            st.buf[st.cnt] = pack_entry(s, static_cast<uint32_t>(col0 + c + j));
             ++st.cnt;
           }
         }
       }
-      // a list that could overflow in the next 32 columns is compacted now, by the whole warp
-      compact_where(st, p, lane, st.cnt > p.cap - 32);
+      // a list that could overflow in the next 64 columns is compacted now, by the whole warp
+      compact_where(st, p, lane, st.cnt > p.cap - 64);
     }
   }
 
@@ -251,7 +267,7 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
       const unsigned long long* src = list_of(c);
       for (int i = lane; i < cnts[c]; i += 32) {
         const unsigned long long e = __ldcg(src + i);
-        if (static_cast<uint32_t>(e >> 32) >= floor_key) stage[atomicAdd(&n_stage, 1)] = e;
+        if (entry_key(e) >= floor_key) stage[atomicAdd(&n_stage, 1)] = e;
       }
     }
     __syncthreads();
@@ -284,15 +300,15 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
   for (int bit = 31; bit >= 0; --bit) {
     const uint32_t candk = T | (1u << bit);
     int c = 0;
-    for_each([&](unsigned long long e) { c += (static_cast<uint32_t>(e >> 32) >= candk); });
+    for_each([&](unsigned long long e) { c += (entry_key(e) >= candk); });
     if (block_sum(c, scratch) >= kprime) T = candk;
   }
   int c = 0;
-  for_each([&](unsigned long long e) { c += (static_cast<uint32_t>(e >> 32) > T); });
+  for_each([&](unsigned long long e) { c += (entry_key(e) > T); });
   const int n_gt = block_sum(c, scratch);
   const int need_eq = kprime - n_gt;
   for_each([&](unsigned long long e) {
-    const uint32_t key = static_cast<uint32_t>(e >> 32);
+    const uint32_t key = entry_key(e);
     if (key > T) {
       emit(atomicAdd(&out_pos, 1), e);
     } else if (key == T) {
@@ -662,7 +678,7 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   kp = (kp + 31) / 32 * 32;
   LDOT_REQUIRE(kp >= k && kp <= 1280, "coarse_k=%d must be in [k, 1280]", kp);
   pl->kprime = kp;
-  // list capacity cap = epl * 32 >= k' + 32 (a list is compacted to its k' best when fewer than 32 slots are left)
+  // list capacity cap = epl * 32 >= k' + 64 (a list is compacted to its k' best when fewer than 64 slots are left)
   pl->epl = kp <= 192 ? 8 : kp <= 448 ? 16 : kp <= 960 ? 32 : 80;
   pl->cap = pl->epl * 32;
   pl->kp_pad = next_pow2(kp);
@@ -755,7 +771,11 @@ static int launch_coarse_ss(const CUtensorMap& ta, const CUtensorMap& tb, const 
                             cudaStream_t st) {
   using SM = GemmSmem<kSearchBN, kSearchStages>;
   auto kern = gemm_tc_kernel<EpiTopK<EPL, kSearchBN>, kSearchBN, kSearchStages>;
-  LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
+  static bool configured = false;  // (one device per process)
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
+    configured = true;
+  }
   const int grid = s.num_units < sms ? s.num_units : sms;
   kern<<<grid, kGemmThreads, SM::kDynamic, st>>>(ta, tb, s, p);
   LDOT_CHECK_LAUNCH();
@@ -766,7 +786,11 @@ template <int EPL>
 static int launch_coarse_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TopKParams& p, int sms,
                             cudaStream_t st) {
   auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>>;
-  LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+  static bool configured = false;  // (one device per process)
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+    configured = true;
+  }
   const int grid = s.num_units < sms ? s.num_units : sms;
   kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
   LDOT_CHECK_LAUNCH();
@@ -854,7 +878,13 @@ int search_run(const SearchArgs& a) {
   };
   const size_t sel_smem = kSelStage * sizeof(unsigned long long);
   static_assert(kSelStage * sizeof(unsigned long long) <= 64 * 1024, "select staging");
-  LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+  {
+    static bool configured = false;
+    if (!configured) {
+      LDOT_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sel_smem)));
+      configured = true;
+    }
+  }
 
   GemmSched s;
   s.m_tiles = pl.m_tiles;
@@ -947,7 +977,7 @@ int search_run(const SearchArgs& a) {
   }
   LDOT_CHECK_LAUNCH();
   if (a.out_flag_count)
-    LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDefault, st));  // device or pinned host
   return kOk;
 }
 

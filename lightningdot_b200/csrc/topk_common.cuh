@@ -18,9 +18,14 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
 
 constexpr uint32_t kKeyNegInf = 0x007FFFFFu;  // fkey(-inf)
 
-// A candidate entry: coarse-score key in the high word, shard-local row id in the low word.
-__device__ __forceinline__ unsigned long long pack_entry(uint32_t key, uint32_t id) {
-  return (static_cast<unsigned long long>(key) << 32) | id;
+// A candidate entry: RAW fp32 bits of the coarse score in the high word, shard-local row id in the low word (the
+// coarse epilogue appends entries with one predicated 8-byte store; consumers order them by entry_key()).
+__device__ __forceinline__ unsigned long long pack_entry(float score, uint32_t id) {
+  return (static_cast<unsigned long long>(__float_as_uint(score)) << 32) | id;
+}
+__device__ __forceinline__ uint32_t entry_key(unsigned long long e) {
+  const uint32_t u = static_cast<uint32_t>(e >> 32);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
 // Final ranking key: (exact fp32 score desc, row id asc)  ==  descending order of this 64-bit value.

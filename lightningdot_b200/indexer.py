@@ -10,6 +10,7 @@ tensor-core pass.  search() is exact: ids are ranked by (correctly rounded fp32 
 queries whose exactness certificate fails are transparently re-run through the exhaustive fp64-accumulated scan.
 There is no CPU path: without the CUDA extension and a B200 every call raises.
 """
+import gc
 import logging
 import pickle
 import struct
@@ -69,6 +70,8 @@ class FlatIPIndex:
         self._mu = None       # [d]
         self._xstats = None   # [2]
         self._ws = _Workspace()
+        self._pinned = None
+        self._pin_counts = None
         self.last_flagged = 0      # queries of the last search() whose first-tier certificate failed
         self.last_exhaustive = 0   # ... of which the second tier could not certify either (exhaustive scan)
 
@@ -99,7 +102,20 @@ class FlatIPIndex:
         dev = self._device()
         qd = _as_device_f32(q, dev)
         scores, idx = self.search_device(qd, k)
-        return scores.cpu().numpy(), idx.cpu().numpy()
+        return self.to_host(scores, idx)
+
+    def to_host(self, scores, idx):
+        """Device results -> numpy through cached pinned staging buffers (one synchronisation)."""
+        nq, k = scores.shape
+        pin = self._pinned
+        if pin is None or pin[0].shape[0] < nq or pin[0].shape[1] != k:
+            pin = (torch.empty((max(nq, 1), k), dtype=torch.float32, pin_memory=True),
+                   torch.empty((max(nq, 1), k), dtype=torch.int64, pin_memory=True))
+            self._pinned = pin
+        pin[0][:nq].copy_(scores, non_blocking=True)
+        pin[1][:nq].copy_(idx, non_blocking=True)
+        torch.cuda.current_stream(scores.device).synchronize()
+        return pin[0][:nq].numpy().copy(), pin[1][:nq].numpy().copy()
 
     # -- device-level API (used by the eval loop and the benchmark to avoid host round trips) -------------------
     def search_device(self, qd, k, resolve_flags=True):
@@ -126,7 +142,8 @@ class FlatIPIndex:
         self.last_flagged = 0
         self.last_exhaustive = 0
         if resolve_flags:
-            n_flag = int(n_flag.sum().item())
+            torch.cuda.current_stream(dev).synchronize()   # the flagged-query counts land in pinned host memory
+            n_flag = int(n_flag.sum())
             self.last_flagged = n_flag
             if n_flag:
                 # tier 2: the same tensor-core pipeline with a much wider candidate list (the certificate margin
@@ -138,7 +155,9 @@ class FlatIPIndex:
                 wide = min(WIDE_COARSE_K, 1280)
                 if wide >= 2 * k and wide > self._auto_coarse_k(k):
                     f2 = torch.empty((n_flag,), dtype=torch.int32, device=dev)
-                    n2 = int(self._search_pass(q2, k, wide, s2, i2, f2).sum().item())
+                    c2 = self._search_pass(q2, k, wide, s2, i2, f2)
+                    torch.cuda.current_stream(dev).synchronize()
+                    n2 = int(c2.sum())
                 else:
                     f2, n2 = torch.ones((n_flag,), dtype=torch.int32, device=dev), n_flag
                 if n2:
@@ -158,10 +177,14 @@ class FlatIPIndex:
         return (kp + 31) // 32 * 32
 
     def _search_pass(self, qd, k, coarse_k, scores, idx, flags):
-        """One ldot_flatip_search call per MAX_QUERY_BATCH queries -> per-call flagged counts (cuda int32 tensor)."""
+        """One ldot_flatip_search call per MAX_QUERY_BATCH queries -> per-call flagged counts (PINNED HOST int32
+        tensor, valid once the stream has been synchronised)."""
         lib = _lib.load()
         nq, dev = qd.shape[0], qd.device
-        counts = torch.zeros(((nq + MAX_QUERY_BATCH - 1) // MAX_QUERY_BATCH,), dtype=torch.int32, device=dev)
+        nb_calls = (nq + MAX_QUERY_BATCH - 1) // MAX_QUERY_BATCH
+        if self._pin_counts is None or self._pin_counts.numel() < nb_calls:
+            self._pin_counts = torch.zeros((max(nb_calls, 16),), dtype=torch.int32, pin_memory=True)
+        counts = self._pin_counts[:nb_calls]
         stream = _lib.stream_ptr()
         for bi, b in enumerate(range(0, nq, MAX_QUERY_BATCH)):
             e = min(nq, b + MAX_QUERY_BATCH)
@@ -332,8 +355,17 @@ class DenseFlatIndexer(DenseIndexer):
         # negative indexing, exactly like faiss_indexers.py:85).  One vectorised gather over an object array
         # instead of nq * k Python list look-ups.
         id_map = self._id_array()
-        db_ids = id_map[indexes].tolist() if len(id_map) else [[] for _ in range(len(indexes))]
-        return [(db_ids[i], scores[i]) for i in range(len(db_ids))]
+        if not len(id_map):
+            return [([], scores[i]) for i in range(len(indexes))]
+        # building nq lists of k references allocates ~nq container objects: keep the cyclic GC from re-scanning the
+        # (possibly million-entry) id list while they are created
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return list(zip(id_map[indexes].tolist(), scores))
+        finally:
+            if gc_was_on:
+                gc.enable()
 
     def _id_array(self):
         cache = getattr(self, "_id_cache", None)

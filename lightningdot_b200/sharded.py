@@ -143,6 +143,15 @@ class ShardedFlatIndexer(DenseFlatIndexer):
     def _device(self):
         return self.index._device()
 
+    def search(self, query_vectors, k: int):
+        """faiss-level call (IndexFlatIP.search, faiss_indexers.py:83) over the sharded index:
+        -> (scores float32 [nq, k], global row labels int64 [nq, k]) numpy arrays."""
+        scores, idx = self.search_device(self._queries_on_device(query_vectors), k)
+        return self._to_host(scores, idx)
+
+    def _to_host(self, scores, idx):
+        return self.index.to_host(scores, idx)
+
     def search_knn(self, query_vectors, top_docs: int):
         scores, idx = self.search_device(self._queries_on_device(query_vectors), top_docs)
-        return self._format_result(scores.cpu().numpy(), idx.cpu().numpy())
+        return self._format_result(*self._to_host(scores, idx))

@@ -67,7 +67,10 @@ def test_eval_loop_on_gpu_matches_reference_fixture(cuda_lib, golden_dir):
     txt, img, batches, img2txt = evalloop_inputs()
     args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
     out = trainer.eval_model_on_dataloader(StubEncoder(txt, img, "cuda"), batches, args, img2txt, num_tops=100)
-    check_evalloop_against_golden(out, gold)
+    # the in-batch accuracy is an argmax over scores that are tied to ~1e-6 relative in this fixture (every batch of
+    # 16 holds several 1e-6-perturbed encodings of the same image), so it may move by a few samples with the
+    # summation order of the score GEMM; recalls, ranks and the loss are compared exactly / to 1e-4
+    check_evalloop_against_golden(out, gold, acc_tol=0.005)
     ix = trainer.get_indexer(StubEncoder(txt, img, "cuda"), batches, args, hnsw_index=False)
     assert ix.index_id_to_db_id == [f"img_{i:07d}.npz" for i in range(200)]
     assert np.array_equal(ix.index.vectors().cpu().numpy(), img[4::5])
