@@ -82,7 +82,8 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {
         const UnitInfo u = unit_info(sched, unit);
-        for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
+        for (int it = 0; it < u.n_tile_end - u.n_tile_begin; ++it) {
+          const int nt = unit_tile(u, it);
           for (int kb2 = 0; kb2 < kb2_count; ++kb2) {
             const int kb0 = kb2 * kTsKbPerStage;
             const int nkb = sched.k_blocks - kb0 < kTsKbPerStage ? sched.k_blocks - kb0 : kTsKbPerStage;
@@ -176,7 +177,8 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
         ptx::mbar_arrive(a_ready);
       }
       Epi::unit_begin(st, ep, u, row);
-      for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
+      for (int it = 0; it < u.n_tile_end - u.n_tile_begin; ++it) {
+        const int nt = unit_tile(u, it);
         ptx::mbar_wait(&tfull[as], aphase);
         ptx::tc_fence_after();
         Epi::tile(st, ep, u, row, nt * sched.tile_stride, lane_base + kTsACols + static_cast<uint32_t>(as * kTsBN));

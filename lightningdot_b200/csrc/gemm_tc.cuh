@@ -50,7 +50,17 @@ struct GemmSched {
 
 struct UnitInfo {
   int unit, m_tile, chunk, n_tile_begin, n_tile_end;
+  int rot;  // the unit visits its tiles starting at n_tile_begin + rot (wrapping): CTAs that share a B chunk in L2
+            // then pull different lines at any one time instead of hammering the same L2 slice together
 };
+
+// i-th tile visited by a unit
+__device__ __forceinline__ int unit_tile(const UnitInfo& u, int i) {
+  const int len = u.n_tile_end - u.n_tile_begin;
+  int t = i + u.rot;
+  if (t >= len) t -= len;
+  return u.n_tile_begin + t;
+}
 
 __device__ __forceinline__ UnitInfo unit_info(const GemmSched& s, int unit) {
   UnitInfo u;
@@ -60,6 +70,8 @@ __device__ __forceinline__ UnitInfo unit_info(const GemmSched& s, int unit) {
   u.n_tile_begin = u.chunk * s.tiles_per_unit;
   int e = u.n_tile_begin + s.tiles_per_unit;
   u.n_tile_end = e < s.n_tiles ? e : s.n_tiles;
+  const int len = u.n_tile_end - u.n_tile_begin;
+  u.rot = len > 0 ? static_cast<int>((static_cast<unsigned>(u.m_tile) * 29u) % static_cast<unsigned>(len)) : 0;
   return u;
 }
 
@@ -127,7 +139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {
         const UnitInfo u = unit_info(sched, unit);
-        for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
+        for (int it = 0; it < u.n_tile_end - u.n_tile_begin; ++it) {
+          const int nt = unit_tile(u, it);
           for (int kb = 0; kb < sched.k_blocks; ++kb) {
             ptx::mbar_wait(&empty[stage], phase ^ 1);
             ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
@@ -191,7 +204,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {
       const UnitInfo u = unit_info(sched, unit);
       Epi::unit_begin(st, ep, u, row);
-      for (int nt = u.n_tile_begin; nt < u.n_tile_end; ++nt) {
+      for (int it = 0; it < u.n_tile_end - u.n_tile_begin; ++it) {
+        const int nt = unit_tile(u, it);
         ptx::mbar_wait(&tfull[as], aphase);
         ptx::tc_fence_after();
         Epi::tile(st, ep, u, row, nt * sched.tile_stride, lane_base + static_cast<uint32_t>(as * BN));

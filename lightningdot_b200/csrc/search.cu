@@ -95,6 +95,7 @@ struct EpiTopK {
     float tau;
     int cnt;
     int q;
+    int tick;
     unsigned long long* buf;
   };
 
@@ -102,6 +103,7 @@ struct EpiTopK {
     st.q = u.m_tile * kBM + row;
     st.buf = p.cand + (static_cast<size_t>(u.unit) * kBM + row) * p.cap;
     st.cnt = 0;
+    st.tick = 0;
     st.tau = st.q < p.nq ? -INFINITY : INFINITY;  // padded query rows never collect anything
   }
 
@@ -123,7 +125,7 @@ struct EpiTopK {
                                               uint32_t taddr) {
     const int lane = threadIdx.x & 31;
     // the shared lower bound only moves when some list is compacted: poll it every 8th tile
-    if (((nt - u.n_tile_begin) & 7) == 0 && st.q < p.nq) {
+    if (((st.tick++) & 7) == 0 && st.q < p.nq) {
       const uint32_t g = *reinterpret_cast<volatile unsigned int*>(p.gtau + st.q);
       if (g > kKeyNegInf) st.tau = fmaxf(st.tau, fkey_inv(g));
     }
@@ -674,6 +676,7 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   LDOT_REQUIRE(d >= 8 && d <= 4096 && d % 8 == 0, "d=%d must be a multiple of 8 in [8, 4096]", d);
   LDOT_REQUIRE(k >= 1 && k <= 1024, "k=%d out of range [1, 1024]", k);
   int kp = coarse_k > 0 ? coarse_k : k + (k / 2 > 32 ? k / 2 : 32);
+  if (coarse_k <= 0 && kp > 1280) kp = 1280;  // k close to the 1024 limit: whatever margin is left
   if (kp < 64) kp = 64;
   kp = (kp + 31) / 32 * 32;
   LDOT_REQUIRE(kp >= k && kp <= 1280, "coarse_k=%d must be in [k, 1280]", kp);
@@ -694,9 +697,19 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   int max_chunks = pl->n_tiles / min_tpu;
   if (max_chunks < 1) max_chunks = 1;
   if (max_chunks > 2048) max_chunks = 2048;
-  int best_chunks = 1;
+  // With several query tiles the CTAs that run together share index chunks through L2: keep two chunks (the ones in
+  // flight at any time) well inside the 126 MB L2.
+  int c_min = 1;
+  if (pl->m_tiles > 1) {
+    const long long tile_bytes = static_cast<long long>(pl->bn) * d * 2;
+    long long max_tpu = (24ll << 20) / tile_bytes;
+    if (max_tpu < 8) max_tpu = 8;
+    c_min = static_cast<int>((pl->n_tiles + max_tpu - 1) / max_tpu);
+    if (c_min > max_chunks) max_chunks = c_min;
+  }
+  int best_chunks = c_min;
   double best_eff = -1.0;
-  for (int c = 1; c <= max_chunks; ++c) {
+  for (int c = c_min; c <= max_chunks; ++c) {
     const int tpu_c = (pl->n_tiles + c - 1) / c;
     const int chunks_c = (pl->n_tiles + tpu_c - 1) / tpu_c;
     const long long units = static_cast<long long>(pl->m_tiles) * chunks_c;
@@ -707,7 +720,7 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
       best_eff = eff;
       best_chunks = chunks_c;
     }
-    if (units >= 32ll * sms) break;
+    if (units >= 32ll * sms && c > c_min) break;
   }
   pl->tiles_per_unit = (pl->n_tiles + best_chunks - 1) / best_chunks;
   pl->chunks = (pl->n_tiles + pl->tiles_per_unit - 1) / pl->tiles_per_unit;

@@ -173,7 +173,7 @@ class FlatIPIndex:
     def _auto_coarse_k(self, k):
         if self.coarse_k:
             return self.coarse_k
-        kp = max(k + max(k // 2, 32), 64)
+        kp = max(min(k + max(k // 2, 32), 1280), 64)
         return (kp + 31) // 32 * 32
 
     def _search_pass(self, qd, k, coarse_k, scores, idx, flags):

@@ -1,0 +1,109 @@
+"""Turn the scratch ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
+
+    python scripts/summarize_profiles.py r01
+
+  profiles/<round>_launches_bench.csv   every launch of `bench.py --steps 2 --warmup 1` aggregated per kernel
+                                        (count, total / mean device time, share) from the gpu__time_duration pass
+  profiles/<round>_ncu_<name>.txt       key raw metrics + stall mix of the `--set full` capture of one kernel
+  profiles/traffic.json                 dram bytes per launch of the hot kernels (bench.py's roofline.traffic)
+"""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+SRC = os.path.join(ROOT, "gpurun_out")
+
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+           "launch__block_size", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
+           "sm__inst_executed.sum.per_cycle_elapsed", "l1tex__data_bank_conflicts_pipe_lsu.sum",
+           "smsp__cycles_active.avg", "sm__cycles_elapsed.avg.per_second"]
+
+
+def short(name):
+    return re.sub(r"\(.*", "", name).replace("void ", "").strip()[:110]
+
+
+def launches(tag):
+    src = os.path.join(SRC, "launches_bench.csv")
+    if not os.path.exists(src):
+        return
+    with open(src) as f:
+        lines = [l for l in f if l.startswith('"')]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        key = (short(row["Kernel Name"]), row["Grid Size"], row["Block Size"])
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += float(row["Metric Value"])
+    tot = sum(v[1] for v in agg.values())
+    dst = os.path.join(OUT, f"{tag}_launches_bench.csv")
+    with open(dst, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["# ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 2 --warmup 1 "
+                    "--no-cpu-baseline --no-e2e (cold-cache, serialised: compare SHARES, not absolutes)"])
+        w.writerow(["kernel", "grid", "block", "launches", "total_ms", "mean_us", "share"])
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            w.writerow([k[0], k[1], k[2], v[0], f"{v[1] / 1e6:.3f}", f"{v[1] / v[0] / 1e3:.1f}", f"{v[1] / tot:.4f}"])
+    print("wrote", dst)
+
+
+def ncu_report(tag, rep, name, traffic_key=None, kernel_index=0, traffic=None):
+    path = os.path.join(SRC, rep)
+    if not os.path.exists(path):
+        return
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    lines = [f"# ncu --set full --clock-control none --import-source on ({rep}); kernel {kernel_index} of the capture"]
+    data = rows[2 + kernel_index]
+    col = {h: i for i, h in enumerate(hdr)}
+    lines.append("kernel: " + data[col["Kernel Name"]][:200])
+    vals = {}
+    for m in METRICS:
+        if m in col:
+            lines.append(f"{m} [{units[col[m]]}] = {data[col[m]]}")
+            vals[m] = (data[col[m]], units[col[m]])
+    stalls = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_stalls.py"), path, str(kernel_index), "12"],
+                            capture_output=True, text=True).stdout
+    lines.append("")
+    lines.append("# warp stall samples (source page, SASS): mix + the 12 hottest instructions")
+    lines.extend(stalls.splitlines()[1:])
+    dst = os.path.join(OUT, f"{tag}_ncu_{name}.txt")
+    with open(dst, "w") as f:
+        f.write("\n".join(lines) + "\n")
+    print("wrote", dst)
+    if traffic is not None and traffic_key:
+        def to_bytes(v, u):
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
+            return float(v) * scale
+        r, w = vals.get("dram__bytes_read.sum"), vals.get("dram__bytes_write.sum")
+        if r and w:
+            traffic[traffic_key] = to_bytes(*r) + to_bytes(*w)
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    launches(tag)
+    traffic = {}
+    ncu_report(tag, "prof_coarse_10k.ncu-rep", "coarse_score_topk_nq10k", "coarse_score_topk", 0, traffic)
+    ncu_report(tag, "prof_coarse_128.ncu-rep", "coarse_score_topk_nq128", "coarse_score_topk_online", 0, traffic)
+    for i, nm in enumerate(["linear_qkv", "linear_oproj", "linear_ffn1_gelu", "linear_ffn2", "linear_next"]):
+        ncu_report(tag, "prof_linear.ncu-rep", nm, "linear_tcgen05" if nm == "linear_ffn1_gelu" else None, i, traffic)
+    if traffic:
+        with open(os.path.join(OUT, "traffic.json"), "w") as f:
+            json.dump(traffic, f, indent=1)
+        print("wrote traffic.json", traffic)
+
+
+if __name__ == "__main__":
+    main()

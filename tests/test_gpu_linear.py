@@ -69,3 +69,22 @@ def test_linear_tails_and_pitches(cuda_lib):
         tol = dict(atol=1e-4, rtol=1e-5) if out_f32 else dict(atol=4e-2, rtol=8e-3)
         torch.testing.assert_close(out[:M, :N].float(), ref, **tol)
         assert (out[M:] == 7.0).all() and (out[:, N:] == 7.0).all()
+
+
+def test_gelu_epilogue_is_the_erf_form(cuda_lib):
+    """The fused activation against the exact erf-GELU of uniter_model/model/layer.py:31-37 in fp64: identity weights
+    route a dense sweep of inputs straight to the epilogue.  Tolerance 5e-6 absolute (the sigmoid-of-polynomial
+    evaluation is within 3.4e-6; tanh-GELU would miss this bar by two orders of magnitude)."""
+    import math
+    lib = _lib.load()
+    K = 64
+    x = torch.linspace(-12.0, 12.0, 4096 * K, device="cuda").to(torch.float16).view(-1, K)
+    w = torch.eye(K, device="cuda", dtype=torch.float16)
+    out = torch.empty((x.shape[0], K), device="cuda", dtype=torch.float32)
+    _lib.check(lib.ldot_linear(_lib.ptr(x), K, _lib.ptr(w), K, None, None, 0, _lib.ptr(out), K, x.shape[0], K, K,
+                               0, 1, 1, _lib.stream_ptr()))
+    xd = x.double()
+    ref = 0.5 * xd * (1.0 + torch.erf(xd / math.sqrt(2.0)))
+    assert (out.double() - ref).abs().max().item() <= 5e-6
+    tanh_form = 0.5 * xd * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (xd + 0.044715 * xd ** 3)))
+    assert (tanh_form - ref).abs().max().item() > 1e-4   # (what the bar excludes)
