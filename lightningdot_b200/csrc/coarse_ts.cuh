@@ -35,7 +35,41 @@ struct TsSmem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
-template <class Epi>
+// MMA issue for one index tile when the vector length is known at compile time (KB 64-wide K blocks, KB even and
+// kTsStages == KB: a tile occupies exactly half of the ring, H selects which half and which accumulator).  Every
+// shared-memory descriptor, TMEM column and barrier address is the per-CTA base plus an immediate, so the single
+// issuing thread spends ~3 instructions per tcgen05.mma - with 64-row tiles an MMA lasts only 32 cycles and the
+// generic loop below (runtime stage / descriptor arithmetic, ~15 instructions per MMA) is issue-bound at half rate.
+template <int KB, int H>
+__device__ __forceinline__ void ts_issue_tile(uint32_t ph, uint64_t desc0, uint32_t tmem_a, uint32_t tmem_d0,
+                                              uint64_t* full, uint64_t* empty, uint64_t* tfull, uint64_t* tempty,
+                                              uint32_t idesc) {
+  constexpr int kStagesPerTile = KB / kTsKbPerStage;
+  ptx::mbar_wait(&tempty[H], ph ^ 1);
+  ptx::tc_fence_after();
+  const uint32_t tmem_d = tmem_d0 + static_cast<uint32_t>(H * kTsBN);
+#pragma unroll
+  for (int s = 0; s < kStagesPerTile; ++s) {
+    constexpr int kDescPerKb = TsSmem::kKbBytes >> 4;
+    const int stage = H * kStagesPerTile + s;
+    ptx::mbar_wait(&full[stage], ph);
+    ptx::tc_fence_after();
+#pragma unroll
+    for (int j = 0; j < kTsKbPerStage; ++j) {
+#pragma unroll
+      for (int k = 0; k < kBK / kUmmaK; ++k) {
+        const int kb = s * kTsKbPerStage + j;
+        ptx::mma_f16_ts(tmem_d, tmem_a + static_cast<uint32_t>(kb * (kBK / 2) + k * (kUmmaK / 2)),
+                        desc0 + static_cast<uint64_t>((stage * kTsKbPerStage + j) * kDescPerKb + 2 * k), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+      }
+    }
+    ptx::mma_commit(&empty[stage]);
+  }
+  ptx::mma_commit(&tfull[H]);
+}
+
+template <class Epi, int KB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sched, const TsQueries tq,
                  const typename Epi::Params ep) {
@@ -103,7 +137,26 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (A from TMEM, B from smem)
-    if (ptx::elect_one()) {
+    if constexpr (KB > 0) {
+      static_assert(KB % kTsKbPerStage == 0 && 2 * (KB / kTsKbPerStage) == kTsStages, "a tile must fill half the ring");
+      if (ptx::elect_one()) {
+        const uint64_t desc0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem));
+        uint32_t tile_idx = 0, uphase = 0;
+        for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {
+          const UnitInfo u = unit_info(sched, unit);
+          ptx::mbar_wait(a_ready, uphase);  // this unit's query tile is in TMEM
+          uphase ^= 1;
+          ptx::tc_fence_after();
+          for (int it = u.n_tile_begin; it < u.n_tile_end; ++it, ++tile_idx) {
+            const uint32_t ph = (tile_idx >> 1) & 1u;
+            if ((tile_idx & 1u) == 0)
+              ts_issue_tile<KB, 0>(ph, desc0, tmem_base, tmem_acc, full, empty, tfull, tempty, sched.idesc);
+            else
+              ts_issue_tile<KB, 1>(ph, desc0, tmem_base, tmem_acc, full, empty, tfull, tempty, sched.idesc);
+          }
+        }
+      }
+    } else if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;

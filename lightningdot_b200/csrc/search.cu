@@ -187,10 +187,74 @@ struct EpiTopK {
 };
 
 // ================================================================================================
+// 2a. threshold pre-pass epilogue: the best score of every (query, sampled index tile)
+// ================================================================================================
+// The t-th largest of a query's tile maxima over a strided sample of S index tiles is a lower bound of its t-th best
+// sample score (t different tiles each hold a row at least that good), hence a valid initial threshold for the main
+// pass: it cuts the index down to ~ t * stride rows per query without any list traffic in the pre-pass itself.
+struct TileMaxParams {
+  int n;             // valid index rows
+  int s_tiles;       // sampled tiles
+  int tile_stride;   // sampled tile i is index tile i * tile_stride
+  float* tmax;       // [m_tiles * 128][s_tiles]
+};
+
+template <int BN>
+struct EpiTileMax {
+  using Params = TileMaxParams;
+  struct State {
+    int q;
+  };
+  static __device__ __forceinline__ void unit_begin(State& st, const Params&, const UnitInfo& u, int row) {
+    st.q = u.m_tile * kBM + row;
+  }
+  static __device__ __forceinline__ void unit_end(State&, const Params&, const UnitInfo&, int) {}
+  static __device__ __forceinline__ void tile(State& st, const Params& p, const UnitInfo&, int, int nt, uint32_t taddr) {
+    const int col0 = nt * BN;
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 64) {
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld32(taddr + c, v0);
+      ptx::tmem_ld32(taddr + c + 32, v1);
+      ptx::tmem_ld_wait();
+      if (col0 + c + 64 <= p.n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + c + j < p.n) m = fmaxf(m, __uint_as_float(v0[j]));
+          if (col0 + c + 32 + j < p.n) m = fmaxf(m, __uint_as_float(v1[j]));
+        }
+      }
+    }
+    p.tmax[static_cast<size_t>(st.q) * p.s_tiles + nt / p.tile_stride] = m;
+  }
+};
+
+// one warp per query: gtau[q] = key of the t-th largest of its s_tiles tile maxima (0 = no threshold)
+__global__ void __launch_bounds__(256) tau_kernel(const float* __restrict__ tmax, int nq, int s_tiles, int t,
+                                                  unsigned int* __restrict__ gtau) {
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const float* v = tmax + static_cast<size_t>(q) * s_tiles;
+  uint32_t T = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+    for (int i = lane; i < s_tiles; i += 32) c += (fkey(__ldg(v + i)) >= cand);
+    if (__reduce_add_sync(0xFFFFFFFFu, c) >= t) T = cand;
+  }
+  if (lane == 0) gtau[q] = (s_tiles >= t && T > kKeyNegInf) ? T : 0u;
+}
+
+// ================================================================================================
 // 3. select: merge the per-chunk lists of one query into its k' best coarse candidates
 // ================================================================================================
 constexpr int kSelStage = 8192;    // entries staged in shared memory (64 KB)
-constexpr int kSelGroup = 64;      // lists merged by one block: 64 lists x k' <= 128 entries fit the stage
+constexpr int kSelGroup = 256;     // lists merged by one block (one list count per thread)
 
 // Where the candidate lists of a query live.  List c of query q holds cnt[c * cnt_sc + q * cnt_sq] entries at
 // ent + c * ent_sc + q * ent_sq.   Level 1 reads the per-unit lists of the coarse pass (c = index chunk), level 2
@@ -742,8 +806,7 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
       pl->sample = 1;
       pl->s_stride = stride;
       pl->s_tiles = (pl->n_tiles + stride - 1) / stride;
-      int sc = (sms + pl->m_tiles - 1) / pl->m_tiles;
-      if (sc > kSelGroup) sc = kSelGroup;  // single-level select
+      int sc = (sms + pl->m_tiles - 1) / pl->m_tiles;   // the pre-pass keeps no lists: chunks only spread the work
       if (sc > pl->s_tiles) sc = pl->s_tiles;
       pl->s_tiles_per_unit = (pl->s_tiles + sc - 1) / sc;
       pl->s_chunks = (pl->s_tiles + pl->s_tiles_per_unit - 1) / pl->s_tiles_per_unit;
@@ -760,21 +823,14 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->off_qstats = take(static_cast<size_t>(nq) * 2 * sizeof(float));
   pl->off_qmu = take(static_cast<size_t>(nq) * sizeof(double));
   pl->off_gtau = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(unsigned int));
-  pl->off_gtau_s = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(unsigned int));
   pl->off_flagcnt = take(sizeof(int));
-  {
-    const int max_units = pl->num_units > pl->s_units ? pl->num_units : pl->s_units;
-    pl->off_cnt = take(static_cast<size_t>(max_units) * kBM * sizeof(int));
-  }
+  pl->off_tmax = take(static_cast<size_t>(pl->m_tiles) * kBM * sizeof(float) * (pl->sample ? pl->s_tiles : 0));
+  pl->off_cnt = take(static_cast<size_t>(pl->num_units) * kBM * sizeof(int));
   pl->off_sel_idx = take(static_cast<size_t>(nq) * kp * sizeof(int));
   pl->off_sel_cmin = take(static_cast<size_t>(nq) * sizeof(float));
   pl->off_l2_ent = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * kp * sizeof(unsigned long long) : 0);
   pl->off_l2_cnt = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * sizeof(int) : 0);
-  {
-    const size_t main_b = static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long);
-    const size_t samp_b = static_cast<size_t>(pl->s_units) * kBM * 256 * sizeof(unsigned long long);
-    pl->off_cand = take(main_b > samp_b ? main_b : samp_b);
-  }
+  pl->off_cand = take(static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long));
   pl->total_bytes = off;
   return kOk;
 }
@@ -798,14 +854,63 @@ static int launch_coarse_ss(const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int EPL>
 static int launch_coarse_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TopKParams& p, int sms,
                             cudaStream_t st) {
-  auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>>;
-  static bool configured = false;  // (one device per process)
+  const int grid = s.num_units < sms ? s.num_units : sms;
+  if (s.k_blocks == kTsStages) {  // d in (704, 768]: the fully unrolled issue loop
+    auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>, kTsStages>;
+    static bool configured = false;  // (one device per process)
+    if (!configured) {
+      LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+  } else {
+    auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>, 0>;
+    static bool configured = false;
+    if (!configured) {
+      LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+  }
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+static int launch_tilemax_ss(const CUtensorMap& ta, const CUtensorMap& tb, const GemmSched& s, const TileMaxParams& p,
+                             int sms, cudaStream_t st) {
+  using SM = GemmSmem<kSearchBN, kSearchStages>;
+  auto kern = gemm_tc_kernel<EpiTileMax<kSearchBN>, kSearchBN, kSearchStages>;
+  static bool configured = false;
   if (!configured) {
-    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
     configured = true;
   }
   const int grid = s.num_units < sms ? s.num_units : sms;
-  kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+  kern<<<grid, kGemmThreads, SM::kDynamic, st>>>(ta, tb, s, p);
+  LDOT_CHECK_LAUNCH();
+  return kOk;
+}
+
+static int launch_tilemax_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TileMaxParams& p, int sms,
+                             cudaStream_t st) {
+  const int grid = s.num_units < sms ? s.num_units : sms;
+  if (s.k_blocks == kTsStages) {
+    auto kern = coarse_ts_kernel<EpiTileMax<kTsBN>, kTsStages>;
+    static bool configured = false;
+    if (!configured) {
+      LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+  } else {
+    auto kern = coarse_ts_kernel<EpiTileMax<kTsBN>, 0>;
+    static bool configured = false;
+    if (!configured) {
+      LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+  }
   LDOT_CHECK_LAUNCH();
   return kOk;
 }
@@ -835,8 +940,8 @@ int search_run(const SearchArgs& a) {
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
   const int nq = static_cast<int>(a.nq);
 
-  // gtau, gtau_s and the flag counter are adjacent in the plan: one memset clears them
-  unsigned int* gtau_s = reinterpret_cast<unsigned int*>(ws + pl.off_gtau_s);
+  // gtau and the flag counter are adjacent in the plan: one memset clears both
+  float* tmax = reinterpret_cast<float*>(ws + pl.off_tmax);
   LDOT_CUDA(cudaMemsetAsync(gtau, 0, (pl.off_flagcnt - pl.off_gtau) + sizeof(int), st));
   const int qblocks = (nq + 7) / 8;
   {
@@ -910,21 +1015,27 @@ int search_run(const SearchArgs& a) {
   tp.cand_cnt = cnt;
 
   if (pl.sample) {
-    // threshold pre-pass: the s_kprime-th best score of every query over a strided sample of the index tiles
+    // threshold pre-pass: tile maxima over a strided sample of the index tiles -> initial gtau[q]
     s.n_tiles = pl.s_tiles;
     s.tiles_per_unit = pl.s_tiles_per_unit;
     s.chunks = pl.s_chunks;
     s.num_units = pl.s_units;
     s.tile_stride = pl.s_stride;
-    tp.kprime = pl.s_kprime;
-    tp.cap = 256;
-    tp.gtau = gtau_s;
-    const double s_rows = static_cast<double>(pl.s_tiles) * pl.bn;
-    if (int e = run_coarse(s, tp, 8, s_rows < static_cast<double>(a.n) ? s_rows : static_cast<double>(a.n))) return e;
+    TileMaxParams mp;
+    mp.n = static_cast<int>(a.n);
+    mp.s_tiles = pl.s_tiles;
+    mp.tile_stride = pl.s_stride;
+    mp.tmax = tmax;
+    double s_rows = static_cast<double>(pl.s_tiles) * pl.bn;
+    if (s_rows > static_cast<double>(a.n)) s_rows = static_cast<double>(a.n);
+    {
+      KernelScope ks(kKcCoarse, st, 2.0 * nq * s_rows * a.d, (s_rows + nq) * a.d * 2.0);
+      const int e = pl.a_in_tmem ? launch_tilemax_ts(tb, s, tq, mp, sms, st) : launch_tilemax_ss(ta, tb, s, mp, sms, st);
+      if (e) return e;
+    }
     {
       KernelScope ks(kKcSelect, st);
-      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(lists_of(pl.s_chunks, 256), gtau_s, pl.s_kprime, 1, nullptr,
-                                                        nullptr, sel_idx, sel_cmin, gtau);
+      tau_kernel<<<(nq + 7) / 8, 256, 0, st>>>(tmax, nq, pl.s_tiles, pl.s_kprime, gtau);
     }
     LDOT_CHECK_LAUNCH();
   }

@@ -22,7 +22,7 @@ struct SearchPlan {
   int s_stride;        // every s_stride-th index tile is sampled
   int s_tiles, s_tiles_per_unit, s_chunks, s_units;
   int s_kprime;        // the s_kprime-th best sample score of a query seeds its threshold
-  size_t off_gtau_s;
+  size_t off_tmax;     // tile maxima of the pre-pass [m_tiles * 128][s_tiles] fp32
   size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_l2_ent,
       off_l2_cnt, off_cand;
   size_t total_bytes;
