@@ -94,6 +94,14 @@ int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, cons
                 const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
                 int32_t dtype, int32_t act, int32_t out_f32, void* stream);
 
+/* ---- Linear + residual + LayerNorm fused: replaces BertSelfOutput / BertOutput (uniter_model/model/layer.py:104-115,
+ * 145-156):  out[M, N] = LayerNorm(A . W^T + bias + residual) * gamma + beta, eps 1e-12, 16-bit output of `dtype`.
+ * N % 32 == 0 and N <= 1024 (the 128-row block is shared by a cluster of ceil(N / 256) CTAs that exchange fp32 row
+ * statistics through distributed shared memory); bias / residual may be NULL; gamma / beta fp32 [N].              */
+int ldot_linear_ln(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
+                   const void* d_residual, int64_t ldr, const float* d_gamma, const float* d_beta, void* d_out,
+                   int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype, void* stream);
+
 /* ---- the rest of the tower arithmetic (16-bit activations of `dtype`, fp32 statistics) -------------------------
  * ldot_layernorm   out[rows, H] = LayerNorm(in[rows, H]) * gamma + beta, eps 1e-12 (layer.py:108-115,149-156);
  *                  `in` is fp32 when in_f32 != 0, else 16-bit; ld_* are row pitches in elements; H = 256 * {1,2,3,4,6,8}

@@ -39,6 +39,8 @@ SIGNATURES = {
     "ldot_topk_merge": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
     "ldot_linear": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                               c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_linear_ln": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_layernorm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                  c_int32, c_void_p]),
     "ldot_embed_text": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -49,6 +49,23 @@ int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint
   return kOk;
 }
 
+int make_tmap_kblocks_16b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                          uint32_t box_rows, uint32_t box_kb) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(kErrCuda, "cuTensorMapEncodeTiled entry point not available");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride_bytes % 16 == 0, "TMA alignment");
+  LDOT_REQUIRE(cols % 64 == 0 && box_rows >= 1 && box_rows <= 256 && box_kb >= 1 && box_kb <= 256, "bad 3-D box");
+  const cuuint64_t gdim[3] = {64, rows, cols / 64};
+  const cuuint64_t gstride[2] = {row_stride_bytes, 128};
+  const cuuint32_t box[3] = {64, box_rows, box_kb};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(kErrCuda, "cuTensorMapEncodeTiled (3-D) failed with CUresult %d", (int)r);
+  return kOk;
+}
+
 int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,
                     uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
@@ -172,6 +189,9 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
 }
 
 namespace ldot {
+int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
+                  long long ldr, const float* gamma, const float* beta, void* out, long long ldo, long long M, int N,
+                  int K, int fmt, void* stream);
 }  // namespace ldot
 #include "encoder_params.h"
 namespace ldot {
@@ -315,6 +335,13 @@ int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, cons
                 int32_t dtype, int32_t act, int32_t out_f32, void* stream) {
   LDOT_REQUIRE(d_a && d_w && d_out, "null pointer argument");
   return linear_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_out, ldo, M, N, K, dtype, act, out_f32, stream);
+}
+
+int ldot_linear_ln(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, const void* d_residual,
+                   int64_t ldr, const float* d_gamma, const float* d_beta, void* d_out, int64_t ldo, int64_t M, int32_t N,
+                   int32_t K, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_a && d_w && d_out && d_gamma && d_beta, "null pointer argument");
+  return linear_ln_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_gamma, d_beta, d_out, ldo, M, N, K, dtype, stream);
 }
 
 int ldot_layernorm(const void* d_in, int64_t ld_in, int32_t in_f32, const float* d_gamma, const float* d_beta,

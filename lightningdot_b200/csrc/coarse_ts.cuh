@@ -17,8 +17,9 @@
 namespace ldot {
 
 constexpr int kTsBN = 64;          // index rows per MMA (UMMA N)
-constexpr int kTsKbPerStage = 2;   // 64-wide K blocks per smem stage (2 x 8 KB)
-constexpr int kTsStages = 12;      // 12 x 16 KB = 192 KB in flight
+constexpr int kTsKbPerStage = 4;   // 64-wide K blocks per smem stage (4 x 8 KB)
+constexpr int kTsStages = 6;       // 6 x 32 KB = 192 KB in flight
+constexpr int kTsFastKb = 12;      // K blocks of the compile-time specialised kernel (d = 768): two tiles per ring revolution
 constexpr int kTsACols = 384;      // TMEM columns holding the query tile (K <= 768)
 constexpr int kTsMaxD = kTsACols * 2;
 
@@ -35,8 +36,25 @@ struct TsSmem {
   static constexpr int kDynamic = kTotal + 1024;
 };
 
-// MMA issue for one index tile when the vector length is known at compile time (KB 64-wide K blocks, KB even and
-// kTsStages == KB: a tile occupies exactly half of the ring, H selects which half and which accumulator).  Every
+// TMA issue for one index tile on the compile-time path (see ts_issue_tile): one 3-D TMA instruction per stage lands
+// kTsKbPerStage consecutive [64 rows x 64 K] swizzled tiles.
+template <int KB, int H>
+__device__ __forceinline__ void ts_load_tile(uint32_t ph, uint8_t* smem, const CUtensorMap* tmap3, uint64_t* full,
+                                             uint64_t* empty, int row0) {
+  constexpr int kStagesPerTile = KB / kTsKbPerStage;
+#pragma unroll
+  for (int s = 0; s < kStagesPerTile; ++s) {
+    const int stage = H * kStagesPerTile + s;
+    ptx::mbar_wait(&empty[stage], ph ^ 1);
+    ptx::mbar_arrive_expect_tx(&full[stage], TsSmem::kStageBytes);
+    ptx::tma_load_3d(smem + stage * TsSmem::kStageBytes, tmap3, &full[stage], 0, row0, s * kTsKbPerStage,
+                     ptx::kEvictNormal);
+  }
+}
+
+// MMA issue for one index tile when the vector length is known at compile time (KB 64-wide K blocks, a multiple of
+// kTsKbPerStage with 2 * KB / kTsKbPerStage == kTsStages: a tile occupies exactly half of the ring, H selects which
+// half and which accumulator).  Every
 // shared-memory descriptor, TMEM column and barrier address is the per-CTA base plus an immediate, so the single
 // issuing thread spends ~3 instructions per tcgen05.mma - with 64-row tiles an MMA lasts only 32 cycles and the
 // generic loop below (runtime stage / descriptor arithmetic, ~15 instructions per MMA) is issue-bound at half rate.
@@ -71,8 +89,8 @@ __device__ __forceinline__ void ts_issue_tile(uint32_t ph, uint64_t desc0, uint3
 
 template <class Epi, int KB>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sched, const TsQueries tq,
-                 const typename Epi::Params ep) {
+coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b3,
+                 const GemmSched sched, const TsQueries tq, const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + TsSmem::kBarOffset);
@@ -98,7 +116,7 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
     ptx::mbar_init(a_ready, 128);
     ptx::fence_mbar_init();
   }
-  if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_b);
+  if (warp == 0 && lane == 0) ptx::prefetch_tmap(KB > 0 ? &tmap_b3 : &tmap_b);
   if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr, 512);
     ptx::tmem_relinquish();
@@ -111,7 +129,20 @@ coarse_ts_kernel(const __grid_constant__ CUtensorMap tmap_b, const GemmSched sch
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (index rows only)
-    if (ptx::elect_one()) {
+    if constexpr (KB > 0) {
+      if (ptx::elect_one()) {
+        uint32_t tile_idx = 0;
+        for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {
+          const UnitInfo u = unit_info(sched, unit);
+          for (int it = 0; it < u.n_tile_end - u.n_tile_begin; ++it, ++tile_idx) {
+            const int row0 = unit_tile(u, it) * sched.tile_stride * kTsBN;
+            const uint32_t ph = (tile_idx >> 1) & 1u;
+            if ((tile_idx & 1u) == 0) ts_load_tile<KB, 0>(ph, smem, &tmap_b3, full, empty, row0);
+            else ts_load_tile<KB, 1>(ph, smem, &tmap_b3, full, empty, row0);
+          }
+        }
+      }
+    } else if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int unit = blockIdx.x; unit < sched.num_units; unit += gridDim.x) {

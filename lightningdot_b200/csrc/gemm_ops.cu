@@ -6,6 +6,7 @@
 // bias / erf-GELU / residual add fused in the epilogue, 16-bit or fp32 output written by TMA stores.
 // The kernel is linear_tc.cuh; this file is its host side.
 #include "linear_tc.cuh"
+#include "linear_ln.cuh"
 #include "host_common.h"
 #include "prof.h"
 
@@ -65,6 +66,77 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
                      (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
   if (act == 1) return out_f32 ? launch_linear<1, 1>(ta, tw, to, s, p, sms, st) : launch_linear<1, 0>(ta, tw, to, s, p, sms, st);
   return out_f32 ? launch_linear<0, 1>(ta, tw, to, s, p, sms, st) : launch_linear<0, 0>(ta, tw, to, s, p, sms, st);
+}
+
+// out = LayerNorm(A . W^T + bias + residual) * gamma + beta, 16-bit output; a cluster of ceil(N / 256) CTAs per row block
+int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
+                  long long ldr, const float* gamma, const float* beta, void* out, long long ldo, long long M, int N,
+                  int K, int fmt, void* stream) {
+  LDOT_REQUIRE(M >= 1 && N >= 32 && K >= 8, "bad GEMM shape M=%lld N=%d K=%d", M, N, K);
+  LDOT_REQUIRE(N % 32 == 0 && N <= kLnMaxCluster * kLinBN, "linear+LayerNorm needs N %% 32 == 0 and N <= %d, got %d",
+               kLnMaxCluster * kLinBN, N);
+  LDOT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0, "K, lda, ldw, ldo must be multiples of 8");
+  LDOT_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE(gamma && beta, "gamma / beta are required");
+  LDOT_REQUIRE(!residual || ldr % 8 == 0, "ldr alignment");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gamma) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(beta) & 15) == 0,
+               "out / residual / bias / gamma / beta must be 16-byte aligned");
+  LDOT_REQUIRE(M < (1ll << 31) - 128, "M too large");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int C = (N + kLinBN - 1) / kLinBN;
+  CUtensorMap ta, tw, to;
+  if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
+  if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN)) return e;
+  if (int e = make_tmap_store(&to, out, 2, M, N, static_cast<uint64_t>(ldo) * 2, 32, 32)) return e;
+
+  static bool configured = false;
+  static int max_clusters[kLnMaxCluster + 1] = {0};
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(linear_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LnSmem::kDynamic));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(C);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = LnSmem::kDynamic;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[C] == 0) {
+    // how many clusters of C CTAs (one CTA per SM) the device keeps resident: the persistent grid must not exceed it
+    cfg.gridDim = dim3(static_cast<unsigned>(C));
+    int n = 0;
+    LDOT_CUDA(cudaOccupancyMaxActiveClusters(&n, linear_ln_kernel, &cfg));
+    LDOT_REQUIRE(n >= 1, "no resident cluster of %d CTAs possible", C);
+    max_clusters[C] = n;
+  }
+  LnSched s;
+  s.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  s.k_blocks = (K + kBK - 1) / kBK;
+  s.cluster = C;
+  s.num_clusters = s.m_tiles < max_clusters[C] ? s.m_tiles : max_clusters[C];
+  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM, kLinBN);
+  LnParams p;
+  p.bias = bias;
+  p.residual = residual;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.ldr = ldr;
+  p.M = M;
+  p.N = N;
+  p.fmt = fmt;
+  cfg.gridDim = dim3(static_cast<unsigned>(s.num_clusters * C));
+  KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
+                 (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * 2.0 +
+                     (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
+  LDOT_CUDA(cudaLaunchKernelEx(&cfg, linear_ln_kernel, ta, tw, to, s, p));
+  return kOk;
 }
 
 }  // namespace ldot

@@ -48,6 +48,11 @@ inline int set_error(int code, const char* fmt, ...) {
 int make_tmap_kmajor_16b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                          uint64_t row_stride_bytes, uint32_t box_rows);
 
+// 3-D view of a K-major 16-bit matrix whose row length is a multiple of 64: [64 (k in block), rows, cols / 64 (k block)],
+// box = [64, box_rows, box_kb]: one TMA instruction lands box_kb consecutive [box_rows x 64] SWIZZLE_128B tiles.
+int make_tmap_kblocks_16b(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                          uint32_t box_rows, uint32_t box_kb);
+
 // 2-D tensor map of a row-major [rows, cols] matrix of `elt_bytes`-wide elements for TMA stores of
 // [box_rows, box_cols] boxes whose inner extent (box_cols * elt_bytes) is 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B).
 int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,

@@ -1,0 +1,311 @@
+// Encoder Linear + residual + LayerNorm in one kernel:
+//
+//     out[M, N] = LayerNorm(A[M, K] . W[N, K]^T + bias + residual) * gamma + beta          (N <= 1024, eps 1e-12)
+//
+// i.e. BertSelfOutput / BertOutput (uniter_model/model/layer.py:104-115, 145-156) without the fp32 round trip of the
+// pre-LayerNorm sums through HBM and without a separate LayerNorm launch.
+//
+// A 128 x N fp32 accumulator needs N tensor-memory columns and an SM has 512 (two 256-column buffers), so the row
+// block is shared by a CLUSTER of C = ceil(N / 256) CTAs: CTA r owns output columns [256 r, 256 r + 256) and the same
+// 128 rows.  Per row block every CTA runs the usual TMA -> tcgen05.mma pipeline for its n-tile (the C CTAs stream the
+// same A tile at the same time, so it is served from L2 once), then its eight epilogue warps make TWO passes over
+// the accumulator in TMEM:
+//   pass 1   x = acc + bias + residual  ->  per-row partial (sum x, sum x^2) over the warp's 128 columns, written
+//            into the statistics table of EVERY CTA of the cluster (st.shared::cluster) and signalled with a
+//            cluster-scope mbarrier arrive;
+//   pass 2   once all 2 C partials of a row have arrived: mean / rstd, x recomputed from TMEM, normalised, scaled,
+//            packed to 16 bit, staged (swizzled) in shared memory and written with one TMA store per 32 x 32 box.
+// Statistics are exact fp32 sums of the fp32 x (nothing is rounded to 16 bit before the normalisation).
+// Warp roles and pipelines are those of linear_tc.cuh (warp 0 TMA, warp 1 MMA, warps 2..9 epilogue).
+#pragma once
+#include "linear_tc.cuh"
+
+namespace ldot {
+
+constexpr int kLnMaxCluster = 4;
+constexpr float kLnEpsF = 1e-12f;
+
+struct LnSched {
+  int m_tiles, k_blocks, num_clusters, cluster;  // cluster = C
+  uint32_t idesc;
+};
+
+struct LnParams {
+  const float* bias;      // [N] or null
+  const void* residual;   // [M, ldr] 16-bit of `fmt`, or null
+  const float* gamma;     // [N]
+  const float* beta;      // [N]
+  long long ldr;
+  long long M;
+  int N;
+  int fmt;
+};
+
+struct LnSmem {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = kLinBN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingPerWarp = 2048;         // one 32 x 32 16-bit box
+  static constexpr int kStagingOffset = kLinStages * kStageBytes;
+  static constexpr int kStatsOffset = kStagingOffset + kLinEpiWarps * kStagingPerWarp;
+  // [2 tile parities][C * 2 column halves][128 rows] float2
+  static constexpr int kStatsBytes = 2 * kLnMaxCluster * 2 * kBM * 8;
+  static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kLinStages + 4 + 2) * 8 + 16;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+static_assert(LnSmem::kDynamic <= 227 * 1024, "linear+LN kernel shared memory");
+
+__global__ void __launch_bounds__(kLinThreads, 1)
+linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_out, const LnSched sched, const LnParams p) {
+  using SM = LnSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kLinStages * SM::kABytes;
+  float2* stats = reinterpret_cast<float2*>(smem + SM::kStatsOffset);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
+  uint64_t* empty = full + kLinStages;
+  uint64_t* tfull = empty + kLinStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* sbar = tempty + 2;  // [2] statistics of tile parity b complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sbar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int C = sched.cluster;
+  const int rank = static_cast<int>(ptx::cluster_ctarank());  // = n-tile of this CTA
+  const int cluster_id = blockIdx.x / C;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kLinStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], kLinEpiWarps);
+      ptx::mbar_init(&sbar[i], static_cast<uint32_t>(C * kLinEpiWarps * 32));  // every epilogue lane of every CTA
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmap_a);
+    ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_out);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // remote arrives must find initialised barriers
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
+        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
+          ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
+                           ptx::kEvictNormal);
+          ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, rank * kLinBN,
+                           ptx::kEvictLast);
+          if (++stage == kLinStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
+        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
+          const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * SM::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit(&empty[stage]);
+          if (++stage == kLinStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::mma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps, two passes per tile)
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    uint8_t* staging = smem + SM::kStagingOffset + (warp - 2) * SM::kStagingPerWarp;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int col_base = rank * kLinBN + half * (kLinBN / 2);
+    int nchunks = (p.N - col_base + 31) / 32;  // N % 32 == 0 (host-checked): chunks are full or absent
+    nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+    const float inv_n = 1.0f / static_cast<float>(p.N);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
+      const long long grow = static_cast<long long>(m_tile) * kBM + row;
+      const bool row_ok = grow < p.M;
+      const uint16_t* res_row =
+          p.residual != nullptr ? static_cast<const uint16_t*>(p.residual) + (row_ok ? grow : 0) * p.ldr : nullptr;
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
+
+      // x = acc + bias + residual for one 32-column chunk (identical arithmetic in both passes)
+      auto load_x = [&](int cc, float (&f)[32]) {
+        const int col = col_base + cc * 32;
+        uint32_t v[32];
+        ptx::tmem_ld32(taddr + cc * 32, v);
+        float4 b4[8];
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+        }
+        uint4 r4[4];
+        if (res_row != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) r4[j] = __ldg(reinterpret_cast<const uint4*>(res_row + col) + j);
+        }
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[4 * j] += b4[j].x;
+            f[4 * j + 1] += b4[j].y;
+            f[4 * j + 2] += b4[j].z;
+            f[4 * j + 3] += b4[j].w;
+          }
+        }
+        if (res_row != nullptr) {
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 x = unpack2(w[q], p.fmt);
+              f[j4 * 8 + q * 2] += x.x;
+              f[j4 * 8 + q * 2 + 1] += x.y;
+            }
+          }
+        }
+      };
+
+      // ---- pass 1: partial row statistics, broadcast to the whole cluster
+      float s1 = 0.f, s2 = 0.f;
+      for (int cc = 0; cc < nchunks; ++cc) {
+        float f[32];
+        load_x(cc, f);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s1 += f[j];
+          s2 = fmaf(f[j], f[j], s2);
+        }
+      }
+      {
+        const uint32_t slot = ptx::smem_u32(stats + (as * 2 * kLnMaxCluster + rank * 2 + half) * kBM + row);
+        const uint32_t bar = ptx::smem_u32(&sbar[as]);
+        for (int c = 0; c < C; ++c) {
+          ptx::st_cluster_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2);
+          ptx::mbar_arrive_cluster(ptx::mapa(bar, static_cast<uint32_t>(c)));
+        }
+      }
+      ptx::mbar_wait_cluster(&sbar[as], aphase);
+      float t1 = 0.f, t2 = 0.f;
+      for (int i = 0; i < 2 * C; ++i) {
+        const float2 s = stats[(as * 2 * kLnMaxCluster + i) * kBM + row];
+        t1 += s.x;
+        t2 += s.y;
+      }
+      const float mean = t1 * inv_n;
+      const float var = fmaxf(t2 * inv_n - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + kLnEpsF);
+
+      // ---- pass 2: normalise, scale, pack, store
+      if (nchunks == 0) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      }
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int col = col_base + cc * 32;
+        float f[32];
+        load_x(cc, f);
+        if (cc == nchunks - 1) {  // accumulator drained for good
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col) + j);
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col) + j);
+          f[4 * j] = fmaf((f[4 * j] - mean) * rstd, g.x, b.x);
+          f[4 * j + 1] = fmaf((f[4 * j + 1] - mean) * rstd, g.y, b.y);
+          f[4 * j + 2] = fmaf((f[4 * j + 2] - mean) * rstd, g.z, b.z);
+          f[4 * j + 3] = fmaf((f[4 * j + 3] - mean) * rstd, g.w, b.w);
+        }
+        if (lane == 0) ptx::bulk_wait_group_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 w;
+          w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
+          w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
+          w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
+          w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
+          *reinterpret_cast<uint4*>(staging + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_2d(&tmap_out, staging, col, m_tile * kBM + quarter * 32);
+          ptx::bulk_commit_group();
+        }
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<0>();
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();  // no CTA may retire while a peer can still write its statistics table / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ldot

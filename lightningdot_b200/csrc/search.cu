@@ -852,17 +852,17 @@ static int launch_coarse_ss(const CUtensorMap& ta, const CUtensorMap& tb, const 
 }
 
 template <int EPL>
-static int launch_coarse_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TopKParams& p, int sms,
-                            cudaStream_t st) {
+static int launch_coarse_ts(const CUtensorMap& tb, const CUtensorMap* tb3, const GemmSched& s, const TsQueries& tq,
+                            const TopKParams& p, int sms, cudaStream_t st) {
   const int grid = s.num_units < sms ? s.num_units : sms;
-  if (s.k_blocks == kTsStages) {  // d in (704, 768]: the fully unrolled issue loop
-    auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>, kTsStages>;
+  if (tb3) {  // d == 768: compile-time unrolled TMA / MMA issue loops
+    auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>, kTsFastKb>;
     static bool configured = false;  // (one device per process)
     if (!configured) {
       LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
       configured = true;
     }
-    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, *tb3, s, tq, p);
   } else {
     auto kern = coarse_ts_kernel<EpiTopK<EPL, kTsBN>, 0>;
     static bool configured = false;
@@ -870,7 +870,7 @@ static int launch_coarse_ts(const CUtensorMap& tb, const GemmSched& s, const TsQ
       LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
       configured = true;
     }
-    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, tb, s, tq, p);
   }
   LDOT_CHECK_LAUNCH();
   return kOk;
@@ -891,17 +891,17 @@ static int launch_tilemax_ss(const CUtensorMap& ta, const CUtensorMap& tb, const
   return kOk;
 }
 
-static int launch_tilemax_ts(const CUtensorMap& tb, const GemmSched& s, const TsQueries& tq, const TileMaxParams& p, int sms,
-                             cudaStream_t st) {
+static int launch_tilemax_ts(const CUtensorMap& tb, const CUtensorMap* tb3, const GemmSched& s, const TsQueries& tq,
+                             const TileMaxParams& p, int sms, cudaStream_t st) {
   const int grid = s.num_units < sms ? s.num_units : sms;
-  if (s.k_blocks == kTsStages) {
-    auto kern = coarse_ts_kernel<EpiTileMax<kTsBN>, kTsStages>;
+  if (tb3) {
+    auto kern = coarse_ts_kernel<EpiTileMax<kTsBN>, kTsFastKb>;
     static bool configured = false;
     if (!configured) {
       LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
       configured = true;
     }
-    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, *tb3, s, tq, p);
   } else {
     auto kern = coarse_ts_kernel<EpiTileMax<kTsBN>, 0>;
     static bool configured = false;
@@ -909,7 +909,7 @@ static int launch_tilemax_ts(const CUtensorMap& tb, const GemmSched& s, const Ts
       LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TsSmem::kDynamic));
       configured = true;
     }
-    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, s, tq, p);
+    kern<<<grid, kGemmThreads, TsSmem::kDynamic, st>>>(tb, tb, s, tq, p);
   }
   LDOT_CHECK_LAUNCH();
   return kOk;
@@ -958,6 +958,13 @@ int search_run(const SearchArgs& a) {
   if (int e = make_tmap_kmajor_16b(&tb, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, pl.bn)) return e;
   if (!pl.a_in_tmem)
     if (int e = make_tmap_kmajor_16b(&ta, q16, a.nq, a.d, static_cast<uint64_t>(a.d) * 2, kBM)) return e;
+  // d == 768: 3-D view of the index for the compile-time unrolled kernel (one TMA instruction per 4 K blocks)
+  CUtensorMap tb3;
+  const CUtensorMap* tb3p = nullptr;
+  if (pl.a_in_tmem && a.d == kTsFastKb * kBK) {
+    if (int e = make_tmap_kblocks_16b(&tb3, a.x16, a.n, a.d, static_cast<uint64_t>(a.d) * 2, kTsBN, kTsKbPerStage)) return e;
+    tb3p = &tb3;
+  }
   TsQueries tq;
   tq.q16 = static_cast<const uint16_t*>(q16);
   tq.nq = nq;
@@ -969,10 +976,10 @@ int search_run(const SearchArgs& a) {
     KernelScope coarse_scope(kKcCoarse, st, 2.0 * nq * rows * a.d, (rows + nq) * a.d * 2.0);
     if (pl.a_in_tmem) {
       switch (epl) {
-        case 8: return launch_coarse_ts<8>(tb, s, tq, tp, sms, st);
-        case 16: return launch_coarse_ts<16>(tb, s, tq, tp, sms, st);
-        case 32: return launch_coarse_ts<32>(tb, s, tq, tp, sms, st);
-        default: return launch_coarse_ts<80>(tb, s, tq, tp, sms, st);
+        case 8: return launch_coarse_ts<8>(tb, tb3p, s, tq, tp, sms, st);
+        case 16: return launch_coarse_ts<16>(tb, tb3p, s, tq, tp, sms, st);
+        case 32: return launch_coarse_ts<32>(tb, tb3p, s, tq, tp, sms, st);
+        default: return launch_coarse_ts<80>(tb, tb3p, s, tq, tp, sms, st);
       }
     }
     switch (epl) {
@@ -1030,7 +1037,7 @@ int search_run(const SearchArgs& a) {
     if (s_rows > static_cast<double>(a.n)) s_rows = static_cast<double>(a.n);
     {
       KernelScope ks(kKcCoarse, st, 2.0 * nq * s_rows * a.d, (s_rows + nq) * a.d * 2.0);
-      const int e = pl.a_in_tmem ? launch_tilemax_ts(tb, s, tq, mp, sms, st) : launch_tilemax_ss(ta, tb, s, mp, sms, st);
+      const int e = pl.a_in_tmem ? launch_tilemax_ts(tb, tb3p, s, tq, mp, sms, st) : launch_tilemax_ss(ta, tb, s, mp, sms, st);
       if (e) return e;
     }
     {

@@ -22,13 +22,16 @@ def _fmt_of(dtype):
 
 
 class TowerEngine:
-    def __init__(self, kind, hidden, heads, ffn, layers, dtype=torch.bfloat16, pre_ln_f32=True):
+    def __init__(self, kind, hidden, heads, ffn, layers, dtype=torch.bfloat16, pre_ln_f32=True, fuse_ln=True):
         assert kind in ("txt", "img")
         if hidden != heads * 64:
             raise ValueError("the attention kernel needs head_dim == 64")
         self.kind, self.H, self.heads, self.ffn, self.layers = kind, hidden, heads, ffn, layers
         self.dtype, self.fmt = dtype, _fmt_of(dtype)
         self.pre_ln_f32 = pre_ln_f32
+        # fuse_ln: BertSelfOutput / BertOutput as ONE kernel (GEMM + bias + residual + LayerNorm, cluster of 3 CTAs per
+        # row block); otherwise GEMM (+bias +residual, fp32 or 16-bit sums) followed by the LayerNorm kernel
+        self.fuse_ln = fuse_ln and hidden % 32 == 0 and hidden <= 1024
         self.w = None
         self.signature = None
 
@@ -90,6 +93,13 @@ class TowerEngine:
                                    0 if residual is None else residual.stride(0), _lib.ptr(out), out.stride(0),
                                    M, N, K, self.fmt, act, int(out.dtype == torch.float32), _lib.stream_ptr()))
 
+    def _linear_ln(self, a, lda, wt, bias, residual, gamma, beta, out, M):
+        lib = _lib.load()
+        N, K = wt.shape
+        _lib.check(lib.ldot_linear_ln(_lib.ptr(a), lda, _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(residual),
+                                      residual.stride(0), _lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(out), out.stride(0),
+                                      M, N, K, self.fmt, _lib.stream_ptr()))
+
     def _layernorm(self, x, g, b, out, rows, H):
         lib = _lib.load()
         _lib.check(lib.ldot_layernorm(_lib.ptr(x), x.stride(0), int(x.dtype == torch.float32), _lib.ptr(g), _lib.ptr(b),
@@ -102,13 +112,18 @@ class TowerEngine:
         w = self.w
         qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
         ctx = torch.empty((T, H), dtype=dt, device=dev)
-        pre = torch.empty((T, H), dtype=torch.float32 if self.pre_ln_f32 else dt, device=dev)
+        pre = None if self.fuse_ln else torch.empty((T, H), dtype=torch.float32 if self.pre_ln_f32 else dt, device=dev)
         a = torch.empty((T, H), dtype=dt, device=dev)
         f = torch.empty((T, self.ffn), dtype=dt, device=dev)
         stream = _lib.stream_ptr()
         for i in range(self.layers):
             self._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
             _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, self.heads, self.fmt, stream))
+            if self.fuse_ln:
+                self._linear_ln(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], h, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T)
+                self._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f, T, act=1)
+                self._linear_ln(f, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], a, w[f"ln2_g{i}"], w[f"ln2_b{i}"], h, T)
+                continue
             self._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre, T, residual=h)
             self._layernorm(pre, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
             self._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f, T, act=1)

@@ -88,3 +88,34 @@ def test_gelu_epilogue_is_the_erf_form(cuda_lib):
     assert (out.double() - ref).abs().max().item() <= 5e-6
     tanh_form = 0.5 * xd * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (xd + 0.044715 * xd ** 3)))
     assert (tanh_form - ref).abs().max().item() > 1e-4   # (what the bar excludes)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 768, 768), (300, 768, 3072), (4097, 768, 768), (77, 256, 64), (1000, 1024, 128),
+                                   (130, 96, 72)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_linear_layernorm_fused(cuda_lib, M, N, K, fmt):
+    """ldot_linear_ln = LayerNorm(A W^T + bias + residual) * gamma + beta against fp32 torch.  The statistics are exact
+    fp32 sums of the fp32 pre-LayerNorm values, so the only error is the final 16-bit rounding (2^-9 / 2^-12 relative)
+    plus fp32 summation-order noise."""
+    lib = _lib.load()
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dt)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(dt)
+    b = torch.randn(N, device="cuda", generator=g)
+    r = (torch.randn(M, N, device="cuda", generator=g) + 0.3).to(dt)
+    gamma = 1.0 + 0.1 * torch.randn(N, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M + 2, N), 7.0, device="cuda", dtype=dt)
+    _lib.check(lib.ldot_linear_ln(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(r), N, _lib.ptr(gamma), _lib.ptr(beta),
+                                  _lib.ptr(out), N, M, N, K, fmt, _lib.stream_ptr()))
+    x = a.float() @ w.float().t() + b + r.float()
+    ref = torch.nn.functional.layer_norm(x, (N,), gamma, beta, 1e-12)
+    tol = dict(atol=4e-3, rtol=2e-3) if fmt == 0 else dict(atol=3e-2, rtol=8e-3)
+    torch.testing.assert_close(out[:M].float(), ref, **tol)
+    assert (out[M:] == 7.0).all()
+    # no bias / no residual
+    _lib.check(lib.ldot_linear_ln(_lib.ptr(a), K, _lib.ptr(w), K, None, None, 0, _lib.ptr(gamma), _lib.ptr(beta),
+                                  _lib.ptr(out), N, M, N, K, fmt, _lib.stream_ptr()))
+    ref2 = torch.nn.functional.layer_norm(a.float() @ w.float().t(), (N,), gamma, beta, 1e-12)
+    torch.testing.assert_close(out[:M].float(), ref2, **tol)
