@@ -12,6 +12,34 @@
 
 namespace ldot {
 
+// 256 x 256 identity matrices (fp16 / bf16 1.0 = 0x3C00 / 0x3F80): the B operand that lets the tensor core add the
+// residual tile.  Module-scope device memory, filled on first use (the library never allocates).
+__device__ uint16_t g_eye[2][kLinBN * kLinBN];
+
+__global__ void eye_init_kernel() {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kLinBN * kLinBN) {
+    const bool diag = (i / kLinBN) == (i % kLinBN);
+    g_eye[0][i] = diag ? 0x3C00 : 0;
+    g_eye[1][i] = diag ? 0x3F80 : 0;
+  }
+}
+
+static int eye_pointer(int fmt, cudaStream_t st, const uint16_t** out) {
+  static const uint16_t* base = nullptr;
+  if (!base) {
+    void* p = nullptr;
+    LDOT_CUDA(cudaGetSymbolAddress(&p, g_eye));
+    eye_init_kernel<<<(kLinBN * kLinBN + 255) / 256, 256, 0, st>>>();
+    LDOT_CHECK_LAUNCH();
+    // later launches may run on other streams: make the one-time fill visible to all of them
+    LDOT_CUDA(cudaStreamSynchronize(st));
+    base = static_cast<const uint16_t*>(p);
+  }
+  *out = base + static_cast<size_t>(fmt) * kLinBN * kLinBN;
+  return kOk;
+}
+
 template <int ACT, int OUT_F32>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
@@ -90,6 +118,13 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
   if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
   if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN)) return e;
   if (int e = make_tmap_store(&to, out, 2, M, N, static_cast<uint64_t>(ldo) * 2, 32, 32)) return e;
+  CUtensorMap tr = ta, te = tw;  // (unused unless there is a residual)
+  if (residual) {
+    const uint16_t* eye = nullptr;
+    if (int e = eye_pointer(fmt, st, &eye)) return e;
+    if (int e = make_tmap_kmajor_16b(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, kBM)) return e;
+    if (int e = make_tmap_kmajor_16b(&te, eye, kLinBN, kLinBN, kLinBN * 2, kLinBN)) return e;
+  }
 
   static bool configured = false;
   static int max_clusters[kLnMaxCluster + 1] = {0};
@@ -120,14 +155,13 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
   s.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
   s.k_blocks = (K + kBK - 1) / kBK;
   s.cluster = C;
+  s.res_blocks = residual ? kLinBN / kBK : 0;
   s.num_clusters = s.m_tiles < max_clusters[C] ? s.m_tiles : max_clusters[C];
   s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM, kLinBN);
   LnParams p;
   p.bias = bias;
-  p.residual = residual;
   p.gamma = gamma;
   p.beta = beta;
-  p.ldr = ldr;
   p.M = M;
   p.N = N;
   p.fmt = fmt;
@@ -135,7 +169,7 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
   KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
                  (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * 2.0 +
                      (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
-  LDOT_CUDA(cudaLaunchKernelEx(&cfg, linear_ln_kernel, ta, tw, to, s, p));
+  LDOT_CUDA(cudaLaunchKernelEx(&cfg, linear_ln_kernel, ta, tw, tr, te, to, s, p));
   return kOk;
 }
 

@@ -15,6 +15,9 @@
 //            cluster-scope mbarrier arrive;
 //   pass 2   once all 2 C partials of a row have arrived: mean / rstd, x recomputed from TMEM, normalised, scaled,
 //            packed to 16 bit, staged (swizzled) in shared memory and written with one TMA store per 32 x 32 box.
+// The residual is added BY THE TENSOR CORE: after the K loop the producer streams the [128 x 256] residual tile as four
+// more K blocks of A against a 256 x 256 identity matrix as B (1.0 * r accumulates exactly in fp32), so it arrives
+// through coalesced, prefetched TMA loads instead of per-row loads in the epilogue.
 // Statistics are exact fp32 sums of the fp32 x (nothing is rounded to 16 bit before the normalisation).
 // Warp roles and pipelines are those of linear_tc.cuh (warp 0 TMA, warp 1 MMA, warps 2..9 epilogue).
 #pragma once
@@ -27,15 +30,14 @@ constexpr float kLnEpsF = 1e-12f;
 
 struct LnSched {
   int m_tiles, k_blocks, num_clusters, cluster;  // cluster = C
+  int res_blocks;                                // 64-column residual blocks appended to the K loop (0 or 4)
   uint32_t idesc;
 };
 
 struct LnParams {
   const float* bias;      // [N] or null
-  const void* residual;   // [M, ldr] 16-bit of `fmt`, or null
   const float* gamma;     // [N]
   const float* beta;      // [N]
-  long long ldr;
   long long M;
   int N;
   int fmt;
@@ -58,6 +60,7 @@ static_assert(LnSmem::kDynamic <= 227 * 1024, "linear+LN kernel shared memory");
 
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_eye,
                  const __grid_constant__ CUtensorMap tmap_out, const LnSched sched, const LnParams p) {
   using SM = LnSmem;
   extern __shared__ uint8_t smem_raw[];
@@ -93,6 +96,8 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    ptx::prefetch_tmap(&tmap_res);
+    ptx::prefetch_tmap(&tmap_eye);
     ptx::prefetch_tmap(&tmap_out);
   }
   if (warp == 1) {
@@ -111,13 +116,20 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
-        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+        for (int kb = 0; kb < sched.k_blocks + sched.res_blocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
-          ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
-                           ptx::kEvictNormal);
-          ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, rank * kLinBN,
-                           ptx::kEvictLast);
+          if (kb < sched.k_blocks) {
+            ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
+                             ptx::kEvictNormal);
+            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, rank * kLinBN,
+                             ptx::kEvictLast);
+          } else {  // residual block j of this n-tile against block j of the identity
+            const int j = kb - sched.k_blocks;
+            ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_res, &full[stage], rank * kLinBN + j * kBK,
+                             m_tile * kBM, ptx::kEvictNormal);
+            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_eye, &full[stage], j * kBK, 0, ptx::kEvictLast);
+          }
           if (++stage == kLinStages) {
             stage = 0;
             phase ^= 1;
@@ -137,7 +149,7 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
-        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+        for (int kb = 0; kb < sched.k_blocks + sched.res_blocks; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
@@ -171,15 +183,11 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
-      const long long grow = static_cast<long long>(m_tile) * kBM + row;
-      const bool row_ok = grow < p.M;
-      const uint16_t* res_row =
-          p.residual != nullptr ? static_cast<const uint16_t*>(p.residual) + (row_ok ? grow : 0) * p.ldr : nullptr;
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
 
-      // x = acc + bias + residual for one 32-column chunk (identical arithmetic in both passes)
+      // x = acc (+ residual, already accumulated by the MMA) + bias for one 32-column chunk (both passes)
       auto load_x = [&](int cc, float (&f)[32]) {
         const int col = col_base + cc * 32;
         uint32_t v[32];
@@ -188,11 +196,6 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-        }
-        uint4 r4[4];
-        if (res_row != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) r4[j] = __ldg(reinterpret_cast<const uint4*>(res_row + col) + j);
         }
         ptx::tmem_ld_wait();
 #pragma unroll
@@ -204,18 +207,6 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             f[4 * j + 1] += b4[j].y;
             f[4 * j + 2] += b4[j].z;
             f[4 * j + 3] += b4[j].w;
-          }
-        }
-        if (res_row != nullptr) {
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 x = unpack2(w[q], p.fmt);
-              f[j4 * 8 + q * 2] += x.x;
-              f[j4 * 8 + q * 2 + 1] += x.y;
-            }
           }
         }
       };
