@@ -96,7 +96,7 @@ int ldot_linear(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, cons
 
 /* ---- Linear + residual + LayerNorm fused: replaces BertSelfOutput / BertOutput (uniter_model/model/layer.py:104-115,
  * 145-156):  out[M, N] = LayerNorm(A . W^T + bias + residual) * gamma + beta, eps 1e-12, 16-bit output of `dtype`.
- * N % 32 == 0 and N <= 1024 (the 128-row block is shared by a cluster of ceil(N / 256) CTAs that exchange fp32 row
+ * N % 32 == 0 and N <= 768 (the 128-row block is shared by a cluster of ceil(N / 256) CTAs that exchange fp32 row
  * statistics through distributed shared memory); bias / residual may be NULL; gamma / beta fp32 [N].              */
 int ldot_linear_ln(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
                    const void* d_residual, int64_t ldr, const float* d_gamma, const float* d_beta, void* d_out,

@@ -25,7 +25,7 @@
 
 namespace ldot {
 
-constexpr int kLnMaxCluster = 4;
+constexpr int kLnMaxCluster = 3;      // N <= 768
 constexpr float kLnEpsF = 1e-12f;
 
 struct LnSched {
@@ -52,7 +52,9 @@ struct LnSmem {
   static constexpr int kStatsOffset = kStagingOffset + kLinEpiWarps * kStagingPerWarp;
   // [2 tile parities][C * 2 column halves][128 rows] float2
   static constexpr int kStatsBytes = 2 * kLnMaxCluster * 2 * kBM * 8;
-  static constexpr int kBarOffset = kStatsOffset + kStatsBytes;
+  static constexpr int kVecOffset = kStatsOffset + kStatsBytes;   // bias | gamma | beta of this CTA's 256 columns
+  static constexpr int kVecBytes = 3 * kLinBN * 4;
+  static constexpr int kBarOffset = kVecOffset + kVecBytes;
   static constexpr int kTotal = kBarOffset + (2 * kLinStages + 4 + 2) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;
 };
@@ -68,6 +70,7 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kLinStages * SM::kABytes;
   float2* stats = reinterpret_cast<float2*>(smem + SM::kStatsOffset);
+  float* vec = reinterpret_cast<float*>(smem + SM::kVecOffset);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
   uint64_t* empty = full + kLinStages;
   uint64_t* tfull = empty + kLinStages;
@@ -103,6 +106,14 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr, 512);
     ptx::tmem_relinquish();
+  }
+  // the per-column vectors of this CTA's n-tile never change: stage them once (columns past N read as 0 / unused)
+  for (int i = threadIdx.x; i < kLinBN; i += blockDim.x) {
+    const int col = static_cast<int>(ptx::cluster_ctarank()) * kLinBN + i;
+    const bool ok = col < p.N;
+    vec[i] = ok && p.bias != nullptr ? __ldg(p.bias + col) : 0.f;
+    vec[kLinBN + i] = ok ? __ldg(p.gamma + col) : 0.f;
+    vec[2 * kLinBN + i] = ok ? __ldg(p.beta + col) : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -189,25 +200,17 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       // x = acc (+ residual, already accumulated by the MMA) + bias for one 32-column chunk (both passes)
       auto load_x = [&](int cc, float (&f)[32]) {
-        const int col = col_base + cc * 32;
         uint32_t v[32];
         ptx::tmem_ld32(taddr + cc * 32, v);
-        float4 b4[8];
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
-        }
+        const float4* b4 = reinterpret_cast<const float4*>(vec + half * (kLinBN / 2) + cc * 32);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            f[4 * j] += b4[j].x;
-            f[4 * j + 1] += b4[j].y;
-            f[4 * j + 2] += b4[j].z;
-            f[4 * j + 3] += b4[j].w;
-          }
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = b4[j];  // (broadcast LDS.128)
+          f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
+          f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+          f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+          f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
         }
       };
 
@@ -225,10 +228,9 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       {
         const uint32_t slot = ptx::smem_u32(stats + (as * 2 * kLnMaxCluster + rank * 2 + half) * kBM + row);
         const uint32_t bar = ptx::smem_u32(&sbar[as]);
-        for (int c = 0; c < C; ++c) {
-          ptx::st_cluster_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2);
-          ptx::mbar_arrive_cluster(ptx::mapa(bar, static_cast<uint32_t>(c)));
-        }
+        for (int c = 0; c < C; ++c) ptx::st_cluster_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2);
+        ptx::fence_acq_rel_cluster();  // one release fence for all C remote stores, then unordered arrives
+        for (int c = 0; c < C; ++c) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(bar, static_cast<uint32_t>(c)));
       }
       ptx::mbar_wait_cluster(&sbar[as], aphase);
       float t1 = 0.f, t2 = 0.f;
@@ -256,10 +258,12 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[as]);
         }
+        const float4* g4 = reinterpret_cast<const float4*>(vec + kLinBN + half * (kLinBN / 2) + cc * 32);
+        const float4* e4 = reinterpret_cast<const float4*>(vec + 2 * kLinBN + half * (kLinBN / 2) + cc * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma + col) + j);
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta + col) + j);
+          const float4 g = g4[j];
+          const float4 b = e4[j];
           f[4 * j] = fmaf((f[4 * j] - mean) * rstd, g.x, b.x);
           f[4 * j + 1] = fmaf((f[4 * j + 1] - mean) * rstd, g.y, b.y);
           f[4 * j + 2] = fmaf((f[4 * j + 2] - mean) * rstd, g.z, b.z);

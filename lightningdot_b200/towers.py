@@ -31,7 +31,7 @@ class TowerEngine:
         self.pre_ln_f32 = pre_ln_f32
         # fuse_ln: BertSelfOutput / BertOutput as ONE kernel (GEMM + bias + residual + LayerNorm, cluster of 3 CTAs per
         # row block); otherwise GEMM (+bias +residual, fp32 or 16-bit sums) followed by the LayerNorm kernel
-        self.fuse_ln = fuse_ln and hidden % 32 == 0 and hidden <= 1024
+        self.fuse_ln = fuse_ln and hidden % 32 == 0 and hidden <= 768
         self.w = None
         self.signature = None
 

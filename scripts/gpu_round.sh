@@ -27,7 +27,7 @@ if [[ "$what" == *ncu* ]]; then
     python scripts/profile_search.py 1000000 10000 1 > gpurun_out/ncu_coarse_10k.out 2>&1; echo "ncu coarse10k rc=$?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:coarse_ts -s 1 -c 1 -f -o gpurun_out/prof_coarse_128 \
     python scripts/profile_search.py 1000000 128 1 > gpurun_out/ncu_coarse_128.out 2>&1; echo "ncu coarse128 rc=$?"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_tc -s 50 -c 5 -f -o gpurun_out/prof_linear \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_ -s 8 -c 4 -f -o gpurun_out/prof_linear \
     python scripts/profile_tower.py 4096 1 > gpurun_out/ncu_linear.out 2>&1; echo "ncu linear rc=$?"
 fi
 ls -la gpurun_out | head -40
