@@ -230,7 +230,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_config(args, world):
@@ -300,7 +300,7 @@ def run_ours(args):
 
     def step_device():
         with torch.no_grad():
-            _, emb, _ = txt_model(ids_d[q_lo:q_hi], mask_d[q_lo:q_hi], pos_d)
+            _, emb, _ = txt_model(ids_d[q_lo:q_hi], mask_d[q_lo:q_hi], pos_d, need_sequence=False)
             q_all = indexer.gather_queries(emb)
             return indexer.search_device(q_all, k)
 
@@ -311,7 +311,7 @@ def run_ours(args):
         with torch.no_grad():
             ids = ids_pin[q_lo:q_hi].to(dev, non_blocking=True)
             mask = mask_pin[q_lo:q_hi].to(dev, non_blocking=True)
-            _, emb, _ = txt_model(ids, mask, pos_d)
+            _, emb, _ = txt_model(ids, mask, pos_d, need_sequence=False)   # (as BiEncoder.forward calls it)
             q_all = indexer.gather_queries(emb)
             return indexer.search(q_all, k) if api == "search" else indexer.search_knn(q_all, k)
 
@@ -471,7 +471,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], par = cpu_baseline(args, sd, ids_h, mask_h, pos_h, x, emb_all, ids_out, scores, gt)
         line["parity"].update(par)
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -514,8 +514,18 @@ def cpu_baseline(args, sd, ids_h, mask_h, pos_h, x_dev, emb_all, ids_gpu, scores
     return base, par
 
 
+_emit = print
+
+
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner, torchrun notes) is
+    # sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the line itself goes to the saved fd.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: (real_stdout.write(text + "\n"), real_stdout.flush())
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LDOT_ABI_VERSION 1
+#define LDOT_ABI_VERSION 2
 
 #define LDOT_OK 0
 #define LDOT_ERR_ARG (-1)
@@ -110,7 +110,10 @@ int ldot_linear_ln(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, c
  * ldot_embed_image out[b * out_seq + row_offset + r, :] = LN(LN_img(lin[b, r]) + LN_pos(W_pos box[b, r] + b_pos) + type1)
  *                  (model.py:262-273,328-336); lin = img_linear(feat) + bias as fp32 [B * R, H] (from ldot_linear)
  * ldot_attention   ctx = softmax(Q K^T / 8 + (1 - mask) * -10000) V per (sequence, head), head dim 64
- *                  (layer.py:80-101, model.py:362-365); qkv [B * S, 3 H] = Q | K | V; mask int64 [B, S]; S <= 128
+ *                  (layer.py:80-101, model.py:362-365); qkv [B * S, 3 H] = Q | K | V; mask int64 [B, S]; S <= 128;
+ *                  only the first q_rows query positions of each sequence are computed: ctx is [B * q_rows, H]
+ *                  (q_rows = S: the whole layer; q_rows = 1: the last layer when only the [CLS] row is read,
+ *                  dvl/models/bi_encoder.py:120,188)
  * ldot_cast_f32    fp32 -> 16-bit, n elements (n % 8 == 0)                                                          */
 int ldot_layernorm(const void* d_in, int64_t ld_in, int32_t in_f32, const float* d_gamma, const float* d_beta,
                    void* d_out, int64_t ld_out, int64_t rows, int32_t H, int32_t dtype, void* stream);
@@ -123,7 +126,7 @@ int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_
                      const float* d_type1, const float* d_ln_g, const float* d_ln_b, void* d_out, int32_t B, int32_t R,
                      int32_t out_seq, int32_t row_offset, int32_t H, int32_t dtype, void* stream);
 int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
-                   int32_t heads, int32_t dtype, void* stream);
+                   int32_t heads, int32_t q_rows, int32_t dtype, void* stream);
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream);
 
 /* ---- in-batch-negative NLL: replaces BiEncoderNllLoss.calc (dvl/models/bi_encoder.py:615-656) -------------------

@@ -11,6 +11,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
 
+ABI_VERSION = 2   # LDOT_ABI_VERSION of include/ldot.h
 COARSE_FP16 = 0
 COARSE_BF16 = 1
 
@@ -46,7 +47,7 @@ SIGNATURES = {
     "ldot_embed_text": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_embed_image": (c_int32, [c_void_p] * 12 + [c_int32] * 6 + [c_void_p]),
-    "ldot_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_cast_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "ldot_split16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ldot_inbatch_nll": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
@@ -72,8 +73,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.ldot_abi_version() != 1:
-        raise LdotError(f"ABI version mismatch: library reports {lib.ldot_abi_version()}, binding expects 1")
+    if lib.ldot_abi_version() != ABI_VERSION:
+        raise LdotError(f"ABI version mismatch: library reports {lib.ldot_abi_version()}, binding expects {ABI_VERSION}")
     _lib = lib
     return lib
 

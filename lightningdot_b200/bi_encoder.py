@@ -266,9 +266,12 @@ class BertEncoder(_TowerBase):
         return model
 
     def forward(self, input_ids, attention_mask, position_ids,
-                img_feat=None, img_pos_feat=None, img_masks=None, gather_index=None):
+                img_feat=None, img_pos_feat=None, img_masks=None, gather_index=None, need_sequence=True):
+        """-> (sequence_output, pooled_output, hidden_states=None) as bi_encoder.py:107-123.  need_sequence=False (what
+        BiEncoder.forward passes unless output_all_encoded_layers is set) returns sequence_output=None and lets the
+        engine evaluate the last layer for the [CLS] position only; pooled_output is unchanged."""
         self._check_inference()
-        seq, pooled = self.engine().encode_text(input_ids, attention_mask, position_ids, want_seq=True)
+        seq, pooled = self.engine().encode_text(input_ids, attention_mask, position_ids, want_seq=need_sequence)
         hidden_states = None
         return seq, pooled, hidden_states
 
@@ -296,16 +299,17 @@ class UniterEncoder(_TowerBase):
         return model
 
     def forward(self, input_ids, attention_mask, position_ids,
-                img_feat, img_pos_feat, img_masks, gather_index=None) -> Tuple[T, ...]:
+                img_feat, img_pos_feat, img_masks, gather_index=None, need_sequence=True) -> Tuple[T, ...]:
+        """bi_encoder.py:163-191; need_sequence as in BertEncoder.forward."""
         self._check_inference()
         if img_masks is not None:
             raise NotImplementedError("img_masks (masked-region modelling, pre-training only) is outside the retrieval path")
         eng = self.engine()
         if img_feat is None:   # txt_model_type == 'uniter-base': text through the UNITER body
-            seq, pooled = eng.encode_text(input_ids, attention_mask, position_ids, want_seq=True)
+            seq, pooled = eng.encode_text(input_ids, attention_mask, position_ids, want_seq=need_sequence)
         else:
             seq, pooled = eng.encode_image(input_ids, attention_mask, position_ids, img_feat, img_pos_feat,
-                                           gather_index, want_seq=True)
+                                           gather_index, want_seq=need_sequence)
         return seq, pooled, None
 
 
@@ -345,21 +349,23 @@ class BiEncoder(nn.Module):
 
     @staticmethod
     def get_representation(sub_model, input_ids, attention_mask, position_ids, img_feat, img_pos_feat, img_masks,
-                           gather_index=None, fix_encoder=False):
+                           gather_index=None, fix_encoder=False, need_sequence=True):
         if fix_encoder:
             with torch.no_grad():
                 sequence_output, pooled_output, hidden_states = sub_model(input_ids, attention_mask, position_ids,
                                                                           img_feat, img_pos_feat, img_masks,
-                                                                          gather_index)
+                                                                          gather_index, need_sequence=need_sequence)
         else:
             sequence_output, pooled_output, hidden_states = sub_model(input_ids, attention_mask, position_ids,
                                                                       img_feat, img_pos_feat, img_masks,
-                                                                      gather_index)
+                                                                      gather_index, need_sequence=need_sequence)
         return sequence_output, pooled_output, hidden_states
 
     def forward(self, batch, output_all_encoded_layers=False):
         # batch keys: imgs / txts / caps  (dvl/data/itm.py:203-288)
         batch = defaultdict(lambda: None, batch)
+        # the pooled outputs are all this call returns unless output_all_encoded_layers: skip the unread rows
+        seq = bool(output_all_encoded_layers)
 
         if 'txts' in batch:
             sb = batch['txts']
@@ -367,7 +373,7 @@ class BiEncoder(nn.Module):
                                                                       sb['attention_mask'], sb['position_ids'],
                                                                       sb['img_feat'], sb['img_pos_feat'],
                                                                       sb['img_masks'],
-                                                                      sb['gather_index'], self.fix_txt_encoder)
+                                                                      sb['gather_index'], self.fix_txt_encoder, need_sequence=seq)
         else:
             txt_seq, txt_pooled = None, None
 
@@ -378,7 +384,7 @@ class BiEncoder(nn.Module):
                                                                       sb['attention_mask'], sb['position_ids'],
                                                                       sb['img_feat'], sb['img_pos_feat'],
                                                                       sb['img_masks'],
-                                                                      sb['gather_index'], self.fix_txt_encoder)
+                                                                      sb['gather_index'], self.fix_txt_encoder, need_sequence=seq)
         else:
             img_seq, img_pooled = None, None
 
@@ -388,7 +394,7 @@ class BiEncoder(nn.Module):
                                                                       sb['attention_mask'], sb['position_ids'],
                                                                       sb['img_feat'], sb['img_pos_feat'],
                                                                       sb['img_masks'],
-                                                                      sb['gather_index'], self.fix_txt_encoder)
+                                                                      sb['gather_index'], self.fix_txt_encoder, need_sequence=seq)
         else:
             cap_seq, cap_pooled = None, None
 

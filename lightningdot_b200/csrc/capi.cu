@@ -195,7 +195,8 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
 }  // namespace ldot
 #include "encoder_params.h"
 namespace ldot {
-int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int fmt, void* stream);
+int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows, int fmt,
+                  void* stream);
 int layernorm_run(const void* in, long long ld_in, int in_f32, const float* gamma, const float* beta, void* out,
                   long long ld_out, long long rows, int H, int fmt, void* stream);
 int embed_text_run(const long long* ids, const long long* pos_ids, long long pos_batch_stride, const void* word,
@@ -377,10 +378,10 @@ int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_
 }
 
 int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
-                   int32_t heads, int32_t dtype, void* stream) {
+                   int32_t heads, int32_t q_rows, int32_t dtype, void* stream) {
   LDOT_REQUIRE(d_qkv && d_mask && d_ctx, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
-  return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, dtype, stream);
+  return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, q_rows, dtype, stream);
 }
 
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream) {

@@ -226,10 +226,12 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 constexpr int kHeadDim = 64;
 constexpr int kRowPad = 72;  // smem row pitch in elements (144 B): conflict-free ldmatrix
 
-// grid (heads, B); block = (SPAD / 16) warps; warp w owns query rows [16 w, 16 w + 16)
+// grid (heads, B); block = (SPAD / 16) warps; warp w owns query rows [16 w, 16 w + 16).  Only the first q_rows query
+// positions of each sequence are computed and written (ctx is [B * q_rows, H]): q_rows = S for a full layer, 1 for the
+// last layer of a tower whose caller only reads the [CLS] row (dvl/models/bi_encoder.py:120,188).
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
-                                                              uint16_t* __restrict__ ctx, int S, int H) {
+                                                              uint16_t* __restrict__ ctx, int S, int H, int q_rows) {
   extern __shared__ __align__(16) uint16_t att_smem[];
   uint16_t* sQ = att_smem;
   uint16_t* sK = sQ + SPAD * kRowPad;
@@ -251,6 +253,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
 
   const int g = lane >> 2, t = lane & 3;
   const int qrow0 = warp * 16;
+  if (qrow0 >= q_rows) return;  // (no block-wide synchronisation past this point)
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -343,14 +346,16 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
   for (int i = 0; i < 4; ++i) {
     const int idx = i * 32 + lane;
     const int r = qrow0 + (idx >> 3), c = (idx & 7) * 8;
-    if (r < S)
-      *reinterpret_cast<uint4*>(ctx + (tok0 + r) * H + head * kHeadDim + c) = *reinterpret_cast<const uint4*>(sQ + r * kRowPad + c);
+    if (r < q_rows)
+      *reinterpret_cast<uint4*>(ctx + (static_cast<long long>(b) * q_rows + r) * H + head * kHeadDim + c) =
+          *reinterpret_cast<const uint4*>(sQ + r * kRowPad + c);
   }
 }
 
 // ================================================================================================ host side
 template <int FMT>
-static int attention_launch(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, cudaStream_t st) {
+static int attention_launch(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows,
+                            cudaStream_t st) {
   const int spad = (S + 15) / 16 * 16;
   const dim3 grid(heads, B);
   const size_t smem = static_cast<size_t>(3) * spad * kRowPad * sizeof(uint16_t);
@@ -358,7 +363,7 @@ static int attention_launch(const void* qkv, const long long* mask, void* ctx, i
   case SP: {                                                                                                      \
     auto kern = attention_kernel<SP, FMT>;                                                                        \
     if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), S, H);  \
+    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), S, H, q_rows);  \
     break;                                                                                                        \
   }
   switch (spad) {
@@ -378,13 +383,17 @@ static int attention_launch(const void* qkv, const long long* mask, void* ctx, i
   return kOk;
 }
 
-int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int fmt, void* stream) {
+int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows, int fmt,
+                  void* stream) {
   LDOT_REQUIRE(B >= 1 && S >= 1 && S <= 128, "attention: bad shape B=%d S=%d (S <= 128)", B, S);
+  LDOT_REQUIRE(q_rows >= 1 && q_rows <= S, "attention: q_rows %d must be in [1, S = %d]", q_rows, S);
   LDOT_REQUIRE(H == heads * kHeadDim && H % 8 == 0, "attention: hidden %d must be heads (%d) x 64", H, heads);
   LDOT_REQUIRE(B <= 65535, "attention: batch %d > 65535 (split the batch)", B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  KernelScope ks(kKcAttention, st, 4.0 * B * static_cast<double>(S) * S * H, static_cast<double>(B) * S * H * 8.0);
-  return fmt == 1 ? attention_launch<1>(qkv, mask, ctx, B, S, H, heads, st) : attention_launch<0>(qkv, mask, ctx, B, S, H, heads, st);
+  KernelScope ks(kKcAttention, st, 4.0 * B * static_cast<double>(q_rows) * S * H,
+                 static_cast<double>(B) * (static_cast<double>(S) * H * 4.0 + static_cast<double>(q_rows) * H * 4.0));
+  return fmt == 1 ? attention_launch<1>(qkv, mask, ctx, B, S, H, heads, q_rows, st)
+                  : attention_launch<0>(qkv, mask, ctx, B, S, H, heads, q_rows, st);
 }
 
 #define LDOT_NV_DISPATCH(H, CALL)                                   \

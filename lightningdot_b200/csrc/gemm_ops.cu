@@ -9,6 +9,7 @@
 #include "linear_ln.cuh"
 #include "host_common.h"
 #include "prof.h"
+#include <cstdlib>
 
 namespace ldot {
 
@@ -40,19 +41,53 @@ static int eye_pointer(int fmt, cudaStream_t st, const uint16_t** out) {
   return kOk;
 }
 
-template <int ACT, int OUT_F32>
+template <int ACT, int OUT_F32, int CTAS>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
-  auto kern = linear_tc_kernel<ACT, OUT_F32>;
+  auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS>;
+  using SM = LinSmemT<CTAS>;
   static bool configured = false;  // (one device per process)
+  static int max_groups = 0;       // resident CTAs (CTAS = 1) or CTA pairs (CTAS = 2)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = SM::kDynamic;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (!configured) {
-    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LinSmem::kDynamic));
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kDynamic));
+    if (CTAS == 2) {
+      cfg.gridDim = dim3(CTAS);
+      LDOT_CUDA(cudaOccupancyMaxActiveClusters(&max_groups, kern, &cfg));
+      LDOT_REQUIRE(max_groups >= 1, "no resident CTA pair possible");
+    } else {
+      max_groups = sms;
+    }
     configured = true;
   }
-  const int grid = s.num_tiles < sms ? s.num_tiles : sms;
-  kern<<<grid, kLinThreads, LinSmem::kDynamic, st>>>(ta, tw, to, s, p);
-  LDOT_CHECK_LAUNCH();
+  const int groups = s.num_tiles < max_groups ? s.num_tiles : max_groups;
+  cfg.gridDim = dim3(static_cast<unsigned>(groups * CTAS));
+  LDOT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, to, s, p));
   return kOk;
+}
+
+// CTA pairs (256 x 256 tiles, cta_group::2) pay off once the problem fills the machine several times over; small
+// problems (projection head, [CLS]-only last layer, tests) keep 128 x 256 tiles so that more SMs get a tile.
+// LDOT_LINEAR_CTAS=1|2 forces one form (measurement only).
+static int linear_ctas(long long M, int N, int sms) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("LDOT_LINEAR_CTAS");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 1 || forced == 2) return forced;
+  const long long tiles1 = ((M + kBM - 1) / kBM) * ((N + kLinBN - 1) / kLinBN);
+  return tiles1 >= 4ll * sms ? 2 : 1;
 }
 
 int linear_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
@@ -67,20 +102,21 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   LDOT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                "out / residual / bias must be 16-byte aligned");
-  LDOT_REQUIRE(M < (1ll << 31) - 128, "M too large");
+  LDOT_REQUIRE(M < (1ll << 31) - 256, "M too large");
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
+  const int ctas = linear_ctas(M, N, sms);
   CUtensorMap ta, tw, to;
   if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
-  if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN)) return e;
+  if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN / ctas)) return e;
   const uint32_t elt = out_f32 ? 4 : 2;
   if (int e = make_tmap_store(&to, out, elt, M, N, static_cast<uint64_t>(ldo) * elt, 32, 32)) return e;
   LinSched s;
-  s.m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  s.m_tiles = static_cast<int>((M + kBM * ctas - 1) / (kBM * ctas));
   s.n_tiles = (N + kLinBN - 1) / kLinBN;
   s.num_tiles = s.m_tiles * s.n_tiles;
   s.k_blocks = (K + kBK - 1) / kBK;
-  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM, kLinBN);
+  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM * ctas, kLinBN);
   LinParams p;
   p.bias = bias;
   p.residual = residual;
@@ -92,8 +128,10 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
                  (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * elt +
                      (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
-  if (act == 1) return out_f32 ? launch_linear<1, 1>(ta, tw, to, s, p, sms, st) : launch_linear<1, 0>(ta, tw, to, s, p, sms, st);
-  return out_f32 ? launch_linear<0, 1>(ta, tw, to, s, p, sms, st) : launch_linear<0, 0>(ta, tw, to, s, p, sms, st);
+#define LDOT_LIN(ACT, F32) (ctas == 2 ? launch_linear<ACT, F32, 2>(ta, tw, to, s, p, sms, st) : launch_linear<ACT, F32, 1>(ta, tw, to, s, p, sms, st))
+  if (act == 1) return out_f32 ? LDOT_LIN(1, 1) : LDOT_LIN(1, 0);
+  return out_f32 ? LDOT_LIN(0, 1) : LDOT_LIN(0, 0);
+#undef LDOT_LIN
 }
 
 // out = LayerNorm(A . W^T + bias + residual) * gamma + beta, 16-bit output; a cluster of ceil(N / 256) CTAs per row block

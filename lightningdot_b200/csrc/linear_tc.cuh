@@ -10,6 +10,17 @@
 //               M / N edges of the output, so there is no tail handling on the store side.
 // Tiles are visited n-fastest (tile t = m_tile * n_tiles + n_tile): CTAs that run at the same time share the A row
 // block (the big operand - activations) through L2 while the weights stay L2-resident anyway.
+//
+// CTAS = 2 (large M): the kernel runs as CTA PAIRS (cluster of 2, tcgen05 cta_group::2).  One pair owns a 256 x 256
+// output tile; each CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 weight rows), the leader
+// CTA's elected thread issues one 256 x 256 x 16 MMA for both SMs, and each CTA's epilogue drains its own 128 x 256
+// half of the accumulator from its own TMEM.  Per SM this halves the W bytes pulled from L2 and written to shared
+// memory (32 KB instead of 48 KB per 64-wide K block), which is what bounds the single-CTA form: 148 SMs x 96 B/clk
+// of operand traffic is above what the L2 delivers (~43 B/clk/SM).  The smaller stage also buys a 6-deep ring.
+//   full[s]    lives in the LEADER: both CTAs' TMA loads complete_tx on it, the leader's producer posts the expect_tx
+//   empty[s]   one per CTA, signalled by the leader's multicast tcgen05.commit
+//   tfull[a]   one per CTA, same multicast commit after the last K block
+//   tempty[a]  lives in the LEADER: 2 x 8 epilogue warps arrive (the peer's remotely, release.cluster)
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -37,17 +48,21 @@ struct LinParams {
   int fmt;                // 0 = fp16, 1 = bf16 (A, W, residual, 16-bit output)
 };
 
-struct LinSmem {
+template <int CTAS>
+struct LinSmemT {
+  static constexpr int kStages = CTAS == 2 ? 6 : kLinStages;
+  static constexpr int kBRows = kLinBN / CTAS;         // W rows staged by one CTA
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB
-  static constexpr int kBBytes = kLinBN * kBK * 2;     // 32 KB
+  static constexpr int kBBytes = kBRows * kBK * 2;     // 32 KB (16 KB per CTA of a pair)
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingPerWarp = 4096;         // one 32 x 32 fp32 box, or two 32 x 32 16-bit boxes
-  static constexpr int kStagingOffset = kLinStages * kStageBytes;
+  static constexpr int kStagingOffset = kStages * kStageBytes;
   static constexpr int kBarOffset = kStagingOffset + kLinEpiWarps * kStagingPerWarp;
-  static constexpr int kTotal = kBarOffset + (2 * kLinStages + 4) * 8 + 16;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;       // slack for manual 1024 B alignment
 };
-static_assert(LinSmem::kDynamic <= 227 * 1024, "linear kernel shared memory");
+using LinSmem = LinSmemT<1>;
+static_assert(LinSmemT<1>::kDynamic <= 227 * 1024 && LinSmemT<2>::kDynamic <= 227 * 1024, "linear kernel shared memory");
 
 // erf-GELU  x * Phi(x) = 0.5 x (1 + erf(x / sqrt 2))  (uniter_model/model/layer.py:31-37) evaluated as
 //   x * sigmoid(x * P(x^2)),  P a degree-4 minimax polynomial of the exact logit  ln(Phi / (1 - Phi)) / x:
@@ -80,32 +95,37 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int ACT, int OUT_F32>
+// sched.m_tiles counts 128 * CTAS-row tile rows; sched.num_tiles = m_tiles * n_tiles tiles of (128 * CTAS) x 256.
+template <int ACT, int OUT_F32, int CTAS>
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
-  using SM = LinSmem;
+  using SM = LinSmemT<CTAS>;
+  constexpr int kStages = SM::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + kLinStages * SM::kABytes;
+  uint8_t* smem_b = smem + kStages * SM::kABytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::kBarOffset);
-  uint64_t* empty = full + kLinStages;
-  uint64_t* tfull = empty + kLinStages;
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = CTAS == 2 ? static_cast<int>(ptx::cluster_ctarank()) : 0;   // 0 = leader of the pair
+  const int first_tile = static_cast<int>(blockIdx.x) / CTAS;
+  const int tile_step = static_cast<int>(gridDim.x) / CTAS;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kLinStages; ++i) {
+    for (int i = 0; i < kStages; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], kLinEpiWarps);
+      ptx::mbar_init(&tempty[i], kLinEpiWarps * CTAS);
     }
     ptx::fence_mbar_init();
   }
@@ -115,29 +135,43 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     ptx::prefetch_tmap(&tmap_out);
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, 512);
-    ptx::tmem_relinquish();
+    if (CTAS == 2) {
+      ptx::tmem_alloc_2cta(tmem_ptr, 512);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(tmem_ptr, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
         const int m_tile = t / sched.n_tiles, n_tile = t - m_tile * sched.n_tiles;
+        const int a_row = (m_tile * CTAS + rank) * kBM;
+        const int w_row = n_tile * kLinBN + rank * SM::kBRows;
         for (int kb = 0; kb < sched.k_blocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
-          ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
-                           ptx::kEvictNormal);
-          ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, n_tile * kLinBN,
-                           ptx::kEvictLast);
-          if (++stage == kLinStages) {
+          if (CTAS == 2) {
+            // bytes of BOTH CTAs are credited to the leader's barrier
+            const uint32_t lbar = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * SM::kStageBytes);
+            ptx::tma_load_2d_2cta(smem_a + stage * SM::kABytes, &tmap_a, lbar, kb * kBK, a_row, ptx::kEvictNormal);
+            ptx::tma_load_2d_2cta(smem_b + stage * SM::kBBytes, &tmap_w, lbar, kb * kBK, w_row, ptx::kEvictLast);
+          } else {
+            ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
+            ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, a_row, ptx::kEvictNormal);
+            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, w_row, ptx::kEvictLast);
+          }
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
@@ -146,14 +180,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (the leader CTA only)
+    if (rank == 0 && ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
-        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+      for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
+        if (CTAS == 2) ptx::mbar_wait_cluster(&tempty[as], aphase ^ 1);
+        else ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
         for (int kb = 0; kb < sched.k_blocks; ++kb) {
@@ -162,15 +197,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
           const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * SM::kBBytes));
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
-          ptx::mma_commit(&empty[stage]);
-          if (++stage == kLinStages) {
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            if (CTAS == 2) ptx::mma_f16_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+            else ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if (CTAS == 2) ptx::mma_commit_2cta(&empty[stage], 0x3);
+          else ptx::mma_commit(&empty[stage]);
+          if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        ptx::mma_commit(&tfull[as]);
+        if (CTAS == 2) ptx::mma_commit_2cta(&tfull[as], 0x3);
+        else ptx::mma_commit(&tfull[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -186,8 +225,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     uint32_t nstore = 0;
-    for (int t = blockIdx.x; t < sched.num_tiles; t += gridDim.x) {
-      const int m_tile = t / sched.n_tiles, n_tile = t - m_tile * sched.n_tiles;
+    // tempty of the LEADER collects the arrivals of both CTAs' epilogue warps
+    const uint32_t tempty_addr[2] = {CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]),
+                                     CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[1]), 0) : ptx::smem_u32(&tempty[1])};
+    auto release_acc = [&](int a) {
+      if (CTAS == 2) ptx::mbar_arrive_cluster(tempty_addr[a]);
+      else ptx::mbar_arrive(&tempty[a]);
+    };
+    for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
+      const int m_pair = t / sched.n_tiles, n_tile = t - m_pair * sched.n_tiles;
+      const int m_tile = m_pair * CTAS + rank;   // 128-row block of this CTA
       const long long grow = static_cast<long long>(m_tile) * kBM + row;
       const bool row_ok = grow < p.M;
       const int col_base = n_tile * kLinBN + half * (kLinBN / 2);
@@ -200,7 +247,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (nchunks == 0) {
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+        if (lane == 0) release_acc(as);
       }
       for (int cc = 0; cc < nchunks; ++cc) {
         const int col = col_base + cc * 32;
@@ -224,7 +271,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (cc == nchunks - 1) {  // accumulator drained: hand it back to the MMA warp before the math
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+          if (lane == 0) release_acc(as);
         }
         float f[32];
 #pragma unroll
@@ -307,9 +354,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all();  // neither CTA may retire (or free TMEM) while the pair's MMAs can still touch it
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if (CTAS == 2) ptx::tmem_dealloc_2cta(tmem_base, 512);
+    else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -228,9 +228,9 @@ __device__ __forceinline__ void mma_f16_ss_2cta(uint32_t tmem_d, uint64_t adesc,
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // commit of the pair's MMAs: arrives on the barrier at this shared-memory offset in every CTA of `cta_mask`
@@ -239,15 +239,15 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t cta_mask
                ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
-// TMA load into THIS CTA's shared memory whose completion bytes are credited to the LEADER CTA's mbarrier
-constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
-__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
-                                                 uint64_t policy) {
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier that may live in the
+// other CTA of the pair: `cluster_bar_addr` is a shared::cluster address (mapa of the leader's barrier)
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint32_t cluster_bar_addr, int c0,
+                                                 int c1, uint64_t policy) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0),
-      "r"(c1), "l"(policy)
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar_addr), "r"(c0), "r"(c1),
+      "l"(policy)
       : "memory");
 }
 

@@ -105,8 +105,11 @@ class TowerEngine:
         _lib.check(lib.ldot_layernorm(_lib.ptr(x), x.stride(0), int(x.dtype == torch.float32), _lib.ptr(g), _lib.ptr(b),
                                       _lib.ptr(out), out.stride(0), rows, H, self.fmt, _lib.stream_ptr()))
 
-    def _layers(self, h, mask, B, S):
-        """h: [B*S, H] 16-bit (updated in place); mask int64 [B, S]."""
+    def _layers(self, h, mask, B, S, cls_only=False):
+        """h: [B*S, H] 16-bit (updated in place); mask int64 [B, S].  Returns (h, cls) where cls is None, or - with
+        cls_only - the compact [B, H] matrix of last-layer [CLS] rows.  With cls_only the last layer is evaluated for the
+        [CLS] query position alone (keys / values still come from every position): the rows the reference computes and
+        then discards at bi_encoder.py:120,188 are not produced, the [CLS] row is bit-identical."""
         lib = _lib.load()
         T, H, dt, dev = B * S, self.H, self.dtype, h.device
         w = self.w
@@ -116,23 +119,36 @@ class TowerEngine:
         a = torch.empty((T, H), dtype=dt, device=dev)
         f = torch.empty((T, self.ffn), dtype=dt, device=dev)
         stream = _lib.stream_ptr()
+
+        def block(i, x_in, ldx, ctx_, a_, f_, out_, rows, q_rows):
+            """attention output ctx_ -> BertSelfOutput -> BertIntermediate -> BertOutput for `rows` rows; x_in (row pitch
+            ldx) is the layer input of those rows (the residual)."""
+            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx_), B, S, H, self.heads, q_rows,
+                                          self.fmt, stream))
+            res = x_in.as_strided((rows, H), (ldx, 1))
+            if self.fuse_ln:
+                self._linear_ln(ctx_, H, w[f"o_w{i}"], w[f"o_b{i}"], res, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a_, rows)
+                self._linear(a_, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f_, rows, act=1)
+                self._linear_ln(f_, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], a_, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out_, rows)
+                return
+            pre_ = pre[:rows]
+            self._linear(ctx_, H, w[f"o_w{i}"], w[f"o_b{i}"], pre_, rows, residual=res)
+            self._layernorm(pre_, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a_, rows, H)
+            self._linear(a_, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f_, rows, act=1)
+            self._linear(f_, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], pre_, rows, residual=a_)
+            self._layernorm(pre_, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out_, rows, H)
+
         for i in range(self.layers):
             self._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
-            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, self.heads, self.fmt, stream))
-            if self.fuse_ln:
-                self._linear_ln(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], h, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T)
-                self._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f, T, act=1)
-                self._linear_ln(f, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], a, w[f"ln2_g{i}"], w[f"ln2_b{i}"], h, T)
-                continue
-            self._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre, T, residual=h)
-            self._layernorm(pre, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
-            self._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], f, T, act=1)
-            self._linear(f, self.ffn, w[f"f2_w{i}"], w[f"f2_b{i}"], pre, T, residual=a)
-            self._layernorm(pre, w[f"ln2_g{i}"], w[f"ln2_b{i}"], h, T, H)
-        return h
+            if cls_only and i == self.layers - 1:
+                cls = torch.empty((B, H), dtype=dt, device=dev)
+                block(i, h, S * H, ctx[:B], a[:B], f[:B], cls, B, 1)
+                return h, cls
+            block(i, h, H, ctx, a, f, h, T, S)
+        return h, None
 
     def _head(self, h, B, S):
-        """CLS rows (row pitch S*H) -> projection head -> fp32 [B, out_dim]."""
+        """CLS rows (row pitch S*H; S = 1 for the compact matrix) -> projection head -> fp32 [B, out_dim]."""
         w, H, dev = self.w, self.H, h.device
         if not self.project:
             return h.view(B, S, H)[:, 0, :].float()
@@ -174,8 +190,8 @@ class TowerEngine:
             nb = b1 - b0
             h = torch.empty((nb * L, self.H), dtype=self.dtype, device=dev)
             self._embed_text(ids[b0:b1], pos if pos.shape[0] == 1 else pos[b0:b1], h, nb, L, L)
-            h = self._layers(h, mask[b0:b1], nb, L)
-            pooled.append(self._head(h, nb, L))
+            h, cls = self._layers(h, mask[b0:b1], nb, L, cls_only=not want_seq)
+            pooled.append(self._head(h, nb, L) if cls is None else self._head(cls, nb, 1))
             if want_seq:
                 seqs.append(h.view(nb, L, self.H))
         return (torch.cat(seqs, 0) if want_seq else None), (pooled[0] if len(pooled) == 1 else torch.cat(pooled, 0))
@@ -217,8 +233,8 @@ class TowerEngine:
                 _lib.ptr(lin), _lib.ptr(box[b0:b1]), _lib.ptr(w["img_ln_g"]), _lib.ptr(w["img_ln_b"]), _lib.ptr(w["pos_w"]),
                 _lib.ptr(w["pos_bias"]), _lib.ptr(w["pos_ln_g"]), _lib.ptr(w["pos_ln_b"]), _lib.ptr(w["type1_f32"]),
                 _lib.ptr(w["iemb_ln_g"]), _lib.ptr(w["iemb_ln_b"]), _lib.ptr(h), nb, R, S, Lt, H, self.fmt, stream))
-            h = self._layers(h, mask[b0:b1], nb, S)
-            pooled.append(self._head(h, nb, S))
+            h, cls = self._layers(h, mask[b0:b1], nb, S, cls_only=not want_seq)
+            pooled.append(self._head(h, nb, S) if cls is None else self._head(cls, nb, 1))
             if want_seq:
                 seqs.append(h.view(nb, S, H))
         return (torch.cat(seqs, 0) if want_seq else None), (pooled[0] if len(pooled) == 1 else torch.cat(pooled, 0))

@@ -92,5 +92,6 @@ def retrieve_query(model, query, indexer, args, top=10):
     attn_mask = torch.ones((1, n), dtype=torch.long, device=args.device)
     pos_ids = torch.arange(n, dtype=torch.long, device=args.device).unsqueeze(0)
     with torch.no_grad():
-        _, query_vector, _ = model.txt_model(input_ids=input_ids, attention_mask=attn_mask, position_ids=pos_ids)
+        _, query_vector, _ = model.txt_model(input_ids=input_ids, attention_mask=attn_mask, position_ids=pos_ids,
+                                             need_sequence=False)
     return indexer.search_knn(query_vector, 100)

@@ -88,3 +88,25 @@ def test_batch_composition_invariance(cuda_lib):
     _, all_ = eng.encode_text(b["input_ids"], b["attention_mask"], b["position_ids"])
     _, one = eng.encode_text(b["input_ids"][17:18], b["attention_mask"][17:18], b["position_ids"])
     assert torch.equal(all_[17:18], one)
+
+
+@pytest.mark.parametrize("kind", ["txt", "img"])
+@pytest.mark.parametrize("fuse_ln", [True, False])
+def test_cls_only_last_layer_is_bit_identical(cuda_lib, kind, fuse_ln):
+    """want_seq=False evaluates the last layer for the [CLS] query position only (the rows bi_encoder.py:120,188
+    discard are never produced); the pooled output must not change by a single bit."""
+    sd = synth.random_tower_state(kind, seed=8, perturb=True, layers=3)
+    eng = TowerEngine(kind, 768, 12, 3072, 3, dtype=torch.bfloat16, fuse_ln=fuse_ln)
+    eng.load(sd, "cuda")
+    if kind == "txt":
+        b = synth.text_batch(133, 32, seed=4, ragged=True)
+        args = (b["input_ids"], b["attention_mask"], b["position_ids"])
+        seq, full = eng.encode_text(*args, want_seq=True)
+        none, pruned = eng.encode_text(*args, want_seq=False)
+    else:
+        b = synth.image_batch(70, 36, seed=4, ragged=True)
+        args = (b["input_ids"], b["attention_mask"], b["position_ids"], b["img_feat"], b["img_pos_feat"], b["gather_index"])
+        seq, full = eng.encode_image(*args, want_seq=True)
+        none, pruned = eng.encode_image(*args, want_seq=False)
+    assert none is None and seq is not None
+    assert torch.equal(full, pruned)
