@@ -37,6 +37,9 @@ constexpr int kLinThreads = 32 * (2 + kLinEpiWarps);
 struct LinSched {
   int m_tiles, n_tiles, num_tiles, k_blocks;
   uint32_t idesc;
+  // split-K (RED kernels only): tile t = (k_split * m_tiles + m_tile) * n_tiles + n_tile covers K blocks
+  // [k_split * kb_per_split, ...); num_tiles = m_tiles * n_tiles * k_splits.  1 / k_blocks otherwise.
+  int k_splits, kb_per_split;
 };
 
 struct LinParams {
@@ -95,8 +98,34 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+// d/dx of the erf-GELU above, from the same logit polynomial: gelu'(x) = Phi(x) + x phi(x), Phi = sigmoid(x P(x^2)),
+// phi(x) = exp(-x^2 / 2) / sqrt(2 pi).  Used by the FFN-up backward epilogue (ACT == 2).
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float x2 = x * x;
+  float p = fmaf(-3.2289885893987957e-06f, x2, 8.823812822811306e-05f);
+  p = fmaf(p, x2, 0.00036027454189024866f);
+  p = fmaf(p, x2, -0.10522668808698654f);
+  p = fmaf(p, x2, -2.3020453453063965f);
+  float e, r, g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(x2 * -0.7213475204444817f));
+  return fmaf(x * 0.3989422804014327f, g, r);
+}
+
 // sched.m_tiles counts 128 * CTAS-row tile rows; sched.num_tiles = m_tiles * n_tiles tiles of (128 * CTAS) x 256.
-template <int ACT, int OUT_F32, int CTAS>
+//
+// Backward-pass forms of the same kernel (training):
+//   AMN / BMN = 1   the operand is MN-major: the global matrix is [K, M] (resp. [K, N]) row-major and is used without
+//                   a transpose pass - dgrad reads the nn.Linear weight [out, in] as B[N = in, K = out], wgrad reads
+//                   dY [tokens, out] as A[M = out, K = tokens] and X [tokens, in] as B[N = in, K = tokens].  TMA lands
+//                   64 (K rows) x 64 (MN, 128 B) SWIZZLE_128B boxes, 8 KB apart per 64-wide MN block; the shared-memory
+//                   descriptor carries LBO = 8192 (MN block pitch), SBO = 1024 (8 K rows), and one 16-deep K step
+//                   advances the start address by 2048 B.
+//   ACT = 2         out = acc * gelu'(aux[m, n]) with aux = p.residual (the saved FFN-up pre-activation)
+//   RED = 1         fp32 output boxes are ADDED to global memory (cp.reduce.async.bulk.tensor .add): gradient
+//                   accumulation, and what makes split-K (sched.k_splits > 1) a pure scheduling decision.
+template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
 __global__ void __launch_bounds__(kLinThreads, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
@@ -154,22 +183,52 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int mn_tiles = sched.m_tiles * sched.n_tiles;
       for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
-        const int m_tile = t / sched.n_tiles, n_tile = t - m_tile * sched.n_tiles;
+        const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+        const int m_tile = tt / sched.n_tiles, n_tile = tt - m_tile * sched.n_tiles;
         const int a_row = (m_tile * CTAS + rank) * kBM;
         const int w_row = n_tile * kLinBN + rank * SM::kBRows;
-        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+        const int kb0 = ks * sched.kb_per_split;
+        const int kb1 = kb0 + sched.kb_per_split < sched.k_blocks ? kb0 + sched.kb_per_split : sched.k_blocks;
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem_a + stage * SM::kABytes;
+          uint8_t* sb = smem_b + stage * SM::kBBytes;
           if (CTAS == 2) {
             // bytes of BOTH CTAs are credited to the leader's barrier
             const uint32_t lbar = ptx::mapa(ptx::smem_u32(&full[stage]), 0);
             if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * SM::kStageBytes);
-            ptx::tma_load_2d_2cta(smem_a + stage * SM::kABytes, &tmap_a, lbar, kb * kBK, a_row, ptx::kEvictNormal);
-            ptx::tma_load_2d_2cta(smem_b + stage * SM::kBBytes, &tmap_w, lbar, kb * kBK, w_row, ptx::kEvictLast);
+            if (AMN) {
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j)
+                ptx::tma_load_2d_2cta(sa + j * 8192, &tmap_a, lbar, a_row + j * 64, kb * kBK, ptx::kEvictNormal);
+            } else {
+              ptx::tma_load_2d_2cta(sa, &tmap_a, lbar, kb * kBK, a_row, ptx::kEvictNormal);
+            }
+            if (BMN) {
+#pragma unroll
+              for (int j = 0; j < SM::kBRows / 64; ++j)
+                ptx::tma_load_2d_2cta(sb + j * 8192, &tmap_w, lbar, w_row + j * 64, kb * kBK, ptx::kEvictLast);
+            } else {
+              ptx::tma_load_2d_2cta(sb, &tmap_w, lbar, kb * kBK, w_row, ptx::kEvictLast);
+            }
           } else {
             ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
-            ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, a_row, ptx::kEvictNormal);
-            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, w_row, ptx::kEvictLast);
+            if (AMN) {
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j)
+                ptx::tma_load_2d(sa + j * 8192, &tmap_a, &full[stage], a_row + j * 64, kb * kBK, ptx::kEvictNormal);
+            } else {
+              ptx::tma_load_2d(sa, &tmap_a, &full[stage], kb * kBK, a_row, ptx::kEvictNormal);
+            }
+            if (BMN) {
+#pragma unroll
+              for (int j = 0; j < SM::kBRows / 64; ++j)
+                ptx::tma_load_2d(sb + j * 8192, &tmap_w, &full[stage], w_row + j * 64, kb * kBK, ptx::kEvictLast);
+            } else {
+              ptx::tma_load_2d(sb, &tmap_w, &full[stage], kb * kBK, w_row, ptx::kEvictLast);
+            }
           }
           if (++stage == kStages) {
             stage = 0;
@@ -186,20 +245,30 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const int mn_tiles = sched.m_tiles * sched.n_tiles;
+      // descriptor start-address step (in 16 B units) of one 16-deep K slice: 32 B inside the 128 B row of a K-major
+      // tile, two 8-row groups (2048 B) of an MN-major one
+      constexpr uint64_t kAStep = AMN ? 128 : 2, kBStep = BMN ? 128 : 2;
       for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
+        const int ks = t / mn_tiles;
+        const int kb0 = ks * sched.kb_per_split;
+        const int kb1 = kb0 + sched.kb_per_split < sched.k_blocks ? kb0 + sched.kb_per_split : sched.k_blocks;
         if (CTAS == 2) ptx::mbar_wait_cluster(&tempty[as], aphase ^ 1);
         else ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
-        for (int kb = 0; kb < sched.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
-          const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * SM::kBBytes));
+          const uint32_t sa = ptx::smem_u32(smem_a + stage * SM::kABytes);
+          const uint32_t sb = ptx::smem_u32(smem_b + stage * SM::kBBytes);
+          const uint64_t adesc = AMN ? ptx::make_smem_desc_sw128_mn(sa) : ptx::make_smem_desc_sw128(sa);
+          const uint64_t bdesc = BMN ? ptx::make_smem_desc_sw128_mn(sb) : ptx::make_smem_desc_sw128(sb);
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
-            if (CTAS == 2) ptx::mma_f16_ss_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
-            else ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t acc = (kb != kb0 || k != 0) ? 1u : 0u;
+            if (CTAS == 2) ptx::mma_f16_ss_2cta(tmem_d, adesc + kAStep * k, bdesc + kBStep * k, sched.idesc, acc);
+            else ptx::mma_f16_ss(tmem_d, adesc + kAStep * k, bdesc + kBStep * k, sched.idesc, acc);
           }
           if (CTAS == 2) ptx::mma_commit_2cta(&empty[stage], 0x3);
           else ptx::mma_commit(&empty[stage]);
@@ -232,9 +301,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (CTAS == 2) ptx::mbar_arrive_cluster(tempty_addr[a]);
       else ptx::mbar_arrive(&tempty[a]);
     };
+    const int mn_tiles = sched.m_tiles * sched.n_tiles;
     for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
-      const int m_pair = t / sched.n_tiles, n_tile = t - m_pair * sched.n_tiles;
+      const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
+      const int m_pair = tt / sched.n_tiles, n_tile = tt - m_pair * sched.n_tiles;
       const int m_tile = m_pair * CTAS + rank;   // 128-row block of this CTA
+      const float* bias = ks == 0 ? p.bias : nullptr;   // (split-K: the first slice carries the bias)
       const long long grow = static_cast<long long>(m_tile) * kBM + row;
       const bool row_ok = grow < p.M;
       const int col_base = n_tile * kLinBN + half * (kLinBN / 2);
@@ -256,9 +328,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::tmem_ld32(taddr + cc * 32, v);
         // operands of the elementwise tail are fetched while the TMEM load is in flight
         float4 b4[8];
-        if (p.bias != nullptr && full_chunk) {
+        if (bias != nullptr && full_chunk) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + col) + j);
+          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col) + j);
         }
         uint4 r4[4];
         const bool res_vec = p.residual != nullptr && row_ok && full_chunk;
@@ -276,7 +348,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+        if (bias != nullptr) {
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -288,7 +360,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col + j < p.N) f[j] += __ldg(p.bias + col + j);
+              if (col + j < p.N) f[j] += __ldg(bias + col + j);
           }
         }
         if (ACT == 1) {
@@ -303,15 +375,24 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float2 x = unpack2(w[q], p.fmt);
-                f[j4 * 8 + q * 2] += x.x;
-                f[j4 * 8 + q * 2 + 1] += x.y;
+                if (ACT == 2) {
+                  f[j4 * 8 + q * 2] *= gelu_erf_grad(x.x);
+                  f[j4 * 8 + q * 2 + 1] *= gelu_erf_grad(x.y);
+                } else {
+                  f[j4 * 8 + q * 2] += x.x;
+                  f[j4 * 8 + q * 2 + 1] += x.y;
+                }
               }
             }
           } else {
             const uint16_t* r16 = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col + j < p.N) f[j] += unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
+              if (col + j < p.N) {
+                const float x = unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
+                if (ACT == 2) f[j] *= gelu_erf_grad(x);
+                else f[j] += x;
+              }
           }
         }
         // stage the 32 x 32 box (swizzled exactly as the output tensor map expects) and hand it to the TMA unit
@@ -340,7 +421,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          ptx::tma_store_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
+          if (RED) ptx::tma_reduce_add_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
+          else ptx::tma_store_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
           ptx::bulk_commit_group();
         }
         ++nstore;

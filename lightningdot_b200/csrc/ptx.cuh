@@ -158,6 +158,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_
                ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// the same box ADDED to global memory (element type and add come from the tensor map: FLOAT32 maps only)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // wait until at most N of this thread's bulk groups still have to READ their shared-memory source
 template <int N>
@@ -303,13 +309,27 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand tile, SWIZZLE_128B, as landed by TMA from a row-major [K, MN] matrix in 64 (K) x 64 (MN) boxes:
+// 128 B rows run along MN, 8 K-rows form a 1024 B swizzle atom (SBO), consecutive 64-wide MN blocks are whole boxes
+// (64 K rows x 128 B = 8192 B, LBO) apart.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(8192 >> 4) << 16;     // LBO = 8192 B
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;     // SBO = 1024 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16: D fp32, A/B both 16-bit (fmt: 0 = fp16, 1 = bf16), both K-major.
-__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N) {
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt, uint32_t M, uint32_t N, uint32_t a_mn = 0,
+                                                      uint32_t b_mn = 0) {
   return (1u << 4)            // D format: F32
          | (fmt << 7)         // A format
          | (fmt << 10)        // B format
-         | (0u << 15)         // A K-major
-         | (0u << 16)         // B K-major
+         | (a_mn << 15)       // A major: 0 = K, 1 = MN
+         | (b_mn << 16)       // B major
          | ((N >> 3) << 17)   // N / 8
          | ((M >> 4) << 24);  // M / 16
 }

@@ -64,6 +64,8 @@ def ncu_report(tag, rep, name, traffic_key=None, kernel_index=0, traffic=None):
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = [f"# ncu --set full --clock-control none --import-source on ({rep}); kernel {kernel_index} of the capture"]
+    if 2 + kernel_index >= len(rows):
+        return
     data = rows[2 + kernel_index]
     col = {h: i for i, h in enumerate(hdr)}
     lines.append("kernel: " + data[col["Kernel Name"]][:200])
