@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LDOT_ABI_VERSION 2
+#define LDOT_ABI_VERSION 3
 
 #define LDOT_OK 0
 #define LDOT_ERR_ARG (-1)
@@ -141,6 +141,65 @@ int ldot_split16(const float* d_in, int64_t rows, int32_t K, int32_t side, void*
 int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap_weight, const int64_t* d_pos,
                      int64_t bq, int64_t bc, int32_t reduction, float* d_scores_out, float* d_row_loss,
                      int32_t* d_row_correct, float* d_loss, int64_t* d_correct, void* stream);
+
+/* ---- training step: the backward of train_itm.py:191-289 through the towers and the loss ---------
+ * The reference gets all of this from torch autograd + apex; these entry points are what the autograd Functions of
+ * lightningdot_b200/training.py call.  Activations and activation gradients are 16-bit of `dtype`, parameter gradients
+ * fp32 and ACCUMULATED (+=) like torch's .grad.
+ *
+ * ldot_gemm          out[M, N] (+)= op(A) . op(B)^T on the tcgen05 kernel with either operand K-major (a_mn / b_mn = 0:
+ *                    row-major [M, K] / [N, K]) or MN-major (1: row-major [K, M] / [K, N], used as stored):
+ *                      forward  x W^T          a_mn 0, b_mn 0   (== ldot_linear)
+ *                      dgrad    dX = dY W      a_mn 0, b_mn 1   A = dY [M, K = out], B = W [K = out, N = in]
+ *                      wgrad    dW += dY^T X   a_mn 1, b_mn 1   A = dY [K = tokens, M = out], B = X [K = tokens, N = in],
+ *                                                               accumulate = 1, fp32 out, split-K over the grid with
+ *                                                               TMA reduce-add stores
+ *                    epi: 0 none, 1 erf-GELU, 2 out = acc * GELU'(aux[m, n]), 3 out = acc + aux[m, n] (aux 16-bit)
+ * ldot_layernorm_bwd dx = LayerNorm backward of y = LN(x) * gamma + beta given dy; dgamma / dbeta [H] += ; when
+ *                    d_dxsum != NULL also dxsum[H] += sum_rows dx (the bias gradient of the Linear that produced x).
+ *                    *_f32 flags: the tensor is fp32 instead of 16-bit.  H = 256 * {1,2,3,4,6}
+ * ldot_attention_bwd d_dqkv [B * S, 3 H] = backward of ldot_attention (q_rows = S) given d_dctx [B * S, H]; the
+ *                    probabilities are recomputed from the saved d_qkv, d_ctx is the saved forward output
+ * ldot_gelu / ldot_gelu_bwd      elementwise erf-GELU (16-bit) and dx = dy * GELU'(x); n % 8 == 0
+ * ldot_colsum16      d_out[N] += column sums of a 16-bit [rows, N] matrix (bias gradients)
+ * ldot_embed_text_sum / ldot_embed_scatter   text-embedding backward (uniter_model/model/model.py:233-246): the fp32
+ *                    LayerNorm input word + pos + type0 recomputed; dword[ids] += dx (row 0 = padding_idx skipped),
+ *                    dpos[pos_ids] += dx
+ * ldot_embed_image_pre / ldot_pos_wgrad      image-embedding backward (model.py:262-273): the fp32 LayerNorm inputs
+ *                    q = pos_linear(box) and spre = LN_img(lin) + LN_pos(q) + type1 recomputed; dW_pos[H, 7] += dq^T box
+ * ldot_inbatch_nll_bwd   d_dscores [bq, ld_ds] 16-bit = upstream * (softmax(scores) - onehot(pos)) (/ bq for the mean
+ *                    reduction), columns bc .. ld_ds - 1 zero (bi_encoder.py:632-640 under autograd)
+ * ldot_sumsq         d_out[0] += sum g^2 (gradient norm, train_itm.py:262-267)
+ * ldot_adamw         torch.optim.AdamW step over one flat fp32 tensor (bi_encoder.py:566-576), `step` counted from 1;
+ *                    d_sumsq != NULL: gradients are first scaled by min(1, max_norm / (sqrt(*d_sumsq) + 1e-6));
+ *                    d_p16 != NULL: the updated parameter is also written as 16-bit of `dtype`                      */
+int ldot_gemm(const void* d_a, int64_t lda, int32_t a_mn, const void* d_b, int64_t ldb, int32_t b_mn,
+              const float* d_bias, const void* d_aux, int64_t ld_aux, void* d_out, int64_t ldo, int64_t M, int32_t N,
+              int64_t K, int32_t dtype, int32_t epi, int32_t out_f32, int32_t accumulate, void* stream);
+int ldot_layernorm_bwd(const void* d_dy, int64_t ld_dy, int32_t dy_f32, const void* d_x, int64_t ld_x, int32_t x_f32,
+                       const float* d_gamma, void* d_dx, int64_t ld_dx, int32_t dx_f32, float* d_dgamma,
+                       float* d_dbeta, float* d_dxsum, int64_t rows, int32_t H, int32_t dtype, void* stream);
+int ldot_attention_bwd(const void* d_qkv, const int64_t* d_mask, const void* d_ctx, const void* d_dctx, void* d_dqkv,
+                       int32_t B, int32_t S, int32_t H, int32_t heads, int32_t dtype, void* stream);
+int ldot_gelu(const void* d_x, void* d_out, int64_t n, int32_t dtype, void* stream);
+int ldot_gelu_bwd(const void* d_x, const void* d_dy, void* d_dx, int64_t n, int32_t dtype, void* stream);
+int ldot_colsum16(const void* d_in, int64_t ld, int64_t rows, int32_t N, float* d_out, int32_t dtype, void* stream);
+int ldot_embed_text_sum(const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride, const void* d_word,
+                        const void* d_pos, const void* d_type0, float* d_out, int32_t B, int32_t L, int32_t H,
+                        int32_t vocab, int32_t max_pos, int32_t dtype, void* stream);
+int ldot_embed_scatter(const float* d_dx, const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride,
+                       float* d_dword, float* d_dpos, int32_t B, int32_t L, int32_t H, int32_t vocab, int32_t max_pos,
+                       void* stream);
+int ldot_embed_image_pre(const float* d_lin, const float* d_box, const float* d_img_g, const float* d_img_b,
+                         const float* d_pos_w, const float* d_pos_bias, const float* d_pos_g, const float* d_pos_b,
+                         const float* d_type1, float* d_q, float* d_spre, int64_t rows, int32_t H, void* stream);
+int ldot_pos_wgrad(const float* d_dq, const float* d_box, int64_t rows, int32_t H, float* d_dw, void* stream);
+int ldot_inbatch_nll_bwd(const float* d_scores, const int64_t* d_pos, int64_t bq, int64_t bc, const float* d_upstream,
+                         int32_t reduction, void* d_dscores, int64_t ld_ds, int32_t dtype, void* stream);
+int ldot_sumsq(const float* d_g, int64_t n, float* d_out, void* stream);
+int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int32_t step, const float* d_sumsq, float max_norm,
+               int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
 
-ABI_VERSION = 2   # LDOT_ABI_VERSION of include/ldot.h
+ABI_VERSION = 3   # LDOT_ABI_VERSION of include/ldot.h
 COARSE_FP16 = 0
 COARSE_BF16 = 1
 
@@ -52,6 +52,27 @@ SIGNATURES = {
     "ldot_split16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ldot_inbatch_nll": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    # training step
+    "ldot_gemm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p,
+                            c_int64, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_layernorm_bwd": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64,
+                                     c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
+    "ldot_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_void_p]),
+    "ldot_gelu": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "ldot_gelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "ldot_colsum16": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),
+    "ldot_embed_text_sum": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                      c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_embed_scatter": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_void_p]),
+    "ldot_embed_image_pre": (c_int32, [c_void_p] * 11 + [c_int64, c_int32, c_void_p]),
+    "ldot_pos_wgrad": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "ldot_inbatch_nll_bwd": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_int64, c_int32,
+                                       c_void_p]),
+    "ldot_sumsq": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "ldot_adamw": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                             c_float, c_int32, c_void_p, c_float, c_int32, c_void_p]),
 }
 
 

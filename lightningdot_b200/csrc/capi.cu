@@ -67,7 +67,7 @@ int make_tmap_kblocks_16b(CUtensorMap* out, const void* base, uint64_t rows, uin
 }
 
 int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,
-                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows) {
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool as_float) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(kErrCuda, "cuTensorMapEncodeTiled entry point not available");
   LDOT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && row_stride_bytes % 16 == 0,
@@ -78,7 +78,10 @@ int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint
   const cuuint64_t gstride[1] = {row_stride_bytes};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = fn(out, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32, 2,
+  const CUtensorMapDataType dt = elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                 : as_float     ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+  const CUresult r = fn(out, dt, 2,
                         const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         inner == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -112,7 +115,7 @@ ProfState& prof_state() {
 const char* kernel_class_name(int c) {
   static const char* names[kKcCount] = {"coarse_score_topk", "select", "rescore", "query_prepare", "index_prepare",
                                         "exact_scan", "merge", "linear_tcgen05", "attention", "layernorm", "embed",
-                                        "cast", "nll"};
+                                        "cast", "nll", "optim"};
   return c >= 0 && c < kKcCount ? names[c] : "?";
 }
 
@@ -208,6 +211,8 @@ int split16_run(const float* in, long long rows, int K, int side, void* out, voi
 int nll_run(const float* s1, const float* s2, float w, const long long* pos, long long bq, long long bc, int reduction,
             float* s_out, float* row_loss, int* row_correct, float* loss, long long* correct, void* stream);
 }
+
+#include "train_params.h"
 
 using namespace ldot;
 
@@ -402,6 +407,110 @@ int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap
                "null pointer argument");
   return nll_run(d_scores, d_scores_cap, cap_weight, reinterpret_cast<const long long*>(d_pos), bq, bc, reduction,
                  d_scores_out, d_row_loss, d_row_correct, d_loss, reinterpret_cast<long long*>(d_correct), stream);
+}
+
+// ---- training step ----------------------------------------------------------------------
+int ldot_gemm(const void* d_a, int64_t lda, int32_t a_mn, const void* d_b, int64_t ldb, int32_t b_mn,
+              const float* d_bias, const void* d_aux, int64_t ld_aux, void* d_out, int64_t ldo, int64_t M, int32_t N,
+              int64_t K, int32_t dtype, int32_t epi, int32_t out_f32, int32_t accumulate, void* stream) {
+  LDOT_REQUIRE(d_a && d_b && d_out, "null pointer argument");
+  return gemm_run(d_a, lda, a_mn, d_b, ldb, b_mn, d_bias, d_aux, ld_aux, d_out, ldo, M, N, K, dtype, epi, out_f32,
+                  accumulate, stream);
+}
+
+int ldot_layernorm_bwd(const void* d_dy, int64_t ld_dy, int32_t dy_f32, const void* d_x, int64_t ld_x, int32_t x_f32,
+                       const float* d_gamma, void* d_dx, int64_t ld_dx, int32_t dx_f32, float* d_dgamma,
+                       float* d_dbeta, float* d_dxsum, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_dy && d_x && d_gamma && d_dx && d_dgamma && d_dbeta, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  LnBwdParams p;
+  p.dy = d_dy; p.ld_dy = ld_dy; p.dy_f32 = dy_f32; p.x = d_x; p.ld_x = ld_x; p.x_f32 = x_f32; p.gamma = d_gamma;
+  p.dx = d_dx; p.ld_dx = ld_dx; p.dx_f32 = dx_f32; p.dgamma = d_dgamma; p.dbeta = d_dbeta; p.dxsum = d_dxsum;
+  p.rows = rows; p.fmt = dtype;
+  return ln_bwd_run(p, H, stream);
+}
+
+int ldot_attention_bwd(const void* d_qkv, const int64_t* d_mask, const void* d_ctx, const void* d_dctx, void* d_dqkv,
+                       int32_t B, int32_t S, int32_t H, int32_t heads, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_qkv && d_mask && d_ctx && d_dctx && d_dqkv, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return attention_bwd_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, d_dctx, d_dqkv, B, S, H, heads,
+                           dtype, stream);
+}
+
+int ldot_gelu(const void* d_x, void* d_out, int64_t n, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_x && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return gelu_run(d_x, nullptr, d_out, n, 0, dtype, stream);
+}
+
+int ldot_gelu_bwd(const void* d_x, const void* d_dy, void* d_dx, int64_t n, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_x && d_dy && d_dx, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return gelu_run(d_x, d_dy, d_dx, n, 1, dtype, stream);
+}
+
+int ldot_colsum16(const void* d_in, int64_t ld, int64_t rows, int32_t N, float* d_out, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_in && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return colsum16_run(d_in, ld, rows, N, d_out, dtype, stream);
+}
+
+int ldot_embed_text_sum(const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride, const void* d_word,
+                        const void* d_pos, const void* d_type0, float* d_out, int32_t B, int32_t L, int32_t H,
+                        int32_t vocab, int32_t max_pos, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_ids && d_pos_ids && d_word && d_pos && d_type0 && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return embed_text_sum_run(reinterpret_cast<const long long*>(d_ids), reinterpret_cast<const long long*>(d_pos_ids),
+                            pos_batch_stride, d_word, d_pos, d_type0, d_out, B, L, H, vocab, max_pos, dtype, stream);
+}
+
+int ldot_embed_scatter(const float* d_dx, const int64_t* d_ids, const int64_t* d_pos_ids, int64_t pos_batch_stride,
+                       float* d_dword, float* d_dpos, int32_t B, int32_t L, int32_t H, int32_t vocab, int32_t max_pos,
+                       void* stream) {
+  LDOT_REQUIRE(d_dx && d_ids && d_pos_ids && d_dword && d_dpos, "null pointer argument");
+  return embed_scatter_run(d_dx, reinterpret_cast<const long long*>(d_ids), reinterpret_cast<const long long*>(d_pos_ids),
+                           pos_batch_stride, d_dword, d_dpos, B, L, H, vocab, max_pos, stream);
+}
+
+int ldot_embed_image_pre(const float* d_lin, const float* d_box, const float* d_img_g, const float* d_img_b,
+                         const float* d_pos_w, const float* d_pos_bias, const float* d_pos_g, const float* d_pos_b,
+                         const float* d_type1, float* d_q, float* d_spre, int64_t rows, int32_t H, void* stream) {
+  LDOT_REQUIRE(d_lin && d_box && d_img_g && d_img_b && d_pos_w && d_pos_bias && d_pos_g && d_pos_b && d_type1 && d_q &&
+                   d_spre, "null pointer argument");
+  EmbedImagePreParams p;
+  p.lin = d_lin; p.box = d_box; p.img_g = d_img_g; p.img_b = d_img_b; p.pos_w = d_pos_w; p.pos_bias = d_pos_bias;
+  p.pos_g = d_pos_g; p.pos_b = d_pos_b; p.type1 = d_type1; p.q = d_q; p.spre = d_spre; p.rows = rows;
+  return embed_image_pre_run(p, H, stream);
+}
+
+int ldot_pos_wgrad(const float* d_dq, const float* d_box, int64_t rows, int32_t H, float* d_dw, void* stream) {
+  LDOT_REQUIRE(d_dq && d_box && d_dw, "null pointer argument");
+  return pos_wgrad_run(d_dq, d_box, rows, H, d_dw, stream);
+}
+
+int ldot_inbatch_nll_bwd(const float* d_scores, const int64_t* d_pos, int64_t bq, int64_t bc, const float* d_upstream,
+                         int32_t reduction, void* d_dscores, int64_t ld_ds, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_scores && d_pos && d_upstream && d_dscores, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return nll_bwd_run(d_scores, reinterpret_cast<const long long*>(d_pos), bq, bc, d_upstream, reduction, d_dscores,
+                     ld_ds, dtype, stream);
+}
+
+int ldot_sumsq(const float* d_g, int64_t n, float* d_out, void* stream) { return sumsq_run(d_g, n, d_out, stream); }
+
+int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int32_t step, const float* d_sumsq, float max_norm,
+               int32_t dtype, void* stream) {
+  LDOT_REQUIRE(step >= 1, "adamw: step counts from 1");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  AdamParams a;
+  a.p = d_p; a.g = d_g; a.m = d_m; a.v = d_v; a.p16 = static_cast<uint16_t*>(d_p16); a.n = n;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  a.sumsq = d_sumsq; a.max_norm = max_norm; a.fmt = dtype;
+  return adamw_run(a, stream);
 }
 
 }  // extern "C"

@@ -41,10 +41,10 @@ static int eye_pointer(int fmt, cudaStream_t st, const uint16_t** out) {
   return kOk;
 }
 
-template <int ACT, int OUT_F32, int CTAS>
+template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
-  auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS>;
+  auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS, AMN, BMN, RED>;
   using SM = LinSmemT<CTAS>;
   static bool configured = false;  // (one device per process)
   static int max_groups = 0;       // resident CTAs (CTAS = 1) or CTA pairs (CTAS = 2)
@@ -116,6 +116,8 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   s.n_tiles = (N + kLinBN - 1) / kLinBN;
   s.num_tiles = s.m_tiles * s.n_tiles;
   s.k_blocks = (K + kBK - 1) / kBK;
+  s.k_splits = 1;
+  s.kb_per_split = s.k_blocks;
   s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM * ctas, kLinBN);
   LinParams p;
   p.bias = bias;
@@ -132,6 +134,88 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   if (act == 1) return out_f32 ? LDOT_LIN(1, 1) : LDOT_LIN(1, 0);
   return out_f32 ? LDOT_LIN(0, 1) : LDOT_LIN(0, 0);
 #undef LDOT_LIN
+}
+
+// General form used by the training backward (include/ldot.h: ldot_gemm): either operand K-major or MN-major, optional
+// accumulation into an fp32 output (split-K over the persistent grid), GELU-gradient / residual epilogues.
+int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, const float* bias,
+             const void* aux, long long ld_aux, void* out, long long ldo, long long M, int N, long long K, int fmt,
+             int epi, int out_f32, int accumulate, void* stream) {
+  LDOT_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad GEMM shape M=%lld N=%d K=%lld", M, N, K);
+  LDOT_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE(epi >= 0 && epi <= 3, "epi must be 0 (none), 1 (GELU), 2 (* GELU'(aux)) or 3 (+ aux)");
+  LDOT_REQUIRE((epi == 2 || epi == 3) == (aux != nullptr), "aux is required by (and only by) epi 2 / 3");
+  LDOT_REQUIRE(!accumulate || (out_f32 && epi == 0), "accumulate needs an fp32 output and no epilogue op");
+  LDOT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda / ldb must be multiples of 8 elements");
+  LDOT_REQUIRE(a_mn ? (M % 8 == 0) : (K % 8 == 0), "the contiguous extent of A must be a multiple of 8");
+  LDOT_REQUIRE(b_mn ? (N % 8 == 0) : (K % 8 == 0), "the contiguous extent of B must be a multiple of 8");
+  LDOT_REQUIRE(out_f32 ? (ldo % 4 == 0) : (ldo % 8 == 0), "ldo alignment");
+  LDOT_REQUIRE(!aux || ld_aux % 8 == 0, "ld_aux alignment");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+               "out / aux / bias must be 16-byte aligned");
+  LDOT_REQUIRE(M < (1ll << 31) - 256 && K < (1ll << 31) - 64, "M / K too large");
+  const int variant = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
+  if (variant == 0 && !accumulate && epi != 2)
+    return linear_run(a, lda, b, ldb, bias, epi == 3 ? aux : nullptr, ld_aux, out, ldo, M, N, static_cast<int>(K), fmt,
+                      epi == 1 ? 1 : 0, out_f32, stream);
+  // the forms the backward pass uses: dgrad (A K-major, B MN-major; 16-bit or fp32 out) and wgrad (both MN-major,
+  // accumulating fp32)
+  LDOT_REQUIRE((variant == 1 && !accumulate && epi != 1) || (variant == 3 && accumulate),
+               "unsupported operand layout / epilogue combination (a_mn=%d b_mn=%d epi=%d accumulate=%d)", a_mn, b_mn,
+               epi, accumulate);
+  LDOT_REQUIRE(!(epi == 2 && out_f32), "the GELU-gradient epilogue writes 16-bit output");
+  int sms = 0;
+  if (int e = device_sm_count(&sms)) return e;
+  // (wgrad tiles are few and K-split: CTA pairs would only halve the number of work items)
+  const int ctas = variant == 3 ? 1 : linear_ctas(M, N, sms);
+  CUtensorMap ta, tb, to;
+  if (a_mn) {
+    if (int e = make_tmap_kmajor_16b(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, kBK)) return e;
+  } else {
+    if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
+  }
+  if (b_mn) {
+    if (int e = make_tmap_kmajor_16b(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, kBK)) return e;
+  } else {
+    if (int e = make_tmap_kmajor_16b(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, kLinBN / ctas)) return e;
+  }
+  const uint32_t elt = out_f32 ? 4 : 2;
+  if (int e = make_tmap_store(&to, out, elt, M, N, static_cast<uint64_t>(ldo) * elt, 32, 32, accumulate != 0)) return e;
+  LinSched s;
+  s.m_tiles = static_cast<int>((M + kBM * ctas - 1) / (kBM * ctas));
+  s.n_tiles = (N + kLinBN - 1) / kLinBN;
+  s.k_blocks = static_cast<int>((K + kBK - 1) / kBK);
+  s.k_splits = 1;
+  s.kb_per_split = s.k_blocks;
+  if (accumulate) {
+    // enough K slices that every SM (pair) gets about two work items
+    const int mn = s.m_tiles * s.n_tiles, groups = sms / ctas;
+    int want = (2 * groups + mn - 1) / mn;
+    want = want < 1 ? 1 : (want > s.k_blocks ? s.k_blocks : want);
+    s.kb_per_split = (s.k_blocks + want - 1) / want;
+    s.k_splits = (s.k_blocks + s.kb_per_split - 1) / s.kb_per_split;
+  }
+  s.num_tiles = s.m_tiles * s.n_tiles * s.k_splits;
+  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM * ctas, kLinBN, a_mn ? 1u : 0u, b_mn ? 1u : 0u);
+  LinParams p;
+  p.bias = bias;
+  p.residual = aux;
+  p.ldr = ld_aux;
+  p.M = M;
+  p.N = N;
+  p.fmt = fmt;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
+                 (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * elt +
+                     (aux ? static_cast<double>(M) * N * 2.0 : 0.0));
+#define LDOT_G(ACT, F32, AMN, BMN, RED)                                                     \
+  (ctas == 2 ? launch_linear<ACT, F32, 2, AMN, BMN, RED>(ta, tb, to, s, p, sms, st)        \
+             : launch_linear<ACT, F32, 1, AMN, BMN, RED>(ta, tb, to, s, p, sms, st))
+  if (variant == 3) return launch_linear<0, 1, 1, 1, 1, 1>(ta, tb, to, s, p, sms, st);
+  if (epi == 2) return LDOT_G(2, 0, 0, 1, 0);
+  return out_f32 ? LDOT_G(0, 1, 0, 1, 0) : LDOT_G(0, 0, 0, 1, 0);
+#undef LDOT_G
 }
 
 // out = LayerNorm(A . W^T + bias + residual) * gamma + beta, 16-bit output; a cluster of ceil(N / 256) CTAs per row block

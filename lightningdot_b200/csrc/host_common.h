@@ -55,8 +55,9 @@ int make_tmap_kblocks_16b(CUtensorMap* out, const void* base, uint64_t rows, uin
 
 // 2-D tensor map of a row-major [rows, cols] matrix of `elt_bytes`-wide elements for TMA stores of
 // [box_rows, box_cols] boxes whose inner extent (box_cols * elt_bytes) is 64 B (SWIZZLE_64B) or 128 B (SWIZZLE_128B).
+// as_float: 4-byte elements are typed FLOAT32 (required by cp.reduce.async.bulk.tensor .add; plain stores do not care).
 int make_tmap_store(CUtensorMap* out, const void* base, uint32_t elt_bytes, uint64_t rows, uint64_t cols,
-                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows);
+                    uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows, bool as_float = false);
 
 int device_sm_count(int* out);
 

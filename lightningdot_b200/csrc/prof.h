@@ -21,6 +21,7 @@ enum KernelClass : int {
   kKcEmbed,
   kKcCast,           // casts / hi-lo splits
   kKcNll,
+  kKcOptim,          // AdamW / gradient norm
   kKcCount
 };
 
