@@ -16,6 +16,8 @@ COARSE_FP16 = 0
 COARSE_BF16 = 1
 
 _lib = None
+# bumped by in-place parameter updates that bypass torch's version counters (FusedAdamW): part of the towers' cache key
+param_generation = [0]
 
 # name -> (restype, argtypes): every symbol include/ldot.h declares
 SIGNATURES = {

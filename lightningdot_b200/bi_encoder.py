@@ -32,6 +32,7 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from . import _lib
 from .towers import TowerEngine
+from .training import FusedAdamW, NllFunction, run_tower_training
 
 logger = logging.getLogger()
 
@@ -192,6 +193,7 @@ def _make_proj(hidden, project_dim):
 
 class _TowerBase(nn.Module):
     KIND = None
+    _warned = False
 
     def __init__(self, config, project_dim: int = 0):
         super().__init__()
@@ -222,7 +224,8 @@ class _TowerBase(nn.Module):
     # -- engine management -----------------------------------------------------------------------------------------
     def _signature(self):
         ps = list(self.parameters())
-        return (self.compute_dtype, ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
+        return (self.compute_dtype, ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]),
+                _lib.param_generation[0])
 
     def engine(self) -> TowerEngine:
         """(Re)build the 16-bit inference copies when parameters, device or compute dtype changed."""
@@ -239,11 +242,18 @@ class _TowerBase(nn.Module):
             self._engine, self._engine_sig = eng, sig
         return self._engine
 
-    def _check_inference(self):
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError(
-                "training-mode forward (autograd through the towers) is not implemented in this round: the CUDA path "
-                "covers inference (eval() / torch.no_grad()); see DESIGN.md, scope row f1")
+    def _wants_grad(self):
+        """True when this call must be recorded for backward (train_itm.py:191-258): grad mode on and trainable
+        parameters.  The training path keeps activations and attaches a TowerFunction node (training.py)."""
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _train_forward(self, kind, inputs):
+        c = self.config
+        if self.training and (c.hidden_dropout_prob > 0 or c.attention_probs_dropout_prob > 0) and not _TowerBase._warned:
+            logger.warning("training forward: dropout (hidden %.2f / attention %.2f) is not applied by the CUDA path; "
+                           "the deterministic network is trained", c.hidden_dropout_prob, c.attention_probs_dropout_prob)
+            _TowerBase._warned = True
+        return run_tower_training(self, self.engine(), kind, inputs)
 
 
 class BertEncoder(_TowerBase):
@@ -270,7 +280,11 @@ class BertEncoder(_TowerBase):
         """-> (sequence_output, pooled_output, hidden_states=None) as bi_encoder.py:107-123.  need_sequence=False (what
         BiEncoder.forward passes unless output_all_encoded_layers is set) returns sequence_output=None and lets the
         engine evaluate the last layer for the [CLS] position only; pooled_output is unchanged."""
-        self._check_inference()
+        if self._wants_grad():
+            if need_sequence:
+                raise NotImplementedError("gradients flow through pooled_output only: call with need_sequence=False "
+                                          "(BiEncoder.forward does) or under torch.no_grad()")
+            return None, self._train_forward("txt", (input_ids, attention_mask, position_ids)), None
         seq, pooled = self.engine().encode_text(input_ids, attention_mask, position_ids, want_seq=need_sequence)
         hidden_states = None
         return seq, pooled, hidden_states
@@ -301,9 +315,16 @@ class UniterEncoder(_TowerBase):
     def forward(self, input_ids, attention_mask, position_ids,
                 img_feat, img_pos_feat, img_masks, gather_index=None, need_sequence=True) -> Tuple[T, ...]:
         """bi_encoder.py:163-191; need_sequence as in BertEncoder.forward."""
-        self._check_inference()
         if img_masks is not None:
             raise NotImplementedError("img_masks (masked-region modelling, pre-training only) is outside the retrieval path")
+        if self._wants_grad():
+            if need_sequence:
+                raise NotImplementedError("gradients flow through pooled_output only: call with need_sequence=False "
+                                          "(BiEncoder.forward does) or under torch.no_grad()")
+            if img_feat is None:
+                return None, self._train_forward("txt", (input_ids, attention_mask, position_ids)), None
+            return None, self._train_forward("img", (input_ids, attention_mask, position_ids, img_feat, img_pos_feat,
+                                                     gather_index)), None
         eng = self.engine()
         if img_feat is None:   # txt_model_type == 'uniter-base': text through the UNITER body
             seq, pooled = eng.encode_text(input_ids, attention_mask, position_ids, want_seq=need_sequence)
@@ -448,33 +469,19 @@ class BiEncoderNllLoss(object):
         Computes nll loss for the given lists of question and ctx vectors (bi_encoder.py:615-656).
         :return: a tuple of loss value and amount of correct predictions per batch (and the score matrix)
         """
-        if torch.is_grad_enabled() and (q_vectors.requires_grad or ctx_vectors.requires_grad):
-            raise NotImplementedError("the loss backward is not implemented in this round (DESIGN.md, scope row f1); "
-                                      "call under torch.no_grad()")
         if reduction not in ('mean', 'sum'):
             raise ValueError("reduction must be 'mean' or 'sum'")
-        lib = _lib.load()
-        scores_img = self.get_scores(q_vectors, ctx_vectors)
-        use_cap = caption_vectors is not None and caption_score_weight != 0
-        scores_cap = self.get_scores(q_vectors, caption_vectors) if use_cap else None
-        bq, bc = scores_img.shape
-        dev = scores_img.device
+        # (hard_negatice_idx_per_question is accepted and unused, exactly as in the reference)
+        dev = q_vectors.device
         pos = torch.as_tensor(positive_idx_per_question, dtype=torch.int64, device=dev).contiguous()
-        if pos.numel() != bq:
+        if pos.numel() != q_vectors.shape[0]:
             raise ValueError("one positive index per question expected")
-        if int(pos.min()) < 0 or int(pos.max()) >= bc:
+        if int(pos.min()) < 0 or int(pos.max()) >= ctx_vectors.shape[0]:
             raise IndexError("positive index out of range")
-        # contiguous copies: the kernels take dense [bq, bc] matrices
-        s1 = scores_img.contiguous()
-        s2 = scores_cap.contiguous() if use_cap else None
-        scores = torch.empty((bq, bc), dtype=torch.float32, device=dev)
-        row_loss = torch.empty((bq,), dtype=torch.float32, device=dev)
-        row_correct = torch.empty((bq,), dtype=torch.int32, device=dev)
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        correct = torch.empty((), dtype=torch.int64, device=dev)
-        _lib.check(lib.ldot_inbatch_nll(_lib.ptr(s1), _lib.ptr(s2), float(caption_score_weight), _lib.ptr(pos), bq, bc,
-                                        0 if reduction == 'mean' else 1, _lib.ptr(scores), _lib.ptr(row_loss),
-                                        _lib.ptr(row_correct), _lib.ptr(loss), _lib.ptr(correct), _lib.stream_ptr()))
+        w = float(caption_score_weight) if caption_vectors is not None else 0.0
+        # one autograd node: scores + NLL forward, tensor-core backward to the embeddings (training.py: NllFunction)
+        loss, correct, scores, scores_img = NllFunction.apply(q_vectors, ctx_vectors, caption_vectors if w != 0 else None,
+                                                              pos, w, 0 if reduction == 'mean' else 1, self.get_scores)
         if experiment is not None:
             experiment.log_metric('score_img_diag_mean', torch.diag(scores_img).mean().item())
             experiment.log_metric('score_diag_mean', torch.diag(scores).mean().item())
@@ -500,7 +507,10 @@ def get_optimizer(model: nn.Module, learning_rate: float = 1e-5, adam_eps: float
          'weight_decay': weight_decay},
         {'params': [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)], 'weight_decay': 0.0}
     ]
-    return torch.optim.AdamW(optimizer_grouped_parameters, lr=learning_rate, eps=adam_eps)
+    # same update rule, one kernel launch per group over flat fp32 master buffers (training.py: FusedAdamW).  The model may
+    # still be on the host here (train_itm.py builds the optimiser before setup_for_distributed_mode moves it): the
+    # flat buffers are laid out at the first step(), when the parameters are on the device.
+    return FusedAdamW(optimizer_grouped_parameters, lr=learning_rate, eps=adam_eps)
 
 
 def setup_for_distributed_mode(model: nn.Module, optimizer: torch.optim.Optimizer, device: object, n_gpu: int = 1,

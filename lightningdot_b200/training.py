@@ -1,0 +1,550 @@
+"""Training step of the two towers on the device: forward with saved activations, hand-written backward, and the
+torch.autograd.Function that lets train_itm.py's `loss.backward()` drive it.
+
+The reference gets its gradients from torch autograd over apex-amp fp16 modules (train_itm.py:252-267,
+dvl/models/bi_encoder.py:589-601).  Here one autograd node per tower call owns the whole tower:
+
+    forward    embeddings -> 12 x [QKV GEMM, attention, O GEMM + residual, LayerNorm, FFN-up GEMM, GELU, FFN-down GEMM
+               + residual, LayerNorm] -> [CLS] rows -> projection head, keeping 16-bit activations per layer
+               (x, qkv, ctx, pre-LN sums, FFN pre-activation and activation: 24.6 KB per token per layer)
+    backward   the mirror image: LayerNorm backward (+ bias-gradient column sums) -> wgrad (split-K tcgen05 GEMM that
+               reads dY and X as stored, accumulating fp32) and dgrad (tcgen05 GEMM that reads the nn.Linear weight as
+               stored; residual-gradient add and GELU' fused in its epilogue) -> attention backward -> ... ->
+               embedding backward (scatter-add)
+
+Activations and activation gradients are bf16 (fp16 when setup_for_distributed_mode(fp16=True) selected it - without
+loss scaling fp16 gradients underflow, so bf16 is the default and the recommended training dtype); parameter gradients
+are fp32 under the reference's parameter names, so torch optimisers, clip_grad_norm_ and state_dict() keep working.
+Dropout (hidden_dropout_prob / attention_probs_dropout_prob, bi_encoder.py:97-99) is NOT applied by this path yet:
+training runs the deterministic network.
+"""
+import torch
+
+from . import _lib
+
+
+class _Tape(object):
+    """Activations one forward keeps for its backward."""
+    __slots__ = ("kind", "B", "S", "Lt", "R", "ids", "pos", "mask", "layers", "h_last", "x0", "x1", "x2", "feat16",
+                 "lin", "box", "h0")
+
+
+class TowerTrainer(object):
+    """Runs a TowerEngine's weights in training mode.  `engine.w` holds the 16-bit copies of the parameters."""
+
+    def __init__(self, engine):
+        self.e = engine
+
+    # ------------------------------------------------------------------------------------------------ primitives
+    def _gemm(self, a, lda, a_mn, b, ldb, b_mn, out, ldo, M, N, K, bias=None, aux=None, ld_aux=0, epi=0, accumulate=False):
+        lib = _lib.load()
+        _lib.check(lib.ldot_gemm(_lib.ptr(a), lda, a_mn, _lib.ptr(b), ldb, b_mn, _lib.ptr(bias), _lib.ptr(aux), ld_aux,
+                                 _lib.ptr(out), ldo, M, N, K, self.e.fmt, epi, int(out.dtype == torch.float32),
+                                 int(accumulate), _lib.stream_ptr()))
+
+    def _dgrad(self, dy, w, out, M, aux=None, epi=0, ld_dy=None, ldo=None):
+        """out[M, in] = dy[M, out] . w[out, in] (+ aux | * GELU'(aux))"""
+        O, I = w.shape
+        self._gemm(dy, O if ld_dy is None else ld_dy, 0, w, I, 1, out, I if ldo is None else ldo, M, I, O, aux=aux,
+                   ld_aux=0 if aux is None else aux.stride(0), epi=epi)
+
+    def _wgrad(self, dy, x, dw, rows, ld_x=None):
+        """dw[out, in] += dy[rows, out]^T . x[rows, in]"""
+        O, I = dw.shape
+        self._gemm(dy, O, 1, x, I if ld_x is None else ld_x, 1, dw, I, O, I, rows, accumulate=True)
+
+    def _colsum(self, x, out, rows):
+        lib = _lib.load()
+        _lib.check(lib.ldot_colsum16(_lib.ptr(x), x.stride(0), rows, x.shape[1], _lib.ptr(out), self.e.fmt, _lib.stream_ptr()))
+
+    def _ln_bwd(self, dy, x, gamma, dx, dgamma, dbeta, dxsum, rows, H, ld_dy=None, ld_x=None, ld_dx=None):
+        lib = _lib.load()
+        f32 = torch.float32
+        _lib.check(lib.ldot_layernorm_bwd(
+            _lib.ptr(dy), dy.stride(0) if ld_dy is None else ld_dy, int(dy.dtype == f32),
+            _lib.ptr(x), x.stride(0) if ld_x is None else ld_x, int(x.dtype == f32), _lib.ptr(gamma),
+            _lib.ptr(dx), dx.stride(0) if ld_dx is None else ld_dx, int(dx.dtype == f32),
+            _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dxsum), rows, H, self.e.fmt, _lib.stream_ptr()))
+
+    def _gelu(self, x, out):
+        _lib.check(_lib.load().ldot_gelu(_lib.ptr(x), _lib.ptr(out), x.numel(), self.e.fmt, _lib.stream_ptr()))
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def _forward_layers(self, h, mask, B, S, tape):
+        e, lib = self.e, _lib.load()
+        T, H, F, dt, dev, w = B * S, e.H, e.ffn, e.dtype, h.device, e.w
+        stream = _lib.stream_ptr()
+        tape.layers = []
+        for i in range(e.layers):
+            qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
+            ctx = torch.empty((T, H), dtype=dt, device=dev)
+            pre1 = torch.empty((T, H), dtype=dt, device=dev)
+            a = torch.empty((T, H), dtype=dt, device=dev)
+            fpre = torch.empty((T, F), dtype=dt, device=dev)
+            f = torch.empty((T, F), dtype=dt, device=dev)
+            pre2 = torch.empty((T, H), dtype=dt, device=dev)
+            out = torch.empty((T, H), dtype=dt, device=dev)
+            e._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
+            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, e.heads, S, e.fmt, stream))
+            e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T, residual=h)
+            e._layernorm(pre1, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
+            e._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, T)
+            self._gelu(fpre, f)
+            e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T, residual=a)
+            e._layernorm(pre2, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out, T, H)
+            tape.layers.append((h, qkv, ctx, pre1, a, fpre, f, pre2))
+            h = out
+        tape.h_last = h
+        return h
+
+    def _forward_head(self, h, B, S, tape):
+        e, w, H, dev, dt = self.e, self.e.w, self.e.H, h.device, self.e.dtype
+        if not e.project:
+            return h.view(B, S, H)[:, 0, :].float()
+        x0 = torch.empty((B, 2 * H), dtype=dt, device=dev)
+        x1 = torch.empty((B, 2 * H), dtype=dt, device=dev)
+        x2 = torch.empty((B, 2 * H), dtype=dt, device=dev)
+        out = torch.empty((B, e.out_dim), dtype=torch.float32, device=dev)
+        e._linear(h, S * H, w["p0_w"], w["p0_b"], x0, B)
+        self._gelu(x0, x1)
+        e._layernorm(x1, w["p_ln_g"], w["p_ln_b"], x2, B, 2 * H)
+        e._linear(x2, 2 * H, w["p3_w"], w["p3_b"], out, B)
+        tape.x0, tape.x1, tape.x2 = x0, x1, x2
+        return out
+
+    def forward_text(self, input_ids, attention_mask, position_ids):
+        e, dev = self.e, self.e.device
+        ids, mask, pos = e._i64(input_ids, dev), e._i64(attention_mask, dev), e._i64(position_ids, dev)
+        B, L = ids.shape
+        if L > 128:
+            raise ValueError(f"sequence length {L} > 128 is not supported by the attention kernel")
+        if pos.dim() == 1:
+            pos = pos[None, :]
+        tape = _Tape()
+        tape.kind, tape.B, tape.S, tape.Lt, tape.R = "txt", B, L, L, 0
+        tape.ids, tape.pos, tape.mask = ids, pos, mask
+        h = torch.empty((B * L, e.H), dtype=e.dtype, device=dev)
+        e._embed_text(ids, pos, h, B, L, L)
+        h = self._forward_layers(h, mask, B, L, tape)
+        return self._forward_head(h, B, L, tape), tape
+
+    def forward_image(self, input_ids, attention_mask, position_ids, img_feat, img_pos_feat, gather_index=None):
+        e, dev, w, H, lib = self.e, self.e.device, self.e.w, self.e.H, _lib.load()
+        ids, mask, pos = e._i64(input_ids, dev), e._i64(attention_mask, dev), e._i64(position_ids, dev)
+        feat = img_feat.to(device=dev, dtype=torch.float32).contiguous()
+        box = img_pos_feat.to(device=dev, dtype=torch.float32).contiguous()
+        B, Lt = ids.shape
+        R = feat.shape[1]
+        S = Lt + R
+        if S > 128:
+            raise ValueError(f"sequence length {S} > 128 is not supported by the attention kernel")
+        if mask.shape[1] != S:
+            raise ValueError(f"attention_mask has {mask.shape[1]} positions, expected {S}")
+        if gather_index is not None:
+            gi = gather_index.to(dev)
+            if not torch.equal(gi, torch.arange(S, device=dev)[None, :].expand(B, S)):
+                raise NotImplementedError("only the identity gather_index of dvl/data/itm.py is supported")
+        if pos.dim() == 1:
+            pos = pos[None, :]
+        stream = _lib.stream_ptr()
+        tape = _Tape()
+        tape.kind, tape.B, tape.S, tape.Lt, tape.R = "img", B, S, Lt, R
+        tape.ids, tape.pos, tape.mask, tape.box = ids, pos, mask, box
+        h = torch.empty((B * S, H), dtype=e.dtype, device=dev)
+        e._embed_text(ids, pos, h, B, Lt, S)
+        f16 = torch.empty((B * R, e.img_dim), dtype=e.dtype, device=dev)
+        _lib.check(lib.ldot_cast_f32(_lib.ptr(feat), _lib.ptr(f16), B * R * e.img_dim, e.fmt, stream))
+        lin = torch.empty((B * R, H), dtype=torch.float32, device=dev)
+        e._linear(f16, e.img_dim, w["img_w"], w["img_bias"], lin, B * R)
+        _lib.check(lib.ldot_embed_image(
+            _lib.ptr(lin), _lib.ptr(box), _lib.ptr(w["img_ln_g"]), _lib.ptr(w["img_ln_b"]), _lib.ptr(w["pos_w"]),
+            _lib.ptr(w["pos_bias"]), _lib.ptr(w["pos_ln_g"]), _lib.ptr(w["pos_ln_b"]), _lib.ptr(w["type1_f32"]),
+            _lib.ptr(w["iemb_ln_g"]), _lib.ptr(w["iemb_ln_b"]), _lib.ptr(h), B, R, S, Lt, H, e.fmt, stream))
+        tape.feat16, tape.lin = f16, lin
+        h = self._forward_layers(h, mask, B, S, tape)
+        return self._forward_head(h, B, S, tape), tape
+
+    # ------------------------------------------------------------------------------------------------ backward
+    def backward(self, tape, d_pooled):
+        """d_pooled fp32 [B, D] -> {reference parameter name: fp32 gradient}."""
+        e, w, lib = self.e, self.e.w, _lib.load()
+        H, F, dt, dev = e.H, e.ffn, e.dtype, d_pooled.device
+        B, S = tape.B, tape.S
+        T = B * S
+        stream = _lib.stream_ptr()
+        f32 = torch.float32
+        g = {}
+
+        def zeros(*shape):
+            return torch.zeros(shape, dtype=f32, device=dev)
+
+        def buf(rows, cols):
+            return torch.empty((rows, cols), dtype=dt, device=dev)
+
+        d_h = torch.zeros((T, H), dtype=dt, device=dev)
+        d_pooled = d_pooled.to(f32).contiguous()
+        if e.project:
+            D = e.out_dim
+            dO = buf(B, D)
+            _lib.check(lib.ldot_cast_f32(_lib.ptr(d_pooled), _lib.ptr(dO), B * D, e.fmt, stream))
+            g["encode_proj.3.weight"], g["encode_proj.3.bias"] = zeros(D, 2 * H), zeros(D)
+            self._wgrad(dO, tape.x2, g["encode_proj.3.weight"], B)
+            self._colsum(dO, g["encode_proj.3.bias"], B)
+            d_x2 = buf(B, 2 * H)
+            self._dgrad(dO, w["p3_w"], d_x2, B)
+            d_x1 = buf(B, 2 * H)
+            g["encode_proj.2.weight"], g["encode_proj.2.bias"] = zeros(2 * H), zeros(2 * H)
+            self._ln_bwd(d_x2, tape.x1, w["p_ln_g"], d_x1, g["encode_proj.2.weight"], g["encode_proj.2.bias"], None, B, 2 * H)
+            d_x0 = buf(B, 2 * H)
+            _lib.check(lib.ldot_gelu_bwd(_lib.ptr(tape.x0), _lib.ptr(d_x1), _lib.ptr(d_x0), B * 2 * H, e.fmt, stream))
+            g["encode_proj.0.weight"], g["encode_proj.0.bias"] = zeros(2 * H, H), zeros(2 * H)
+            self._wgrad(d_x0, tape.h_last, g["encode_proj.0.weight"], B, ld_x=S * H)
+            self._colsum(d_x0, g["encode_proj.0.bias"], B)
+            self._dgrad(d_x0, w["p0_w"], d_h, B, ldo=S * H)
+        else:
+            d_h.view(B, S, H)[:, 0, :] = d_pooled.to(dt)
+
+        for i in reversed(range(e.layers)):
+            x, qkv, ctx, pre1, a, fpre, f, pre2 = tape.layers[i]
+            p = f"bert.encoder.layer.{i}."
+            # BertOutput: h = LN(f W2^T + b2 + a)
+            d_pre2 = buf(T, H)
+            g[p + "output.LayerNorm.weight"], g[p + "output.LayerNorm.bias"] = zeros(H), zeros(H)
+            g[p + "output.dense.bias"] = zeros(H)
+            self._ln_bwd(d_h, pre2, w[f"ln2_g{i}"], d_pre2, g[p + "output.LayerNorm.weight"],
+                         g[p + "output.LayerNorm.bias"], g[p + "output.dense.bias"], T, H)
+            g[p + "output.dense.weight"] = zeros(H, F)
+            self._wgrad(d_pre2, f, g[p + "output.dense.weight"], T)
+            d_fpre = buf(T, F)
+            self._dgrad(d_pre2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=2)
+            # BertIntermediate
+            g[p + "intermediate.dense.weight"], g[p + "intermediate.dense.bias"] = zeros(F, H), zeros(F)
+            self._wgrad(d_fpre, a, g[p + "intermediate.dense.weight"], T)
+            self._colsum(d_fpre, g[p + "intermediate.dense.bias"], T)
+            d_a = buf(T, H)
+            self._dgrad(d_fpre, w[f"f1_w{i}"], d_a, T, aux=d_pre2, epi=3)
+            del d_fpre
+            # BertSelfOutput: a = LN(ctx Wo^T + bo + x)
+            d_pre1 = buf(T, H)
+            g[p + "attention.output.LayerNorm.weight"], g[p + "attention.output.LayerNorm.bias"] = zeros(H), zeros(H)
+            g[p + "attention.output.dense.bias"] = zeros(H)
+            self._ln_bwd(d_a, pre1, w[f"ln1_g{i}"], d_pre1, g[p + "attention.output.LayerNorm.weight"],
+                         g[p + "attention.output.LayerNorm.bias"], g[p + "attention.output.dense.bias"], T, H)
+            g[p + "attention.output.dense.weight"] = zeros(H, H)
+            self._wgrad(d_pre1, ctx, g[p + "attention.output.dense.weight"], T)
+            d_ctx = buf(T, H)
+            self._dgrad(d_pre1, w[f"o_w{i}"], d_ctx, T)
+            # self-attention
+            d_qkv = buf(T, 3 * H)
+            _lib.check(lib.ldot_attention_bwd(_lib.ptr(qkv), _lib.ptr(tape.mask), _lib.ptr(ctx), _lib.ptr(d_ctx),
+                                              _lib.ptr(d_qkv), B, S, H, e.heads, e.fmt, stream))
+            dwqkv, dbqkv = zeros(3 * H, H), zeros(3 * H)
+            self._wgrad(d_qkv, x, dwqkv, T)
+            self._colsum(d_qkv, dbqkv, T)
+            for j, nm in enumerate(("query", "key", "value")):
+                g[p + f"attention.self.{nm}.weight"] = dwqkv[j * H:(j + 1) * H]
+                g[p + f"attention.self.{nm}.bias"] = dbqkv[j * H:(j + 1) * H]
+            d_x = buf(T, H)
+            self._dgrad(d_qkv, w[f"qkv_w{i}"], d_x, T, aux=d_pre1, epi=3)
+            d_h = d_x
+            tape.layers[i] = None   # release this layer's activations
+
+        self._backward_embeddings(tape, d_h, g)
+        return g
+
+    def _backward_embeddings(self, tape, d_h, g):
+        e, w, lib = self.e, self.e.w, _lib.load()
+        H, dev, f32 = e.H, d_h.device, torch.float32
+        B, S, Lt, R = tape.B, tape.S, tape.Lt, tape.R
+        stream = _lib.stream_ptr()
+
+        def zeros(*shape):
+            return torch.zeros(shape, dtype=f32, device=dev)
+
+        pe = "bert.embeddings."
+        g[pe + "word_embeddings.weight"] = zeros(e.vocab, H)
+        g[pe + "position_embeddings.weight"] = zeros(e.max_pos, H)
+        g[pe + "token_type_embeddings.weight"] = zeros(2, H)
+        g[pe + "LayerNorm.weight"], g[pe + "LayerNorm.bias"] = zeros(H), zeros(H)
+        # text positions: rows b * S + l, l < Lt
+        d_txt = d_h if Lt == S else d_h.view(B, S, H)[:, :Lt, :].contiguous().view(B * Lt, H)
+        pos_stride = 0 if tape.pos.shape[0] == 1 else tape.pos.stride(0)
+        s = torch.empty((B * Lt, H), dtype=f32, device=dev)
+        _lib.check(lib.ldot_embed_text_sum(_lib.ptr(tape.ids), _lib.ptr(tape.pos), pos_stride, _lib.ptr(w["word"]),
+                                           _lib.ptr(w["pos"]), _lib.ptr(w["type0"]), _lib.ptr(s), B, Lt, H, e.vocab,
+                                           e.max_pos, e.fmt, stream))
+        dxe = torch.empty((B * Lt, H), dtype=f32, device=dev)
+        self._ln_bwd(d_txt, s, w["emb_ln_g"], dxe, g[pe + "LayerNorm.weight"], g[pe + "LayerNorm.bias"],
+                     g[pe + "token_type_embeddings.weight"][0], B * Lt, H)
+        _lib.check(lib.ldot_embed_scatter(_lib.ptr(dxe), _lib.ptr(tape.ids), _lib.ptr(tape.pos), pos_stride,
+                                          _lib.ptr(g[pe + "word_embeddings.weight"]),
+                                          _lib.ptr(g[pe + "position_embeddings.weight"]), B, Lt, H, e.vocab, e.max_pos,
+                                          stream))
+        if tape.kind != "img":
+            return
+        pi = "bert.img_embeddings."
+        rows = B * R
+        d_img = d_h.view(B, S, H)[:, Lt:, :].contiguous().view(rows, H)
+        q = torch.empty((rows, H), dtype=f32, device=dev)
+        spre = torch.empty((rows, H), dtype=f32, device=dev)
+        _lib.check(lib.ldot_embed_image_pre(_lib.ptr(tape.lin), _lib.ptr(tape.box), _lib.ptr(w["img_ln_g"]),
+                                            _lib.ptr(w["img_ln_b"]), _lib.ptr(w["pos_w"]), _lib.ptr(w["pos_bias"]),
+                                            _lib.ptr(w["pos_ln_g"]), _lib.ptr(w["pos_ln_b"]), _lib.ptr(w["type1_f32"]),
+                                            _lib.ptr(q), _lib.ptr(spre), rows, H, stream))
+        for nm in ("LayerNorm", "img_layer_norm", "pos_layer_norm"):
+            g[pi + nm + ".weight"], g[pi + nm + ".bias"] = zeros(H), zeros(H)
+        g[pi + "img_linear.bias"], g[pi + "pos_linear.bias"] = zeros(H), zeros(H)
+        ds = torch.empty((rows, H), dtype=f32, device=dev)
+        self._ln_bwd(d_img, spre, w["iemb_ln_g"], ds, g[pi + "LayerNorm.weight"], g[pi + "LayerNorm.bias"],
+                     g[pe + "token_type_embeddings.weight"][1], rows, H)
+        d_lin = torch.empty((rows, H), dtype=e.dtype, device=dev)
+        self._ln_bwd(ds, tape.lin, w["img_ln_g"], d_lin, g[pi + "img_layer_norm.weight"], g[pi + "img_layer_norm.bias"],
+                     g[pi + "img_linear.bias"], rows, H)
+        dq = torch.empty((rows, H), dtype=f32, device=dev)
+        self._ln_bwd(ds, q, w["pos_ln_g"], dq, g[pi + "pos_layer_norm.weight"], g[pi + "pos_layer_norm.bias"],
+                     g[pi + "pos_linear.bias"], rows, H)
+        g[pi + "pos_linear.weight"] = zeros(H, 7)
+        _lib.check(lib.ldot_pos_wgrad(_lib.ptr(dq), _lib.ptr(tape.box), rows, H, _lib.ptr(g[pi + "pos_linear.weight"]), stream))
+        g[pi + "img_linear.weight"] = zeros(H, e.img_dim)
+        self._wgrad(d_lin, tape.feat16, g[pi + "img_linear.weight"], rows)
+
+
+# ------------------------------------------------------------------------------------------------------- autograd
+class TowerFunction(torch.autograd.Function):
+    """pooled = tower(inputs; parameters): one autograd node per tower call.  `names` are the reference parameter
+    names of `params` (same order); parameters the forward never reads (pooler, mask_embedding) are not passed."""
+
+    @staticmethod
+    def forward(ctx, runner, names, *params):
+        pooled, tape = runner()
+        ctx.tape, ctx.names = tape, names
+        ctx.trainer = runner.trainer
+        return pooled
+
+    @staticmethod
+    def backward(ctx, d_pooled):
+        if ctx.tape is None:
+            raise RuntimeError("the tower's activations were already released: backward through a tower call runs once")
+        grads = ctx.trainer.backward(ctx.tape, d_pooled)
+        ctx.tape = None
+        out = []
+        for i, nm in enumerate(ctx.names):
+            out.append(grads.get(nm) if ctx.needs_input_grad[2 + i] else None)
+        return (None, None) + tuple(out)
+
+
+class _Runner(object):
+    def __init__(self, trainer, fn):
+        self.trainer, self.fn = trainer, fn
+
+    def __call__(self):
+        return self.fn()
+
+
+UNUSED_PARAMETERS = ("bert.pooler.", "bert.img_embeddings.mask_embedding.")
+
+
+def run_tower_training(module, engine, kind, inputs):
+    """module: BertEncoder / UniterEncoder (parameters under the reference names); returns pooled fp32 [B, D] attached
+    to the autograd graph."""
+    trainer = TowerTrainer(engine)
+    named = [(n, p) for n, p in module.named_parameters() if not n.startswith(UNUSED_PARAMETERS)]
+    names = tuple(n for n, _ in named)
+    if kind == "txt":
+        runner = _Runner(trainer, lambda: trainer.forward_text(*inputs))
+    else:
+        runner = _Runner(trainer, lambda: trainer.forward_image(*inputs))
+    return TowerFunction.apply(runner, names, *[p for _, p in named])
+
+
+class NllFunction(torch.autograd.Function):
+    """loss = in-batch NLL(q, ctx[, captions]) with gradients to the embeddings (bi_encoder.py:615-656 under autograd).
+    Forward: hi/lo-split tcgen05 scores + fused row log-sum-exp.  Backward: d scores (bf16) from one kernel, then
+    dQ = dS . C (dgrad form) and dC = dS^T . Q (wgrad form) on the tensor cores."""
+
+    @staticmethod
+    def forward(ctx, q, c, cap, pos, cap_weight, reduction, scores_fn):
+        lib = _lib.load()
+        use_cap = cap is not None and cap_weight != 0
+        s1 = scores_fn(q, c).contiguous()
+        s2 = scores_fn(q, cap).contiguous() if use_cap else None
+        bq, bc = s1.shape
+        dev = s1.device
+        scores = torch.empty((bq, bc), dtype=torch.float32, device=dev)
+        row_loss = torch.empty((bq,), dtype=torch.float32, device=dev)
+        row_correct = torch.empty((bq,), dtype=torch.int32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        correct = torch.empty((), dtype=torch.int64, device=dev)
+        _lib.check(lib.ldot_inbatch_nll(_lib.ptr(s1), _lib.ptr(s2), float(cap_weight), _lib.ptr(pos), bq, bc, reduction,
+                                        _lib.ptr(scores), _lib.ptr(row_loss), _lib.ptr(row_correct), _lib.ptr(loss),
+                                        _lib.ptr(correct), _lib.stream_ptr()))
+        ctx.save_for_backward(q, c, cap if use_cap else None, pos, scores)
+        ctx.use_cap, ctx.cap_weight, ctx.reduction = use_cap, float(cap_weight), reduction
+        ctx.mark_non_differentiable(correct, scores, s1)
+        return loss, correct, scores, s1
+
+    @staticmethod
+    def backward(ctx, d_loss, _dc, _ds, _ds1):
+        lib = _lib.load()
+        q, c, cap, pos, scores = ctx.saved_tensors
+        bq, bc = scores.shape
+        D = q.shape[1]
+        dev = q.device
+        stream = _lib.stream_ptr()
+        fmt, dt = _lib.COARSE_BF16, torch.bfloat16
+        ld = (bc + 7) // 8 * 8
+        bqp = (bq + 7) // 8 * 8
+        ds = torch.empty((bq, ld), dtype=dt, device=dev)
+        up = d_loss.to(torch.float32).reshape(1).contiguous()
+        _lib.check(lib.ldot_inbatch_nll_bwd(_lib.ptr(scores), _lib.ptr(pos), bq, bc, _lib.ptr(up), ctx.reduction,
+                                            _lib.ptr(ds), ld, fmt, stream))
+
+        def cast16(x, rows_padded):
+            out = torch.zeros((rows_padded, D), dtype=dt, device=dev)
+            xf = x.detach().to(torch.float32).contiguous()
+            _lib.check(lib.ldot_cast_f32(_lib.ptr(xf), _lib.ptr(out), x.shape[0] * D, fmt, stream))
+            return out
+
+        def gemm(a, lda, a_mn, b, ldb, out, ldo, M, N, K, acc):
+            _lib.check(lib.ldot_gemm(_lib.ptr(a), lda, a_mn, _lib.ptr(b), ldb, 1, None, None, 0, _lib.ptr(out), ldo, M, N, K,
+                                     fmt, 0, 1, int(acc), stream))
+
+        need_q, need_c, need_cap = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and ctx.use_cap
+        w = ctx.cap_weight if ctx.use_cap else 0.0
+        dq = dc = dcap = None
+        if need_q:
+            dq = torch.empty((bq, D), dtype=torch.float32, device=dev)
+            mix = c if not ctx.use_cap else (1.0 - w) * c.detach().float() + w * cap.detach().float()
+            gemm(ds, ld, 0, cast16(mix, ld), D, dq, D, bq, D, ld, False)       # dQ = dS . ((1 - w) C + w Cap)
+        if need_c or need_cap:
+            dct = torch.zeros((ld, D), dtype=torch.float32, device=dev)
+            gemm(ds, ld, 1, cast16(q, bqp)[:bq], D, dct, D, ld, D, bq, True)   # dS^T . Q
+            if need_c:
+                dc = dct[:bc] * (1.0 - w) if ctx.use_cap else dct[:bc]
+            if need_cap:
+                dcap = dct[:bc] * w
+        return dq, dc, dcap, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------- optimiser
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (what transformers.AdamW of bi_encoder.py:566-576 computes with
+    correct_bias=True) as ONE kernel launch per parameter group: parameters, gradients and both moments of a group
+    live in flat fp32 buffers (the nn.Parameters become views of the flat master copy), `step()` is ldot_adamw over the
+    flat buffers, optionally preceded by the global gradient-norm clip of train_itm.py:262-267 (`max_grad_norm` > 0:
+    one extra reduction launch per group instead of a pass per tensor).
+
+    Like torch, parameters that have never received a gradient (the unused pooler, mask_embedding) are left alone:
+    the flat buffers are laid out at the first step() from the parameters that carry a gradient, and re-laid out if
+    another parameter starts receiving one.  `state_dict()` has torch.optim.AdamW's layout (step / exp_avg /
+    exp_avg_sq per parameter)."""
+
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = float(max_grad_norm)
+        self._flat = None
+        self._steps = 0
+
+    def _flatten(self):
+        flat = []
+        for group in self.param_groups:
+            ps = [p for p in group["params"] if p.requires_grad and (p.grad is not None or "exp_avg" in self.state.get(p, {}))]
+            if not ps:
+                flat.append(None)
+                continue
+            dev = ps[0].device
+            if dev.type != "cuda":
+                raise _lib.LdotError("FusedAdamW runs only on CUDA parameters (move the model to the GPU first)")
+            n = sum(p.numel() for p in ps)
+            f = dict(p=torch.empty(n, dtype=torch.float32, device=dev), g=torch.zeros(n, dtype=torch.float32, device=dev),
+                     m=torch.zeros(n, dtype=torch.float32, device=dev), v=torch.zeros(n, dtype=torch.float32, device=dev),
+                     params=ps, ids=set(id(p) for p in ps))
+            off = 0
+            for p in ps:
+                k = p.numel()
+                sl = slice(off, off + k)
+                f["p"][sl].copy_(p.data.reshape(-1))
+                p.data = f["p"][sl].view(p.shape)
+                if p.grad is not None:
+                    f["g"][sl].copy_(p.grad.reshape(-1))
+                p.grad = f["g"][sl].view(p.shape)
+                old = self.state.get(p, {})
+                if "exp_avg" in old:
+                    f["m"][sl].copy_(old["exp_avg"].reshape(-1))
+                    f["v"][sl].copy_(old["exp_avg_sq"].reshape(-1))
+                    self._steps = max(self._steps, int(old.get("step", 0)))
+                self.state[p] = {"step": torch.tensor(float(self._steps)), "exp_avg": f["m"][sl].view(p.shape),
+                                 "exp_avg_sq": f["v"][sl].view(p.shape)}
+                off += k
+            flat.append(f)
+        self._flat = flat
+        _lib.param_generation[0] += 1
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._flat = None     # re-laid out at the next step(), adopting the loaded moments and step count
+        self._steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        """Clears the flat gradient buffers in place (the .grad views stay attached)."""
+        if self._flat is None:
+            return super().zero_grad(set_to_none=True)
+        for f in self._flat:
+            if f is None:
+                continue
+            f["g"].zero_()
+            off = 0
+            for p in f["params"]:   # (model.zero_grad() may have dropped the views)
+                k = p.numel()
+                if p.grad is None or p.grad.data_ptr() != f["g"].data_ptr() + off * 4:
+                    p.grad = f["g"][off:off + k].view(p.shape)
+                off += k
+
+    def _needs_layout(self):
+        if self._flat is None:
+            return True
+        for group, f in zip(self.param_groups, self._flat):
+            known = f["ids"] if f is not None else ()
+            for p in group["params"]:
+                if p.requires_grad and p.grad is not None and id(p) not in known:
+                    return True
+        return False
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        lib = _lib.load()
+        if self._needs_layout():
+            self._flatten()
+        self._steps += 1
+        stream = _lib.stream_ptr()
+        live = [f for f in self._flat if f is not None]
+        if not live:
+            return None
+        # gradients that autograd left outside the flat buffer (after model.zero_grad() dropped the views)
+        for f in live:
+            off = 0
+            for p in f["params"]:
+                k = p.numel()
+                if p.grad is None:
+                    f["g"][off:off + k].zero_()
+                elif p.grad.data_ptr() != f["g"].data_ptr() + off * 4:
+                    f["g"][off:off + k].copy_(p.grad.reshape(-1))
+                off += k
+        ss = None
+        if self.max_grad_norm > 0:
+            ss = torch.zeros(1, dtype=torch.float32, device=live[0]["p"].device)
+            for f in live:
+                _lib.check(lib.ldot_sumsq(_lib.ptr(f["g"]), f["g"].numel(), _lib.ptr(ss), stream))
+        for group, f in zip(self.param_groups, self._flat):
+            if f is None:
+                continue
+            b1, b2 = group["betas"]
+            _lib.check(lib.ldot_adamw(_lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["m"]), _lib.ptr(f["v"]), None,
+                                      f["p"].numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                      float(group["weight_decay"]), self._steps, _lib.ptr(ss), self.max_grad_norm,
+                                      _lib.COARSE_BF16, stream))
+            for p in f["params"]:
+                self.state[p]["step"].fill_(float(self._steps))
+        _lib.param_generation[0] += 1   # cached 16-bit inference copies of the towers are stale now
+        return None

@@ -21,7 +21,7 @@ from oracle import ref_shims  # noqa: E402
 ref_shims.install()
 
 from lightningdot_b200 import synth  # noqa: E402
-from oracle import evalloop, flatip, loss as oloss, towers  # noqa: E402
+from oracle import evalloop, flatip, loss as oloss, towers, train as otrain  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 
@@ -94,6 +94,55 @@ def loss_case():
     print(f"[loss] reference loss {l0.item():.6f}/{l1.item():.6f} correct {int(c0)}/{int(c1)}: oracle matches")
     np.savez_compressed(os.path.join(GOLD, "loss_inbatch.npz"), loss0=l0.numpy(), correct0=np.array(int(c0)),
                         loss1=l1.numpy(), correct1=np.array(int(c1)), scores0=s0.numpy(), scores1=s1.numpy())
+
+
+def train_case(name, layers, seed, batch):
+    """One train_itm.py step (train_itm.py:191-222,252-258) by the reference modules: forward of both towers, the two
+    _calc_loss calls, 0.5 / 0.5 mix, loss.backward().  eval() mode: dropout off, so the step is deterministic."""
+    from dvl.models.bi_encoder import BiEncoderNllLoss
+    from dvl.utils import _calc_loss
+    sd_t = synth.random_tower_state("txt", seed=seed, perturb=True, layers=layers)
+    sd_i = synth.random_tower_state("img", seed=seed + 1, perturb=True, layers=layers)
+    mt, mi = build_reference_tower("txt", layers, sd_t), build_reference_tower("img", layers, sd_i)
+    tb = synth.text_batch(batch, 32, seed=seed, ragged=True)
+    ib = synth.image_batch(batch, 36, seed=seed, ragged=True)
+    _, t, _ = mt(tb["input_ids"], tb["attention_mask"], tb["position_ids"])
+    _, i, _ = mi(ib["input_ids"], ib["attention_mask"], ib["position_ids"], ib["img_feat"], ib["img_pos_feat"], None,
+                 ib["gather_index"])
+    args = types.SimpleNamespace(caption_score_weight=0.0)
+    pos = list(range(batch))
+    l_txt, c_txt, _ = _calc_loss(args, BiEncoderNllLoss(), i, t, None, pos, None)
+    l_img, c_img, _ = _calc_loss(args, BiEncoderNllLoss(), t, i, None, pos, None)
+    loss = 0.5 * l_txt + 0.5 * l_img
+    loss.backward()
+    oloss_v, _, gt, gi = otrain.train_step(sd_t, sd_i, tb, ib)
+    assert abs(loss.item() - oloss_v.item()) < 1e-5, (loss.item(), oloss_v.item())
+    out = {"loss": np.array(loss.item(), dtype=np.float64), "correct": np.array((int(c_txt) + int(c_img)) / 2)}
+    worst = 0.0
+    for tag, model, og in (("txt", mt, gt), ("img", mi, gi)):
+        names, norms, samples = [], [], []
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                assert n not in og, n
+                continue
+            assert n in og, n
+            g = p.grad
+            # (key.bias gradients are identically zero in exact arithmetic - softmax is shift-invariant - so the
+            # comparison carries an absolute floor)
+            err, gn = (g - og[n]).norm().item(), g.norm().item()
+            assert err <= 2e-4 * gn + 1e-6, (n, err, gn)
+            worst = max(worst, err / max(gn, 1e-4))
+            names.append(n)
+            norms.append(g.norm().item())
+            samples.append(g.reshape(-1)[otrain.sample_index(g.numel())].numpy())
+        assert len(names) == len(og), (len(names), len(og))
+        out[f"{tag}_names"] = np.array(names)
+        out[f"{tag}_norms"] = np.array(norms, dtype=np.float64)
+        out[f"{tag}_samples"] = np.stack(samples).astype(np.float32)
+    print(f"[train {name}] reference loss {loss.item():.6f}; oracle gradients match the reference's "
+          f"(worst relative L2 error {worst:.2e}) over {len(out['txt_names'])} + {len(out['img_names'])} tensors")
+    out["meta"] = np.array([layers, seed, batch])
+    np.savez_compressed(os.path.join(GOLD, f"train_step_{name}.npz"), **out)
 
 
 def indexer_case():
@@ -176,6 +225,7 @@ def main():
     for case in TOWER_CASES:
         tower_case(*case)
     loss_case()
+    train_case("l2", 2, 201, 6)
     indexer_case()
     evalloop_case()
     print("golden fixtures written to", GOLD)

@@ -1,0 +1,32 @@
+"""Per-parameter gradient error of the GPU training step against the CPU oracle (diagnostic).
+python scripts/grad_errors.py [bf16|fp16] [layers]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from lightningdot_b200 import synth  # noqa: E402
+from oracle import train as otrain  # noqa: E402
+import test_gpu_training as T  # noqa: E402
+
+dtype = torch.float16 if len(sys.argv) > 1 and sys.argv[1] == "fp16" else torch.bfloat16
+layers = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+seed, batch = 201, 6
+sd_t = synth.random_tower_state("txt", seed=seed, perturb=True, layers=layers)
+sd_i = synth.random_tower_state("img", seed=seed + 1, perturb=True, layers=layers)
+tb = synth.text_batch(batch, 32, seed=seed, ragged=True)
+ib = synth.image_batch(batch, 36, seed=seed, ragged=True)
+mt, mi = T.towers(layers, sd_t, sd_i)
+mt.compute_dtype = mi.compute_dtype = dtype
+loss, correct = T.gpu_step(mt, mi, tb, ib, batch)
+loss.backward()
+oloss, _, gt, gi = otrain.train_step(sd_t, sd_i, tb, ib)
+print("loss", loss.item(), "oracle", oloss.item())
+for tag, m, want in (("txt", mt, gt), ("img", mi, gi)):
+    for n, p in m.named_parameters():
+        if n in want:
+            g, w = p.grad.cpu(), want[n]
+            cos = torch.nn.functional.cosine_similarity(g.reshape(1, -1), w.reshape(1, -1)).item()
+            print(f"{tag} {n:60s} |g| {w.norm().item():10.3e} rel {((g - w).norm() / w.norm().clamp_min(1e-30)).item():8.4f} cos {cos:.5f}")

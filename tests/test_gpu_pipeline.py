@@ -113,11 +113,13 @@ def test_biencoder_forward_on_collate_batch(cuda_lib):
     assert seqs[0].shape == (9, 32, 768) and seqs[1].shape == (9, 37, 768) and seqs[2] is None
 
 
-def test_training_mode_forward_fails_loudly(cuda_lib):
+def test_sequence_outputs_carry_no_gradient(cuda_lib):
+    """Gradients flow through the pooled outputs only (what train_itm.py uses); asking for differentiable sequence
+    outputs fails loudly instead of returning a tensor that silently has no grad_fn."""
     model = _small_biencoder().cuda().train()
     tb = synth.text_batch(2, 16, seed=1)
     with pytest.raises(NotImplementedError):
-        model({"txts": tb})
+        model({"txts": tb}, output_all_encoded_layers=True)
 
 
 def test_towers_refuse_cpu():

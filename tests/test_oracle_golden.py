@@ -99,3 +99,28 @@ def test_f64_oracle_vs_fp32_sgemm_agree_off_ties():
     diff_rows, diff_cols = np.nonzero(i64 != i32)
     for r, c in zip(diff_rows, diff_cols):  # every disagreement is a swap of two scores within fp32 noise
         assert abs(float(s64[r, c]) - float(s32[r, c])) <= 4e-7 * max(1.0, abs(float(s64[r, c])))
+
+
+def test_oracle_train_step_matches_reference_gradients(golden_dir):
+    """oracle/train.py (autograd over the functional towers) against the fixture minted from loss.backward() of the
+    reference's own modules (oracle/make_golden.py: train_case)."""
+    import torch
+    from lightningdot_b200 import synth
+    from oracle import train as otrain
+    gold = np.load(os.path.join(golden_dir, "train_step_l2.npz"))
+    layers, seed, batch = (int(v) for v in gold["meta"])
+    sd_t = synth.random_tower_state("txt", seed=seed, perturb=True, layers=layers)
+    sd_i = synth.random_tower_state("img", seed=seed + 1, perturb=True, layers=layers)
+    tb = synth.text_batch(batch, 32, seed=seed, ragged=True)
+    ib = synth.image_batch(batch, 36, seed=seed, ragged=True)
+    loss, correct, gt, gi = otrain.train_step(sd_t, sd_i, tb, ib)
+    assert abs(loss.item() - float(gold["loss"])) < 1e-5
+    assert float(correct) == float(gold["correct"])
+    for tag, grads in (("txt", gt), ("img", gi)):
+        names = [str(n) for n in gold[f"{tag}_names"]]
+        assert sorted(names) == sorted(grads.keys())
+        for n, norm, samples in zip(names, gold[f"{tag}_norms"], gold[f"{tag}_samples"]):
+            g = grads[n]
+            assert abs(g.norm().item() - norm) <= 2e-4 * norm + 1e-6, n
+            got = g.reshape(-1)[otrain.sample_index(g.numel())].numpy()
+            assert np.abs(got - samples).max() <= 2e-4 * norm + 1e-7, n
