@@ -18,6 +18,25 @@ COARSE_BF16 = 1
 _lib = None
 # bumped by in-place parameter updates that bypass torch's version counters (FusedAdamW): part of the towers' cache key
 param_generation = [0]
+# flat buffers of the live FusedAdamW optimisers: dicts with "p" (fp32 master), "p16" (16-bit mirror the AdamW kernel
+# keeps up to date, or None) and "g" (fp32 gradients).  Towers alias their weights to them (towers.py: load).
+flat_buffers = []
+
+
+def shadow_view(t, dtype):
+    """The 16-bit mirror of the fp32 parameter tensor `t` inside a FusedAdamW flat buffer (same shape), or None."""
+    if t.device.type != "cuda" or not t.is_contiguous() or t.dtype.itemsize != 4:
+        return None
+    ptr, n = t.data_ptr(), t.numel()
+    for f in flat_buffers:
+        p16 = f.get("p16")
+        if p16 is None or p16.dtype != dtype or p16.device != t.device:
+            continue
+        base = f["p"].data_ptr()
+        if base <= ptr and ptr + 4 * n <= base + 4 * f["p"].numel():
+            off = (ptr - base) // 4
+            return p16[off:off + n].view(t.shape)
+    return None
 
 # name -> (restype, argtypes): every symbol include/ldot.h declares
 SIGNATURES = {

@@ -205,6 +205,7 @@ class _TowerBase(nn.Module):
         self.compute_dtype = torch.bfloat16   # setup_for_distributed_mode(fp16=True) switches to torch.float16
         self._engine = None
         self._engine_sig = None
+        self._engine_gen = -1
 
     def _init_weights(self, module):
         # uniter_model/model/model.py:134-147
@@ -224,8 +225,7 @@ class _TowerBase(nn.Module):
     # -- engine management -----------------------------------------------------------------------------------------
     def _signature(self):
         ps = list(self.parameters())
-        return (self.compute_dtype, ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]),
-                _lib.param_generation[0])
+        return (self.compute_dtype, ps[0].device, tuple(p._version for p in ps), tuple(p.data_ptr() for p in ps[:4]))
 
     def engine(self) -> TowerEngine:
         """(Re)build the 16-bit inference copies when parameters, device or compute dtype changed."""
@@ -234,13 +234,21 @@ class _TowerBase(nn.Module):
             raise _lib.LdotError("the towers run only on a CUDA device (B200): move the model with .to('cuda'); "
                                  "there is no CPU fallback")
         sig = self._signature()
-        if self._engine is None or self._engine_sig != sig:
+        gen = _lib.param_generation[0]
+        # (an engine whose weights alias the optimiser's buffers sees optimiser steps without a reload)
+        if self._engine is None or self._engine_sig != sig or (not self._engine.aliased and self._engine_gen != gen):
             c = self.config
             eng = TowerEngine(self.KIND, c.hidden_size, c.num_attention_heads, c.intermediate_size, c.num_hidden_layers,
                               dtype=self.compute_dtype)
-            eng.load(self.state_dict(), dev)
-            self._engine, self._engine_sig = eng, sig
+            eng.load(self.state_dict(), dev, trainable={n for n, p in self.named_parameters() if p.requires_grad})
+            self._engine, self._engine_sig, self._engine_gen = eng, sig, gen
         return self._engine
+
+    def zero_grad(self, set_to_none: bool = True):
+        """nn.Module.zero_grad, except that gradients living in a FusedAdamW flat buffer are cleared IN PLACE (one
+        memset per parameter group) so that the next backward keeps accumulating straight into them."""
+        from .training import zero_grads
+        zero_grads(self, set_to_none)
 
     def _wants_grad(self):
         """True when this call must be recorded for backward (train_itm.py:191-258): grad mode on and trainable
@@ -367,6 +375,11 @@ class BiEncoder(nn.Module):
         if fix_img_encoder:
             for param in self.img_model.parameters():
                 param.requires_grad = False
+
+    def zero_grad(self, set_to_none: bool = True):
+        """bi_encoder.zero_grad() of train_itm.py:282: flat-buffer gradients are cleared in place (see _TowerBase)."""
+        from .training import zero_grads
+        zero_grads(self, set_to_none)
 
     @staticmethod
     def get_representation(sub_model, input_ids, attention_mask, position_ids, img_feat, img_pos_feat, img_masks,
@@ -520,7 +533,11 @@ def setup_for_distributed_mode(model: nn.Module, optimizer: torch.optim.Optimize
                                teacher_model=None) -> (nn.Module, torch.optim.Optimizer):
     """bi_encoder.py:579-610.  The reference wraps the model with apex amp when fp16 is set; here fp16=True selects
     fp16 activations / weights for the tower kernels (what amp O1/O2 run the GEMMs in) and fp16=False the default
-    bf16.  No apex needed."""
+    bf16.  No apex needed.  With local_rank != -1 and an initialised torch.distributed group (one process per GPU)
+    the reference would wrap the model in DistributedDataParallel (:603-607); here the parameters are broadcast from
+    rank 0 once and the optimiser averages its flat gradient buffers over the ranks in step() (FusedAdamW.distributed),
+    so the model object and its state_dict() keys stay unwrapped."""
+    import torch.distributed as dist
     model.to(device)
     if teacher_model is not None:
         teacher_model.to(device)
@@ -528,6 +545,18 @@ def setup_for_distributed_mode(model: nn.Module, optimizer: torch.optim.Optimize
     for m in model.modules():
         if isinstance(m, _TowerBase):
             m.compute_dtype = dtype
+    if optimizer is not None and hasattr(optimizer, "shadow_dtype") and optimizer.shadow_dtype != dtype:
+        optimizer.shadow_dtype = dtype
+        optimizer._flat = None if not optimizer._flat else optimizer._relayout()
+    if local_rank != -1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        with torch.no_grad():
+            for t in list(model.parameters()) + list(model.buffers()):
+                dist.broadcast(t.data, src=0)
+        _lib.param_generation[0] += 1
+        if optimizer is not None:
+            if not hasattr(optimizer, "sync_gradients"):
+                raise TypeError("distributed training needs the optimiser get_optimizer() returns (FusedAdamW)")
+            optimizer.distributed = True
     return model, optimizer
 
 

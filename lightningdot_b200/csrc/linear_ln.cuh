@@ -198,12 +198,11 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::tc_fence_after();
       const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
 
-      // x = acc (+ residual, already accumulated by the MMA) + bias for one 32-column chunk (both passes)
-      auto load_x = [&](int cc, float (&f)[32]) {
-        uint32_t v[32];
-        ptx::tmem_ld32(taddr + cc * 32, v);
+      // x = acc (+ residual, already accumulated by the MMA) + bias for one 32-column chunk (both passes).  TMEM loads are
+      // software-pipelined in both passes: chunk cc + 1 is in flight while chunk cc is consumed.
+      uint32_t v2[2][32];
+      auto add_bias = [&](int cc, const uint32_t (&v)[32], float (&f)[32]) {
         const float4* b4 = reinterpret_cast<const float4*>(vec + half * (kLinBN / 2) + cc * 32);
-        ptx::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 b = b4[j];  // (broadcast LDS.128)
@@ -216,15 +215,22 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
       // ---- pass 1: partial row statistics, broadcast to the whole cluster
       float s1 = 0.f, s2 = 0.f;
-      for (int cc = 0; cc < nchunks; ++cc) {
+      if (nchunks > 0) ptx::tmem_ld32(taddr, v2[0]);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc >= nchunks) break;
+        ptx::tmem_ld_wait();
+        // (after the last chunk of pass 1 the first chunk of pass 2 is fetched: it overlaps the statistics exchange)
+        ptx::tmem_ld32(taddr + (cc + 1 < nchunks ? cc + 1 : 0) * 32, v2[(cc + 1) & 1]);
         float f[32];
-        load_x(cc, f);
+        add_bias(cc, v2[cc & 1], f);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           s1 += f[j];
           s2 = fmaf(f[j], f[j], s2);
         }
       }
+      const int first2 = nchunks & 1;   // v2 buffer that holds pass 2's chunk 0
       {
         const uint32_t slot = ptx::smem_u32(stats + (as * 2 * kLnMaxCluster + rank * 2 + half) * kBM + row);
         const uint32_t bar = ptx::smem_u32(&sbar[as]);
@@ -249,15 +255,22 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tempty[as]);
       }
-      for (int cc = 0; cc < nchunks; ++cc) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc >= nchunks) break;
         const int col = col_base + cc * 32;
-        float f[32];
-        load_x(cc, f);
-        if (cc == nchunks - 1) {  // accumulator drained for good
+        ptx::tmem_ld_wait();
+        if (cc + 1 < nchunks) {
+          if ((first2 + cc + 1) & 1) ptx::tmem_ld32(taddr + (cc + 1) * 32, v2[1]);
+          else ptx::tmem_ld32(taddr + (cc + 1) * 32, v2[0]);
+        } else {  // accumulator drained for good
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[as]);
         }
+        float f[32];
+        if ((first2 + cc) & 1) add_bias(cc, v2[1], f);
+        else add_bias(cc, v2[0], f);
         const float4* g4 = reinterpret_cast<const float4*>(vec + kLinBN + half * (kLinBN / 2) + cc * 32);
         const float4* e4 = reinterpret_cast<const float4*>(vec + 2 * kLinBN + half * (kLinBN / 2) + cc * 32);
 #pragma unroll

@@ -4,9 +4,9 @@
 //   warp 0      TMA producer: A (activations) 128 x 64 and W 256 x 64 K-major boxes, SWIZZLE_128B, 4-stage ring
 //   warp 1      TMEM owner + tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accumulate, 2 accumulators)
 //   warps 2..9  epilogue: warp w reads TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the 128 x 256 tile in
-//               32-column chunks.  Per chunk: tcgen05.ld (async) | bias + residual prefetch | wait | bias, erf-GELU,
-//               residual in registers | swizzled st.shared into the warp's staging buffer | one TMA store
-//               (cp.async.bulk.tensor) of the 32 x 32 box.  Stores are coalesced by the TMA unit and clipped at the
+//               16-column slices, software-pipelined: tcgen05.ld of slice s + 1 is in flight while slice s gets bias,
+//               erf-GELU, residual in registers | swizzled st.shared into the warp's staging buffer; every two
+//               slices one TMA store (cp.async.bulk.tensor) of the 32 x 32 box.  Stores are coalesced by the TMA unit and clipped at the
 //               M / N edges of the output, so there is no tail handling on the store side.
 // Tiles are visited n-fastest (tile t = m_tile * n_tiles + n_tile): CTAs that run at the same time share the A row
 // block (the big operand - activations) through L2 while the weights stay L2-resident anyway.
@@ -221,8 +221,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ks = t / mn_tiles;
         const int kb0 = ks * sched.kb_per_split;
         const int kb1 = kb0 + sched.kb_per_split < sched.k_blocks ? kb0 + sched.kb_per_split : sched.k_blocks;
-        if (CTAS == 2) ptx::mbar_wait_cluster(&tempty[as], aphase ^ 1);
-        else ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        // (the epilogue warps hand the accumulator back with CTA-scope arrives: only TMEM reads are ordered, by
+        // tcgen05 fences - a cluster-scope acquire here would invalidate L1 on every poll of the spin)
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kLinBN);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -266,7 +267,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tempty_addr[2] = {CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]),
                                      CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[1]), 0) : ptx::smem_u32(&tempty[1])};
     auto release_acc = [&](int a) {
-      if (CTAS == 2) ptx::mbar_arrive_cluster(tempty_addr[a]);
+      if (CTAS == 2) ptx::mbar_arrive_remote(tempty_addr[a]);
       else ptx::mbar_arrive(&tempty[a]);
     };
     const int mn_tiles = sched.m_tiles * sched.n_tiles;
@@ -278,48 +279,56 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long grow = static_cast<long long>(m_tile) * kBM + row;
       const bool row_ok = grow < p.M;
       const int col_base = n_tile * kLinBN + half * (kLinBN / 2);
-      // chunks of this warp that hold valid columns (uniform across the warp)
-      int nchunks = (p.N - col_base + 31) / 32;
-      nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+      // 16-column slices of this warp's 128 columns that hold valid columns (uniform across the warp)
+      int nslices = (p.N - col_base + 15) / 16;
+      nslices = nslices < 0 ? 0 : (nslices > 8 ? 8 : nslices);
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
       const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
-      if (nchunks == 0) {
+      if (nslices == 0) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) release_acc(as);
       }
-      for (int cc = 0; cc < nchunks; ++cc) {
-        const int col = col_base + cc * 32;
-        const bool full_chunk = col + 32 <= p.N;
-        uint32_t v[32];
-        ptx::tmem_ld32(taddr + cc * 32, v);
-        // operands of the elementwise tail are fetched while the TMEM load is in flight
-        float4 b4[8];
-        if (bias != nullptr && full_chunk) {
+      // TMEM loads are software-pipelined: slice s + 1 is in flight while slice s goes through the elementwise tail.
+      // Two slices fill one 32 x 32 staging box, which goes out as one TMA store.
+      uint32_t v2[2][16];
+      if (nslices > 0) ptx::tmem_ld16(taddr, v2[0]);
+      uint8_t* buf = staging;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col) + j);
+      for (int sl = 0; sl < 8; ++sl) {
+        if (sl >= nslices) break;
+        const int col = col_base + sl * 16;
+        const bool full_slice = col + 16 <= p.N;
+        uint32_t (&v)[16] = v2[sl & 1];
+        // operands of the elementwise tail are fetched while the TMEM load is in flight
+        float4 b4[4];
+        if (bias != nullptr && full_slice) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col) + j);
         }
-        uint4 r4[4];
-        const bool res_vec = p.residual != nullptr && row_ok && full_chunk;
+        uint4 r4[2];
+        const bool res_vec = p.residual != nullptr && row_ok && full_slice;
         if (res_vec) {
           const uint4* r = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) r4[j] = __ldg(r + j);
+          r4[0] = __ldg(r);
+          r4[1] = __ldg(r + 1);
         }
         ptx::tmem_ld_wait();
-        if (cc == nchunks - 1) {  // accumulator drained: hand it back to the MMA warp before the math
+        if (sl + 1 < nslices) {
+          ptx::tmem_ld16(taddr + (sl + 1) * 16, v2[(sl + 1) & 1]);
+        } else {  // accumulator drained: hand it back to the MMA warp before the math
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) release_acc(as);
         }
-        float f[32];
+        float f[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
         if (bias != nullptr) {
-          if (full_chunk) {
+          if (full_slice) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
               f[4 * j] += b4[j].x;
               f[4 * j + 1] += b4[j].y;
               f[4 * j + 2] += b4[j].z;
@@ -327,18 +336,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (col + j < p.N) f[j] += __ldg(bias + col + j);
           }
         }
         if (ACT == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
         }
         if (p.residual != nullptr && row_ok) {
-          if (full_chunk) {
+          if (full_slice) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
+            for (int j4 = 0; j4 < 2; ++j4) {
               const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -355,7 +364,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
             const uint16_t* r16 = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < 16; ++j)
               if (col + j < p.N) {
                 const float x = unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
                 if (ACT == 2) f[j] *= gelu_erf_grad(x);
@@ -363,37 +372,43 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
           }
         }
-        // stage the 32 x 32 box (swizzled exactly as the output tensor map expects) and hand it to the TMA unit
-        uint8_t* buf = OUT_F32 ? staging : staging + (nstore & 1u) * (SM::kStagingPerWarp / 2);
-        if (lane == 0) {
-          if (OUT_F32) ptx::bulk_wait_group_read<0>();
-          else ptx::bulk_wait_group_read<1>();
+        // stage the slice into its half of the 32 x 32 box (swizzled exactly as the output tensor map expects)
+        const int hs = sl & 1;
+        if (hs == 0) {
+          buf = OUT_F32 ? staging : staging + (nstore & 1u) * (SM::kStagingPerWarp / 2);
+          if (lane == 0) {
+            if (OUT_F32) ptx::bulk_wait_group_read<0>();
+            else ptx::bulk_wait_group_read<1>();
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (OUT_F32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(buf + lane * 128 + (((hs * 4 + j) ^ (lane & 7)) << 4)) =
                 make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 2; ++j) {
             uint4 w;
             w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
             w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
             w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
             w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
-            *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+            *reinterpret_cast<uint4*>(buf + lane * 64 + (((hs * 2 + j) ^ ((lane >> 1) & 3)) << 4)) = w;
           }
         }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (RED) ptx::tma_reduce_add_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
-          else ptx::tma_store_2d(&tmap_out, buf, col, m_tile * kBM + quarter * 32);
-          ptx::bulk_commit_group();
+        if (hs == 1 || sl + 1 == nslices) {   // box complete (or the N edge cuts it short: the TMA store clips)
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int bcol = col_base + (sl >> 1) * 32;
+            if (RED) ptx::tma_reduce_add_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
+            else ptx::tma_store_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
+            ptx::bulk_commit_group();
+          }
+          ++nstore;
         }
-        ++nstore;
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;

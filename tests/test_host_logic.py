@@ -235,3 +235,57 @@ def test_inbatch_loss_global_negatives_two_ranks_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_loss_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def _train_sync_worker(rank, world, port, tmp):
+    """Global-batch training protocol: differentiable embedding gather + gradient average over the ranks
+    must reproduce the single-process gradient of the symmetric loss on the whole batch.  Towers are stand-in
+    torch Linears (the protocol is host logic; the CUDA towers are tested on the GPU)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from lightningdot_b200 import utils
+        g = torch.Generator().manual_seed(9)
+        B, b = 12, 12 // world
+        xt, xi = torch.randn(B, 20, generator=g), torch.randn(B, 24, generator=g)
+
+        def towers():
+            torch.manual_seed(3)
+            return torch.nn.Linear(20, 16), torch.nn.Linear(24, 16)
+
+        # single process, global batch
+        ft, fi = towers()
+        loss_ref, _ = oloss.symmetric_nll(ft(xt), fi(xi))
+        loss_ref.backward()
+        # this rank's slice
+        mt, mi = towers()
+        lo, hi = rank * b, rank * b + b
+        t, i = mt(xt[lo:hi]), mi(xi[lo:hi])
+        args = types.SimpleNamespace(distributed_world_size=world, caption_score_weight=0.0)
+        pos = list(range(b))
+        l_txt, _, _ = utils._calc_loss(args, OracleLoss(), i, t, None, pos, None)
+        l_img, _, _ = utils._calc_loss(args, OracleLoss(), t, i, None, pos, None)
+        loss = 0.5 * l_txt + 0.5 * l_img
+        loss.backward()
+        params = list(mt.parameters()) + list(mi.parameters())
+        utils.sync_gradients(params)
+        for p, r in zip(params, list(ft.parameters()) + list(fi.parameters())):
+            assert torch.allclose(p.grad, r.grad, rtol=1e-4, atol=1e-6), (p.grad - r.grad).abs().max()
+        mean_loss = utils._mean_or_sum_(loss.detach().clone(), None, mean=True)
+        assert torch.allclose(mean_loss, loss_ref.detach(), rtol=1e-5)
+        # no-grad gather path returns the same rows
+        with torch.no_grad():
+            assert torch.equal(utils.gather_embeddings(t.detach()), ft(xt).detach()) or \
+                torch.allclose(utils.gather_embeddings(t.detach()), ft(xt).detach())
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_global_batch_training_protocol_two_ranks_gloo(tmp_path):
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_train_sync_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
