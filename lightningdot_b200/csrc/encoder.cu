@@ -15,6 +15,7 @@
 #include "prof.h"
 #include "encoder_params.h"
 #include "rowops.cuh"
+#include "mma_sync.cuh"
 
 namespace ldot {
 
@@ -158,29 +159,6 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-template <int FMT>
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  if (FMT == 1)
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-  else
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-constexpr int kHeadDim = 64;
-constexpr int kRowPad = 72;  // smem row pitch in elements (144 B): conflict-free ldmatrix
-
 // grid (heads, B); block = (SPAD / 16) warps; warp w owns query rows [16 w, 16 w + 16).  Only the first q_rows query
 // positions of each sequence are computed and written (ctx is [B * q_rows, H]): q_rows = S for a full layer, 1 for the
 // last layer of a tower whose caller only reads the [CLS] row (dvl/models/bi_encoder.py:120,188).

@@ -20,6 +20,7 @@
 #include "host_common.h"
 #include "prof.h"
 #include "rowops.cuh"
+#include "mma_sync.cuh"
 #include "gelu.cuh"
 #include "train_params.h"
 
@@ -137,7 +138,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
 
 static unsigned row_grid(long long rows) {
   long long b = (rows + 7) / 8;
-  const long long cap = 148 * 4;
+  // two resident blocks per SM: each block ends with 3 H global atomics, so fewer, longer-running blocks keep the
+  // contention on the H column accumulators low
+  const long long cap = 148 * 2;
   return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -153,8 +156,6 @@ int ln_bwd_run(const LnBwdParams& p, int H, void* stream) {
 }
 
 // ------------------------------------------------------------------------------------------------ attention backward
-constexpr int kHd = 64;
-constexpr int kPitch = 66;   // shared-memory row pitch in 16-bit elements (33 words: conflict-free row-strided reads)
 
 __device__ __forceinline__ float h2f(uint16_t u, int fmt) {
   if (fmt == 1) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
@@ -168,126 +169,266 @@ __device__ __forceinline__ uint16_t f2h(float f, int fmt) {
   __half h = __float2half_rn(f);
   return *reinterpret_cast<uint16_t*>(&h);
 }
-__device__ __forceinline__ float dot64(const uint16_t* a, const uint16_t* b, int fmt) {
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < kHd; c += 2) {
-    const uint32_t ua = *reinterpret_cast<const uint32_t*>(a + c), ub = *reinterpret_cast<const uint32_t*>(b + c);
-    const float2 x = fmt == 1 ? cvt2<1>(ua) : cvt2<0>(ua);
-    const float2 y = fmt == 1 ? cvt2<1>(ub) : cvt2<0>(ub);
-    s = fmaf(x.x, y.x, s);
-    s = fmaf(x.y, y.y, s);
-  }
-  return s;
-}
-
-// grid (heads, B), 256 threads.  qkv [B * S, 3 H] (saved forward activations), ctx / dctx [B * S, H], dqkv [B * S, 3 H].
-// The probabilities are recomputed (S <= 128), never stored by the forward.
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
-                                                            const uint16_t* __restrict__ ctx, const uint16_t* __restrict__ dctx,
-                                                            uint16_t* __restrict__ dqkv, int S, int H, int fmt) {
-  extern __shared__ __align__(16) uint8_t ab_smem[];
-  uint16_t* sQ = reinterpret_cast<uint16_t*>(ab_smem);
-  uint16_t* sK = sQ + S * kPitch;
-  uint16_t* sV = sK + S * kPitch;
-  uint16_t* sdO = sV + S * kPitch;
-  float* sP = reinterpret_cast<float*>(sdO + S * kPitch);   // (4 S rows of 132 B: 4-byte aligned)
-  float* sD = sP + S * (S + 1);
-  float* sMb = sD + S;
+// grid (heads, B); block = SPAD / 16 warps.  qkv [B * S, 3 H] (saved forward activations), dctx [B * S, H],
+// dqkv [B * S, 3 H].  All five contractions run on mma.sync m16n8k16 tiles (16-bit operands, fp32 accumulation):
+//   phase 1   warp w owns QUERY rows [16 w, 16 w + 16): S = Q K^T / 8 + mask -> P = softmax(S) (recomputed exactly as the
+//             forward does, never stored by it); dP = dO V^T; D_i = sum_j P_ij dP_ij (= dO_i . O_i); dS = P (dP - D) / 8;
+//             dQ = dS K.  P and dS leave as 16-bit tiles in shared memory.
+//   phase 2   warp w owns KEY rows [16 w, 16 w + 16): dV = P^T dO and dK = dS^T Q, the transposed A operands read with
+//             ldmatrix.trans straight from the phase-1 tiles.
+// Outputs are staged per warp and written with 16-byte coalesced stores.
+template <int SPAD, int FMT>
+__global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
+                                                                  const uint16_t* __restrict__ dctx, uint16_t* __restrict__ dqkv,
+                                                                  int S, int H) {
+  constexpr int PP = SPAD + 8;          // pitch of the P / dS tiles (odd multiple of 16 B: conflict-free ldmatrix)
+  constexpr int NT = SPAD / 8;
+  extern __shared__ __align__(16) uint16_t ab_smem[];
+  uint16_t* sQ = ab_smem;
+  uint16_t* sK = sQ + SPAD * kRowPad;
+  uint16_t* sV = sK + SPAD * kRowPad;
+  uint16_t* sdO = sV + SPAD * kRowPad;
+  uint16_t* sP = sdO + SPAD * kRowPad;
+  uint16_t* sdS = sP + SPAD * PP;
+  uint16_t* sOut = sdS + SPAD * PP;     // [warps][16][kRowPad] output staging
   const int head = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok0 = static_cast<long long>(b) * S;
   const int ld = 3 * H;
 
-  for (int i = tid; i < S * 8 * 4; i += blockDim.x) {
-    const int mat = i / (S * 8), rem = i - mat * S * 8;
+  for (int i = threadIdx.x; i < SPAD * 8 * 4; i += blockDim.x) {
+    const int mat = i / (SPAD * 8), rem = i - mat * SPAD * 8;
     const int r = rem >> 3, c = (rem & 7) * 8;
-    const uint16_t* src = mat < 3 ? qkv + (tok0 + r) * ld + mat * H + head * kHd + c
-                                  : dctx + (tok0 + r) * H + head * kHd + c;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sQ + mat * S * kPitch + r * kPitch + c);
-    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < S) {
+      const uint16_t* src = mat < 3 ? qkv + (tok0 + r) * ld + mat * H + head * kHeadDim + c
+                                    : dctx + (tok0 + r) * H + head * kHeadDim + c;
+      v = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+    *reinterpret_cast<uint4*>(ab_smem + mat * SPAD * kRowPad + r * kRowPad + c) = v;
   }
-  for (int j = tid; j < S; j += blockDim.x) sMb[j] = mask[tok0 + j] != 0 ? 0.f : -10000.f;
   __syncthreads();
 
-  // scores
-  for (int idx = tid; idx < S * S; idx += blockDim.x) {
-    const int i = idx / S, j = idx - i * S;
-    sP[i * (S + 1) + j] = fmaf(dot64(sQ + i * kPitch, sK + j * kPitch, fmt), 0.125f, sMb[j]);
-  }
-  __syncthreads();
-  // row softmax + D_i = dO_i . O_i
-  for (int i = warp; i < S; i += 8) {
-    float* row = sP + i * (S + 1);
-    float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, row[j]);
+  const int g = lane >> 2, t = lane & 3;
+  const int row0 = warp * 16;
+  uint16_t* stage = sOut + warp * 16 * kRowPad;
+  auto smem_addr = [](const uint16_t* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); };
+  // 16 x 64 fp32 fragments -> staging -> global rows [row0, row0 + 16) of column block `which` (0 = dQ, 1 = dK, 2 = dV)
+  auto store_tile = [&](float (&o)[8][4], int which) {
+    __syncwarp();
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-    float sum = 0.f;
-    for (int j = lane; j < S; j += 32) {
-      const float e = __expf(row[j] - mx);
-      row[j] = e;
-      sum += e;
+    for (int n = 0; n < 8; ++n) {
+      *reinterpret_cast<uint32_t*>(stage + g * kRowPad + n * 8 + t * 2) = pk2<FMT>(o[n][0], o[n][1]);
+      *reinterpret_cast<uint32_t*>(stage + (g + 8) * kRowPad + n * 8 + t * 2) = pk2<FMT>(o[n][2], o[n][3]);
     }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int j = lane; j < S; j += 32) row[j] *= inv;
-    const uint32_t uo = __ldg(reinterpret_cast<const uint32_t*>(ctx + (tok0 + i) * H + head * kHd + lane * 2));
-    const uint32_t ud = *reinterpret_cast<const uint32_t*>(sdO + i * kPitch + lane * 2);
-    const float2 o2 = fmt == 1 ? cvt2<1>(uo) : cvt2<0>(uo);
-    const float2 d2 = fmt == 1 ? cvt2<1>(ud) : cvt2<0>(ud);
-    const float d = warp_sum(fmaf(o2.x, d2.x, o2.y * d2.y));
-    if (lane == 0) sD[i] = d;
-  }
-  __syncthreads();
-  // dV[j, d] = sum_i P[i, j] dO[i, d]
-  for (int idx = tid; idx < S * kHd; idx += blockDim.x) {
-    const int j = idx >> 6, d = idx & 63;
-    float acc = 0.f;
-    for (int i = 0; i < S; ++i) acc = fmaf(sP[i * (S + 1) + j], h2f(sdO[i * kPitch + d], fmt), acc);
-    dqkv[(tok0 + j) * ld + 2 * H + head * kHd + d] = f2h(acc, fmt);
-  }
-  __syncthreads();
-  // dS = P * (dP - D) / 8 in place, dP[i, j] = dO_i . V_j
-  for (int idx = tid; idx < S * S; idx += blockDim.x) {
-    const int i = idx / S, j = idx - i * S;
-    const float dp = dot64(sdO + i * kPitch, sV + j * kPitch, fmt);
-    sP[i * (S + 1) + j] *= (dp - sD[i]) * 0.125f;
-  }
-  __syncthreads();
-  // dQ[i, d] = sum_j dS[i, j] K[j, d];  dK[j, d] = sum_i dS[i, j] Q[i, d]
-  for (int idx = tid; idx < S * kHd; idx += blockDim.x) {
-    const int r = idx >> 6, d = idx & 63;
-    float aq = 0.f, ak = 0.f;
-    for (int t = 0; t < S; ++t) {
-      aq = fmaf(sP[r * (S + 1) + t], h2f(sK[t * kPitch + d], fmt), aq);
-      ak = fmaf(sP[t * (S + 1) + r], h2f(sQ[t * kPitch + d], fmt), ak);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 32 + lane;
+      const int r = idx >> 3, c = (idx & 7) * 8;
+      if (row0 + r < S)
+        *reinterpret_cast<uint4*>(dqkv + (tok0 + row0 + r) * ld + which * H + head * kHeadDim + c) =
+            *reinterpret_cast<const uint4*>(stage + r * kRowPad + c);
     }
-    dqkv[(tok0 + r) * ld + head * kHd + d] = f2h(aq, fmt);
-    dqkv[(tok0 + r) * ld + H + head * kHd + d] = f2h(ak, fmt);
+  };
+
+  // ---------------------------------------------------------------- phase 1: query-row block of this warp
+  {
+    uint32_t qa[4][4], da[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+      const int c = ks * 16 + 8 * (lane >> 4);
+      ldsm_x4(qa[ks], smem_addr(sQ + r * kRowPad + c));
+      ldsm_x4(da[ks], smem_addr(sdO + r * kRowPad + c));
+    }
+    float sc[NT][4], dp[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+      dp[n][0] = dp[n][1] = dp[n][2] = dp[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int n2 = 0; n2 < NT / 2; ++n2) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t kb[4], vb[4];
+        const int r = n2 * 16 + (lane & 7) + 8 * (lane >> 4);
+        const int c = ks * 16 + 8 * ((lane >> 3) & 1);
+        ldsm_x4(kb, smem_addr(sK + r * kRowPad + c));
+        ldsm_x4(vb, smem_addr(sV + r * kRowPad + c));
+        mma16816<FMT>(sc[2 * n2], qa[ks], kb[0], kb[1]);
+        mma16816<FMT>(sc[2 * n2 + 1], qa[ks], kb[2], kb[3]);
+        mma16816<FMT>(dp[2 * n2], da[ks], vb[0], vb[1]);
+        mma16816<FMT>(dp[2 * n2 + 1], da[ks], vb[2], vb[3]);
+      }
+    }
+    // softmax over keys, exactly as attention_kernel (rows g and g + 8 of this warp)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = n * 8 + t * 2 + j;
+        float add;
+        if (col >= S) add = -INFINITY;
+        else add = mask[tok0 + col] != 0 ? 0.f : -10000.f;
+        sc[n][j] = fmaf(sc[n][j], 0.125f, add);
+        sc[n][2 + j] = fmaf(sc[n][2 + j], 0.125f, add);
+        mx0 = fmaxf(mx0, sc[n][j]);
+        mx1 = fmaxf(mx1, sc[n][2 + j]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xFFFFFFFFu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xFFFFFFFFu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[n][j] = __expf(sc[n][j] - mx0);
+        sc[n][2 + j] = __expf(sc[n][2 + j] - mx1);
+        sum0 += sc[n][j];
+        sum1 += sc[n][2 + j];
+      }
+    }
+    sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xFFFFFFFFu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
+    const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sc[n][j] *= inv0;
+        sc[n][2 + j] *= inv1;
+        d0 = fmaf(sc[n][j], dp[n][j], d0);
+        d1 = fmaf(sc[n][2 + j], dp[n][2 + j], d1);
+      }
+    }
+    d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, 1);
+    d0 += __shfl_xor_sync(0xFFFFFFFFu, d0, 2);
+    d1 += __shfl_xor_sync(0xFFFFFFFFu, d1, 1);
+    d1 += __shfl_xor_sync(0xFFFFFFFFu, d1, 2);
+    // P and dS = P (dP - D) / 8 as 16-bit tiles: A fragments of dQ = dS K here, transposed operands of phase 2
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const uint32_t p_lo = pk2<FMT>(sc[n][0], sc[n][1]), p_hi = pk2<FMT>(sc[n][2], sc[n][3]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        dp[n][j] = sc[n][j] * (dp[n][j] - d0) * 0.125f;
+        dp[n][2 + j] = sc[n][2 + j] * (dp[n][2 + j] - d1) * 0.125f;
+      }
+      const int col = n * 8 + t * 2;
+      *reinterpret_cast<uint32_t*>(sP + (row0 + g) * PP + col) = p_lo;
+      *reinterpret_cast<uint32_t*>(sP + (row0 + g + 8) * PP + col) = p_hi;
+      *reinterpret_cast<uint32_t*>(sdS + (row0 + g) * PP + col) = pk2<FMT>(dp[n][0], dp[n][1]);
+      *reinterpret_cast<uint32_t*>(sdS + (row0 + g + 8) * PP + col) = pk2<FMT>(dp[n][2], dp[n][3]);
+    }
+#pragma unroll
+    for (int kk = 0; kk < SPAD / 16; ++kk) {
+      uint32_t sa[4];
+      sa[0] = pk2<FMT>(dp[2 * kk][0], dp[2 * kk][1]);
+      sa[1] = pk2<FMT>(dp[2 * kk][2], dp[2 * kk][3]);
+      sa[2] = pk2<FMT>(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+      sa[3] = pk2<FMT>(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+      for (int d2 = 0; d2 < 4; ++d2) {
+        uint32_t kb[4];
+        const int r = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int c = d2 * 16 + 8 * (lane >> 4);
+        ldsm_x4_t(kb, smem_addr(sK + r * kRowPad + c));
+        mma16816<FMT>(o[2 * d2], sa, kb[0], kb[1]);
+        mma16816<FMT>(o[2 * d2 + 1], sa, kb[2], kb[3]);
+      }
+    }
+    store_tile(o, 0);
   }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- phase 2: key-row block of this warp
+  {
+    float ov[8][4], ok[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      ov[n][0] = ov[n][1] = ov[n][2] = ov[n][3] = 0.f;
+      ok[n][0] = ok[n][1] = ok[n][2] = ok[n][3] = 0.f;
+    }
+#pragma unroll
+    for (int kk = 0; kk < SPAD / 16; ++kk) {
+      // A = (P^T | dS^T)[keys row0 .. +16, queries 16 kk .. +16]: tile (m, k) sits at stored [16 kk + k][row0 + m]
+      uint32_t pa[4], sa[4];
+      const int ar = kk * 16 + (lane & 7) + 8 * (lane >> 4);
+      const int ac = row0 + 8 * ((lane >> 3) & 1);
+      ldsm_x4_t(pa, smem_addr(sP + ar * PP + ac));
+      ldsm_x4_t(sa, smem_addr(sdS + ar * PP + ac));
+#pragma unroll
+      for (int d2 = 0; d2 < 4; ++d2) {
+        uint32_t ob[4], qb[4];
+        const int r = kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        const int c = d2 * 16 + 8 * (lane >> 4);
+        ldsm_x4_t(ob, smem_addr(sdO + r * kRowPad + c));
+        ldsm_x4_t(qb, smem_addr(sQ + r * kRowPad + c));
+        mma16816<FMT>(ov[2 * d2], pa, ob[0], ob[1]);
+        mma16816<FMT>(ov[2 * d2 + 1], pa, ob[2], ob[3]);
+        mma16816<FMT>(ok[2 * d2], sa, qb[0], qb[1]);
+        mma16816<FMT>(ok[2 * d2 + 1], sa, qb[2], qb[3]);
+      }
+    }
+    store_tile(ok, 1);
+    store_tile(ov, 2);
+  }
+}
+
+template <int FMT>
+static int attention_bwd_launch(const void* qkv, const long long* mask, const void* dctx, void* dqkv, int B, int S, int H,
+                                int heads, cudaStream_t st) {
+  const int spad = (S + 15) / 16 * 16;
+  const dim3 grid(heads, B);
+  const size_t smem = (static_cast<size_t>(4) * spad * kRowPad + static_cast<size_t>(2) * spad * (spad + 8) +
+                       static_cast<size_t>(spad / 16) * 16 * kRowPad) * sizeof(uint16_t);
+#define LDOT_ATTB_CASE(SP)                                                                                         \
+  case SP: {                                                                                                       \
+    auto kern = attention_bwd_kernel<SP, FMT>;                                                                     \
+    if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<const uint16_t*>(dctx),  \
+                                      static_cast<uint16_t*>(dqkv), S, H);                                         \
+    break;                                                                                                         \
+  }
+  switch (spad) {
+    LDOT_ATTB_CASE(16)
+    LDOT_ATTB_CASE(32)
+    LDOT_ATTB_CASE(48)
+    LDOT_ATTB_CASE(64)
+    LDOT_ATTB_CASE(80)
+    LDOT_ATTB_CASE(96)
+    LDOT_ATTB_CASE(112)
+    LDOT_ATTB_CASE(128)
+    default:
+      return set_error(kErrArg, "attention_bwd: sequence length %d > 128 not supported", S);
+  }
+#undef LDOT_ATTB_CASE
+  LDOT_CHECK_LAUNCH();
+  return kOk;
 }
 
 int attention_bwd_run(const void* qkv, const long long* mask, const void* ctx, const void* dctx, void* dqkv, int B, int S,
                       int H, int heads, int fmt, void* stream) {
+  (void)ctx;   // (D_i = dO_i . O_i is evaluated as sum_j P_ij dP_ij from the recomputed probabilities)
   LDOT_REQUIRE(B >= 1 && S >= 1 && S <= 128, "attention_bwd: bad shape B=%d S=%d (S <= 128)", B, S);
-  LDOT_REQUIRE(H == heads * kHd, "attention_bwd: hidden %d must be heads (%d) x 64", H, heads);
+  LDOT_REQUIRE(H == heads * kHeadDim, "attention_bwd: hidden %d must be heads (%d) x 64", H, heads);
   LDOT_REQUIRE(B <= 65535, "attention_bwd: batch %d > 65535 (split the batch)", B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(4) * S * kPitch * 2 + (static_cast<size_t>(S) * (S + 1) + 2 * S) * 4;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    LDOT_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   KernelScope ks(kKcAttention, st, 10.0 * B * static_cast<double>(S) * S * H, static_cast<double>(B) * S * H * 16.0);
-  attention_bwd_kernel<<<dim3(heads, B), 256, smem, st>>>(static_cast<const uint16_t*>(qkv), mask,
-                                                           static_cast<const uint16_t*>(ctx),
-                                                           static_cast<const uint16_t*>(dctx),
-                                                           static_cast<uint16_t*>(dqkv), S, H, fmt);
-  LDOT_CHECK_LAUNCH();
-  return kOk;
+  return fmt == 1 ? attention_bwd_launch<1>(qkv, mask, dctx, dqkv, B, S, H, heads, st)
+                  : attention_bwd_launch<0>(qkv, mask, dctx, dqkv, B, S, H, heads, st);
 }
 
 // ------------------------------------------------------------------------------------------------ GELU (elementwise)

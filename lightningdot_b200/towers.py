@@ -81,7 +81,8 @@ class TowerEngine:
             """[3 n, ...] operand over three parameters: ONE strided view when their (aliased) copies are adjacent."""
             parts, aliases = zip(*[conv(k) for k in keys])
             step = parts[0].numel() * parts[0].element_size()
-            if all(aliases) and all(parts[j].data_ptr() == parts[0].data_ptr() + j * step for j in (1, 2)):
+            same = all(parts[j].untyped_storage().data_ptr() == parts[0].untyped_storage().data_ptr() for j in (1, 2))
+            if same and all(aliases) and all(parts[j].data_ptr() == parts[0].data_ptr() + j * step for j in (1, 2)):
                 shape = (3 * parts[0].shape[0],) + tuple(parts[0].shape[1:])
                 return torch.as_strided(parts[0], shape, parts[0].stride())
             for k in keys:

@@ -51,7 +51,8 @@ class _GradSinks(dict):
         ts = [self.sinks.get(n) for n in names]
         if all(t is not None for t in ts):
             step = ts[0].numel() * 4
-            if all(ts[j].data_ptr() == ts[0].data_ptr() + j * step for j in (1, 2)):
+            same = all(ts[j].untyped_storage().data_ptr() == ts[0].untyped_storage().data_ptr() for j in (1, 2))
+            if same and all(ts[j].data_ptr() == ts[0].data_ptr() + j * step for j in (1, 2)):
                 for n, t in zip(names, ts):
                     self[n] = t
                 return torch.as_strided(ts[0], (3 * rows,) + tuple(rest), ts[0].stride())
