@@ -417,6 +417,30 @@ def run_ours(args):
                   "traffic": None, "kernel": "coarse_score_topk", "queries_per_pass": 128,
                   "shard_rows": int(hi - lo), "us_per_launch": 1e3 * c["ms"] / max(1, c["timed"]),
                   "search_us_total": 1e3 * tot / 10, "peak_source": peaks["source"]}
+        if world == 1 and not args.no_e2e:
+            # retrieve_query / rerank.py regime end to end (host token ids -> host top-k): eager calls vs ONE CUDA graph
+            from lightningdot_b200.online import GraphedRetriever
+            lat = {}
+            for qb in (1, 128):
+                gr = GraphedRetriever(txt_model, indexer.index, batch=qb, seq_len=L, k=k)
+                qi, qm = ids_h[:qb], mask_h[:qb]
+
+                def eager():
+                    with torch.no_grad():
+                        _, e, _ = txt_model(qi.to(dev), qm.to(dev), pos_d, need_sequence=False)
+                    return indexer.index.search(e, k)
+                for fn, tag in ((lambda: gr.search(qi, qm), "graph"), (eager, "eager")):
+                    for _ in range(3):
+                        res = fn()
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for _ in range(20):
+                        res = fn()
+                    lat[f"{tag}_us_per_call_batch{qb}"] = 1e6 * (time.perf_counter() - t0) / 20
+                same = bool((gr.search(qi, qm)[1] == eager()[1]).all())
+                lat[f"graph_equals_eager_batch{qb}"] = same
+                del gr
+            online["e2e_latency"] = lat
     barrier()
 
     if rank != 0:

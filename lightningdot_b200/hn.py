@@ -1,0 +1,92 @@
+"""Host-side mirror of dvl/hn.py: hard-negative mining for train_itm.py.
+
+  random_hard_neg           dvl/hn.py:17-27    random same-set negatives
+  get_img_txt_mappings      dvl/hn.py:30-44    img <-> txt <-> dataset-folder maps from the img2txts.json files
+  sampled_hard_negatives    dvl/hn.py:47-68    encode the training set, search both directions with
+                                               num_tops = min(max(2 * num_hard_negatives + 10, 50), 1000), drop the
+                                               positives, sample num_hard_negatives per query
+
+The device work is eval_model_on_dataloader (trainer.py): both towers over the whole training set, two exact top-k
+searches with k up to 1000 through the same fused score + top-k kernel as evaluation (ldot_flatip_search supports
+k <= 1024).  Only the dataset plumbing differs from the reference: its load_dataset / build_dataloader read LMDB
+databases (lmdb, lz4 - not available here), so the per-dataset dataloaders are passed in.
+"""
+import collections
+import itertools
+import json
+import logging
+import os
+import random
+from collections import ChainMap
+
+from .trainer import eval_model_on_dataloader
+
+logger = logging.getLogger()
+
+
+def random_hard_neg(fname2id, num_hard_negatives, id2set, set2id):
+    """dvl/hn.py:17-27 (num_hard_negatives must be very small: rejection sampling)."""
+    hard_negs = dict()
+    for i in fname2id:
+        while True:
+            hard_neg = random.choices(set2id[id2set[i]], k=num_hard_negatives)
+            if fname2id[i] not in hard_neg:
+                break
+        hard_negs[i] = hard_neg
+    return hard_negs
+
+
+def get_img_txt_mappings(train_txt_dbs):
+    """dvl/hn.py:30-44 -> (img2txt, txt2img, img2set, txt2set, set2img, set2txt)."""
+    train_json = []
+    for db_folder in train_txt_dbs:
+        with open(os.path.join(db_folder, 'img2txts.json')) as f:
+            train_json.append(json.load(f))
+    train_img2txt = dict(ChainMap(*train_json))
+    train_txt2img = dict(itertools.chain(*[[(v, k) for v in vals] for k, vals in train_img2txt.items()]))
+    train_img2set = dict(ChainMap(*[{k: v for k in tj} for tj, v in zip(train_json, train_txt_dbs)]))
+    train_txt2set = {txt_id: train_img2set[img_id] for txt_id, img_id in train_txt2img.items()}
+    train_set2img, train_set2txt = collections.defaultdict(list), collections.defaultdict(list)
+    for img_id, set_id in train_img2set.items():
+        train_set2img[set_id].append(img_id)
+        train_set2txt[set_id] += train_img2txt[img_id]
+    return train_img2txt, train_txt2img, train_img2set, train_txt2set, train_set2img, train_set2txt
+
+
+def num_hard_sampled(num_hard_negatives):
+    """Candidates retrieved per query before the positives are removed (dvl/hn.py:55)."""
+    return min(max(num_hard_negatives * 2 + 10, 50), 1000)
+
+
+def filter_and_sample(hard_neg_img, hard_neg_txt, train_img2txt, train_txt2img, num_hard_negatives):
+    """dvl/hn.py:59-65.  hard_neg_img: {txt id: ranked image ids} (text -> image search), hard_neg_txt: {image id: ranked
+    text ids}.  The positive image is removed from each text's list (in place, order kept), the positive captions from
+    each image's list (through a set, as the reference does), then num_hard_negatives are drawn without replacement."""
+    for k, v in hard_neg_img.items():
+        if train_txt2img[k] in v:
+            v.remove(train_txt2img[k])
+    hard_neg_txt = {k: list(set(v) - set(train_img2txt[k])) for k, v in hard_neg_txt.items()}
+    txt_out = {k: random.sample(v, num_hard_negatives) for k, v in hard_neg_txt.items()}
+    img_out = {k: random.sample(v, num_hard_negatives) for k, v in hard_neg_img.items()}
+    return txt_out, img_out
+
+
+def sampled_hard_negatives(all_img_dbs, args, collate_func, bi_encoder, train_img2txt, train_txt2img,
+                           train_dataloaders=None):
+    """dvl/hn.py:47-68.  `train_dataloaders`: one evaluation-mode dataloader per training dataset (what the reference
+    builds from LMDB with load_dataset(..., True) + build_dataloader(dset, collate_func, True, args,
+    args.valid_batch_size)); required here."""
+    if train_dataloaders is None:
+        raise NotImplementedError(
+            "the LMDB-backed load_dataset / build_dataloader of dvl/trainer.py are outside this package (no lmdb / lz4): "
+            "pass train_dataloaders=[one eval-mode dataloader per training dataset]")
+    hard_negs_txt_all, hard_negs_img_all = [], []
+    for loader in train_dataloaders:
+        logger.info(f'eval for train dataloader len (for hn) = {len(loader)}')
+        k = num_hard_sampled(args.num_hard_negatives)
+        _, _, _, _, (hard_neg_img, hard_neg_txt) = eval_model_on_dataloader(bi_encoder, loader, args, train_img2txt, k)
+        txt_out, img_out = filter_and_sample(hard_neg_img, hard_neg_txt, train_img2txt, train_txt2img,
+                                             args.num_hard_negatives)
+        hard_negs_txt_all.append(txt_out)
+        hard_negs_img_all.append(img_out)
+    return dict(ChainMap(*hard_negs_txt_all)), dict(ChainMap(*hard_negs_img_all))

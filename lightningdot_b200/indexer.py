@@ -118,9 +118,12 @@ class FlatIPIndex:
         return pin[0][:nq].numpy().copy(), pin[1][:nq].numpy().copy()
 
     # -- device-level API (used by the eval loop and the benchmark to avoid host round trips) -------------------
-    def search_device(self, qd, k, resolve_flags=True):
+    def search_device(self, qd, k, resolve_flags=True, return_flags=False):
         """qd: cuda fp32 [nq, d].  -> (scores [nq, k] fp32, labels [nq, k] int64) cuda tensors.
-        With resolve_flags (default) flagged queries are re-run exhaustively (one 4-byte D2H sync per call)."""
+        With resolve_flags (default) flagged queries are re-run exhaustively (one 4-byte D2H sync per call).
+        resolve_flags=False, return_flags=True: no host synchronisation at all (CUDA-graph capturable); additionally
+        returns (flags int32 [nq] on the device, per-call flagged counts in PINNED host memory) for the caller to check
+        after it has synchronised (online.py)."""
         lib = _lib.load()
         self._finalize()
         if qd.dim() != 2 or qd.shape[1] != self.d:
@@ -168,6 +171,8 @@ class FlatIPIndex:
                     self.last_exhaustive = n2
                 scores.index_copy_(0, rows, s2)
                 idx.index_copy_(0, rows, i2)
+        if return_flags:
+            return scores, idx, flags, n_flag
         return scores, idx
 
     def _auto_coarse_k(self, k):

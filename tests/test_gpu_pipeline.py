@@ -205,3 +205,72 @@ def test_launch_accounting(cuda_lib):
     assert c["launches"] == 3 and c["timed"] == 3 and c["ms"] > 0
     assert c["flops"] == 3 * 2.0 * 256 * 20000 * 768
     assert p["rescore"]["launches"] == 3 and p["select"]["launches"] >= 3 and p["linear_tcgen05"]["launches"] == 0
+
+
+def test_hard_negative_mining_on_gpu(cuda_lib):
+    """dvl/hn.py:47-68 through the CUDA eval loop with num_tops = 90 (num_hard_negatives = 40; the fixture's image index
+    has 200 rows, and past the index size faiss pads with label -1, which the reference maps to the LAST db id): every
+    sampled negative comes from the oracle's exact top-90 of its query and is never a positive."""
+    import random
+    from lightningdot_b200 import hn
+    txt, img, batches, img2txt = evalloop_inputs()
+    txt2img = {t: i for i, ts in img2txt.items() for t in ts}
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0, num_hard_negatives=40)
+    random.seed(3)
+    neg_txt, neg_img = hn.sampled_hard_negatives(None, args, None, StubEncoder(txt, img, "cuda"), img2txt, txt2img,
+                                                 train_dataloaders=[batches])
+    assert len(neg_txt) == 200 and len(neg_img) == 1000
+    k = hn.num_hard_sampled(40)
+    assert k == 90
+    _, oi = flatip.search(txt, img[4::5], k)          # text -> image (index rows = images in first-seen order)
+    for j in (0, 17, 503, 999):
+        got = neg_img[str(j)]
+        want = {f"img_{r:07d}.npz" for r in oi[j]}
+        assert len(got) == 40 and len(set(got)) == 40 and txt2img[str(j)] not in got and set(got) <= want
+    _, oi2 = flatip.search(img[4::5], txt, k)         # image -> text
+    for i in (0, 99, 199):
+        name = f"img_{i:07d}.npz"
+        got = neg_txt[name]
+        assert len(got) == 40 and not set(got) & set(img2txt[name]) and set(got) <= {str(r) for r in oi2[i]}
+
+
+def test_graphed_retriever_matches_eager_path(cuda_lib):
+    """online.GraphedRetriever (token ids -> text tower -> exact top-k as one CUDA graph, rows a9 / f3) against the eager
+    calls on the same padded inputs (bit-identical: same kernels, same data) and against the un-padded call of
+    dvl/utils.py:204-211 (ids identical, scores to 1e-3 relative: padding changes only the softmax summation width)."""
+    from lightningdot_b200.online import GraphedRetriever, retrieve_query
+    sd = synth.random_tower_state("txt", seed=21, perturb=True, layers=2)
+    model = BertEncoder(TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=2), project_dim=768)
+    model.load_state_dict(sd, strict=True)
+    model.cuda().eval()
+    n, k, L = 6000, 10, 24
+    tb = synth.text_batch(64, L, seed=5, ragged=True)
+    with torch.no_grad():
+        _, emb, _ = model(tb["input_ids"].cuda(), tb["attention_mask"].cuda(), tb["position_ids"].cuda(), need_sequence=False)
+    x = synth.gaussian_index(n, 768, seed=9)
+    x[100:164] = emb.cpu().numpy() * 0.9 + x[100:164] * 0.1      # rows close to the queries: a meaningful ranking
+    ix = DenseFlatIndexer(768)
+    ids = [f"img_{i:07d}.npz" for i in range(n)]
+    ix.index_matrix(ids, x)
+    gr = GraphedRetriever(model, ix, batch=4, seq_len=L, k=k)
+    for lo in (0, 4, 9):
+        nb = 3 if lo == 9 else 4
+        q_ids, q_mask = tb["input_ids"][lo:lo + nb], tb["attention_mask"][lo:lo + nb]
+        s, lab = gr.search(q_ids, q_mask)
+        with torch.no_grad():
+            _, e, _ = model(q_ids.cuda(), q_mask.cuda(), tb["position_ids"].cuda(), need_sequence=False)
+        es, el = ix.index.search(e, k)
+        assert np.array_equal(lab, el) and np.array_equal(s, es)
+        os_, oi = flatip.search(e.cpu().numpy(), x, k)
+        assert np.array_equal(lab, oi)
+    assert gr.replays == 3 and gr.fallbacks == 0
+    # one un-padded query, the retrieve_query way
+    length = int(tb["attention_mask"][1].sum())
+    tok = types.SimpleNamespace(encode=lambda text: tb["input_ids"][1, :length].tolist())
+    res = retrieve_query(GraphedRetriever(model, ix, batch=1, seq_len=L, k=k), "a query", types.SimpleNamespace(tokenizer=tok))
+    with torch.no_grad():
+        _, e1, _ = model(tb["input_ids"][1:2, :length].cuda(), torch.ones(1, length, dtype=torch.long).cuda(),
+                         torch.arange(length)[None].cuda(), need_sequence=False)
+    want = ix.search_knn(e1, k)
+    assert res[0][0] == want[0][0]
+    np.testing.assert_allclose(res[0][1], want[0][1], rtol=1e-3)

@@ -289,3 +289,45 @@ def test_global_batch_training_protocol_two_ranks_gloo(tmp_path):
         port = s.getsockname()[1]
     mp.spawn(_train_sync_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def test_hard_negative_sampling_logic(tmp_path, monkeypatch):
+    """dvl/hn.py: candidate count formula, positives removed (image side in place / order kept, text side through a set),
+    num_hard_negatives drawn without replacement, per-dataset results chained; mapping builder on img2txts.json."""
+    import json as _json
+    import random as _random
+    from lightningdot_b200 import hn
+    assert [hn.num_hard_sampled(k) for k in (0, 10, 20, 100, 600)] == [50, 50, 50, 210, 1000]
+    img2txt = {"a.npz": ["0", "1"], "b.npz": ["2", "3"], "c.npz": ["4"]}
+    txt2img = {t: i for i, ts in img2txt.items() for t in ts}
+    rank_txt = {"0": ["b.npz", "a.npz", "c.npz"], "2": ["a.npz", "c.npz", "b.npz"], "4": ["a.npz", "b.npz"]}
+    rank_img = {"a.npz": ["1", "2", "0", "4"], "b.npz": ["4", "0", "3", "1"], "c.npz": ["0", "2", "4"]}
+    _random.seed(0)
+    t_out, i_out = hn.filter_and_sample({k: list(v) for k, v in rank_txt.items()}, rank_img, img2txt, txt2img, 2)
+    assert set(t_out) == set(rank_img) and set(i_out) == set(rank_txt)
+    for img, negs in t_out.items():
+        assert len(negs) == 2 and len(set(negs)) == 2 and not set(negs) & set(img2txt[img]) and set(negs) <= set(rank_img[img])
+    for txt, negs in i_out.items():
+        assert len(negs) == 2 and txt2img[txt] not in negs and set(negs) <= set(rank_txt[txt])
+    # plumbing: one eval per dataloader with k = num_hard_sampled, later datasets do not override earlier keys (ChainMap)
+    calls = []
+
+    def fake_eval(model, loader, args, i2t, k):
+        calls.append((loader, k))
+        return 0.0, 0.0, None, None, ({k_: list(v) for k_, v in rank_txt.items()}, dict(rank_img))
+    monkeypatch.setattr(hn, "eval_model_on_dataloader", fake_eval)
+    args = types.SimpleNamespace(num_hard_negatives=2)
+    t_all, i_all = hn.sampled_hard_negatives(None, args, None, object(), img2txt, txt2img, train_dataloaders=[[1], [2]])
+    assert calls == [([1], 50), ([2], 50)] and set(t_all) == set(rank_img) and set(i_all) == set(rank_txt)
+    with pytest.raises(NotImplementedError):
+        hn.sampled_hard_negatives(None, args, None, object(), img2txt, txt2img)
+    # mappings
+    for name, part in (("d1", {"a.npz": ["0", "1"]}), ("d2", {"b.npz": ["2", "3"], "c.npz": ["4"]})):
+        os.makedirs(tmp_path / name)
+        _json.dump(part, open(tmp_path / name / "img2txts.json", "w"))
+    dbs = [str(tmp_path / "d1"), str(tmp_path / "d2")]
+    i2t, t2i, i2s, t2s, s2i, s2t = hn.get_img_txt_mappings(dbs)
+    assert i2t == img2txt and t2i == txt2img and i2s["c.npz"] == dbs[1] and t2s["1"] == dbs[0]
+    assert sorted(s2i[dbs[1]]) == ["b.npz", "c.npz"] and sorted(s2t[dbs[1]]) == ["2", "3", "4"]
+    negs = hn.random_hard_neg({"b.npz": "b.npz", "c.npz": "c.npz"}, 1, i2s, s2i)   # (a one-image set would never end)
+    assert negs["b.npz"] == ["c.npz"] and negs["c.npz"] == ["b.npz"]
