@@ -45,7 +45,7 @@ template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
   auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS, AMN, BMN, RED>;
-  using SM = LinSmemT<CTAS>;
+  using SM = LinSmemT<CTAS, lin_epi_warps(ACT)>;
   static bool configured = false;  // (one device per process)
   static int max_groups = 0;       // resident CTAs (CTAS = 1) or CTA pairs (CTAS = 2)
   cudaLaunchConfig_t cfg = {};
@@ -54,7 +54,7 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kLinThreads);
+  cfg.blockDim = dim3(lin_threads(ACT));
   cfg.dynamicSmemBytes = SM::kDynamic;
   cfg.stream = st;
   cfg.attrs = attr;

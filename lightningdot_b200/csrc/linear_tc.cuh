@@ -3,7 +3,8 @@
 // Persistent, warp-specialised, one CTA per SM, 320 threads:
 //   warp 0      TMA producer: A (activations) 128 x 64 and W 256 x 64 K-major boxes, SWIZZLE_128B, 4-stage ring
 //   warp 1      TMEM owner + tcgen05.mma issuer (128 x 256 x 16 per instruction, fp32 accumulate, 2 accumulators)
-//   warps 2..9  epilogue: warp w reads TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the 128 x 256 tile in
+//   warps 2..   epilogue (8 warps; 12 for the GELU form): warp w reads TMEM lane quarter (w % 4) and every
+//               ((w - 2) / 4)-th 32-column box of the 128 x 256 tile in
 //               16-column slices, software-pipelined: tcgen05.ld of slice s + 1 is in flight while slice s gets bias,
 //               erf-GELU, residual in registers | swizzled st.shared into the warp's staging buffer; every two
 //               slices one TMA store (cp.async.bulk.tensor) of the 32 x 32 box.  Stores are coalesced by the TMA unit and clipped at the
@@ -34,6 +35,10 @@ constexpr int kLinBN = 256;
 constexpr int kLinStages = 4;
 constexpr int kLinEpiWarps = 8;
 constexpr int kLinThreads = 32 * (2 + kLinEpiWarps);
+// The erf-GELU epilogue (FFN-up: K = 768 behind 3072 output columns) is paced by per-warp instruction latency, not by
+// a pipe: it runs with 12 epilogue warps (3 per scheduler) and pays for their staging buffers with one pipeline stage.
+__host__ __device__ constexpr int lin_epi_warps(int act) { return act == 1 ? 12 : 8; }
+__host__ __device__ constexpr int lin_threads(int act) { return 32 * (2 + lin_epi_warps(act)); }
 
 struct LinSched {
   int m_tiles, n_tiles, num_tiles, k_blocks;
@@ -52,21 +57,22 @@ struct LinParams {
   int fmt;                // 0 = fp16, 1 = bf16 (A, W, residual, 16-bit output)
 };
 
-template <int CTAS>
+template <int CTAS, int EW = kLinEpiWarps>
 struct LinSmemT {
-  static constexpr int kStages = CTAS == 2 ? 6 : kLinStages;
+  static constexpr int kStages = (CTAS == 2 ? 6 : kLinStages) - (EW > 8 ? 1 : 0);
   static constexpr int kBRows = kLinBN / CTAS;         // W rows staged by one CTA
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB
   static constexpr int kBBytes = kBRows * kBK * 2;     // 32 KB (16 KB per CTA of a pair)
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingPerWarp = 4096;         // one 32 x 32 fp32 box, or two 32 x 32 16-bit boxes
   static constexpr int kStagingOffset = kStages * kStageBytes;
-  static constexpr int kBarOffset = kStagingOffset + kLinEpiWarps * kStagingPerWarp;
+  static constexpr int kBarOffset = kStagingOffset + EW * kStagingPerWarp;
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;       // slack for manual 1024 B alignment
 };
 using LinSmem = LinSmemT<1>;
-static_assert(LinSmemT<1>::kDynamic <= 227 * 1024 && LinSmemT<2>::kDynamic <= 227 * 1024, "linear kernel shared memory");
+static_assert(LinSmemT<1>::kDynamic <= 227 * 1024 && LinSmemT<2>::kDynamic <= 227 * 1024 &&
+              LinSmemT<1, 12>::kDynamic <= 227 * 1024 && LinSmemT<2, 12>::kDynamic <= 227 * 1024, "linear kernel shared memory");
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   if (fmt == 1) {
@@ -94,10 +100,12 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
 //   RED = 1         fp32 output boxes are ADDED to global memory (cp.reduce.async.bulk.tensor .add): gradient
 //                   accumulation, and what makes split-K (sched.k_splits > 1) a pure scheduling decision.
 template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
-__global__ void __launch_bounds__(kLinThreads, 1)
+__global__ void __launch_bounds__(lin_threads(ACT), 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
-  using SM = LinSmemT<CTAS>;
+  constexpr int EW = lin_epi_warps(ACT);   // epilogue warps
+  constexpr int EC = EW / 4;               // ... per TMEM lane quarter: they share the row block's 32-column boxes
+  using SM = LinSmemT<CTAS, EW>;
   constexpr int kStages = SM::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,7 +130,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], kLinEpiWarps * CTAS);
+      ptx::mbar_init(&tempty[i], EW * CTAS);
     }
     ptx::fence_mbar_init();
   }
@@ -254,9 +262,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------------ epilogue (EW warps)
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cgrp = (warp - 2) >> 2;   // boxes cgrp, cgrp + EC, ... of every tile row block belong to this warp
     const int row = quarter * 32 + lane;
     uint8_t* staging = smem + SM::kStagingOffset + (warp - 2) * SM::kStagingPerWarp;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -267,8 +275,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t tempty_addr[2] = {CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]),
                                      CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[1]), 0) : ptx::smem_u32(&tempty[1])};
     auto release_acc = [&](int a) {
-      if (CTAS == 2) ptx::mbar_arrive_remote(tempty_addr[a]);
-      else ptx::mbar_arrive(&tempty[a]);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2) ptx::mbar_arrive_remote(tempty_addr[a]);
+        else ptx::mbar_arrive(&tempty[a]);
+      }
     };
     const int mn_tiles = sched.m_tiles * sched.n_tiles;
     for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
@@ -278,136 +290,132 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const float* bias = ks == 0 ? p.bias : nullptr;   // (split-K: the first slice carries the bias)
       const long long grow = static_cast<long long>(m_tile) * kBM + row;
       const bool row_ok = grow < p.M;
-      const int col_base = n_tile * kLinBN + half * (kLinBN / 2);
-      // 16-column slices of this warp's 128 columns that hold valid columns (uniform across the warp)
-      int nslices = (p.N - col_base + 15) / 16;
-      nslices = nslices < 0 ? 0 : (nslices > 8 ? 8 : nslices);
+      const int tile_col = n_tile * kLinBN;
+      int nboxes = (p.N - tile_col + 31) / 32;   // 32-column boxes of this tile that hold valid columns
+      nboxes = nboxes > kLinBN / 32 ? kLinBN / 32 : nboxes;
       ptx::mbar_wait(&tfull[as], aphase);
       ptx::tc_fence_after();
-      const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN + half * (kLinBN / 2));
-      if (nslices == 0) {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release_acc(as);
-      }
-      // TMEM loads are software-pipelined: slice s + 1 is in flight while slice s goes through the elementwise tail.
-      // Two slices fill one 32 x 32 staging box, which goes out as one TMA store.
-      uint32_t v2[2][16];
-      if (nslices > 0) ptx::tmem_ld16(taddr, v2[0]);
-      uint8_t* buf = staging;
+      const uint32_t taddr = lane_base + static_cast<uint32_t>(as * kLinBN);
+      if (cgrp >= nboxes) {
+        release_acc(as);
+      } else {
+        // TMEM loads are software-pipelined over 16-column slices: slice s + 1 is in flight while slice s goes through
+        // the elementwise tail.  Two slices fill one 32 x 32 staging box, which leaves as one TMA store.
+        uint32_t v2[2][16];
+        ptx::tmem_ld16(taddr + cgrp * 32, v2[0]);
+        for (int bx = cgrp; bx < nboxes; bx += EC) {
+          uint8_t* buf = OUT_F32 ? staging : staging + (nstore & 1u) * (SM::kStagingPerWarp / 2);
 #pragma unroll
-      for (int sl = 0; sl < 8; ++sl) {
-        if (sl >= nslices) break;
-        const int col = col_base + sl * 16;
-        const bool full_slice = col + 16 <= p.N;
-        uint32_t (&v)[16] = v2[sl & 1];
-        // operands of the elementwise tail are fetched while the TMEM load is in flight
-        float4 b4[4];
-        if (bias != nullptr && full_slice) {
+          for (int hs = 0; hs < 2; ++hs) {
+            const int col = tile_col + bx * 32 + hs * 16;
+            const bool valid = col < p.N;               // (warp-uniform)
+            const bool full_slice = col + 16 <= p.N;
+            uint32_t (&v)[16] = v2[hs];
+            // operands of the elementwise tail are fetched while the TMEM load is in flight
+            float4 b4[4];
+            if (bias != nullptr && full_slice) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col) + j);
-        }
-        uint4 r4[2];
-        const bool res_vec = p.residual != nullptr && row_ok && full_slice;
-        if (res_vec) {
-          const uint4* r = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col);
-          r4[0] = __ldg(r);
-          r4[1] = __ldg(r + 1);
-        }
-        ptx::tmem_ld_wait();
-        if (sl + 1 < nslices) {
-          ptx::tmem_ld16(taddr + (sl + 1) * 16, v2[(sl + 1) & 1]);
-        } else {  // accumulator drained: hand it back to the MMA warp before the math
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) release_acc(as);
-        }
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (bias != nullptr) {
-          if (full_slice) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              f[4 * j] += b4[j].x;
-              f[4 * j + 1] += b4[j].y;
-              f[4 * j + 2] += b4[j].z;
-              f[4 * j + 3] += b4[j].w;
+              for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + col) + j);
             }
-          } else {
+            uint4 r4[2];
+            const bool res_vec = p.residual != nullptr && row_ok && full_slice;
+            if (res_vec) {
+              const uint4* r = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col);
+              r4[0] = __ldg(r);
+              r4[1] = __ldg(r + 1);
+            }
+            ptx::tmem_ld_wait();
+            if (hs == 0) ptx::tmem_ld16(taddr + bx * 32 + 16, v2[1]);
+            else if (bx + EC < nboxes) ptx::tmem_ld16(taddr + (bx + EC) * 32, v2[0]);
+            else release_acc(as);   // accumulator drained: hand it back to the MMA warp before the math
+            if (hs == 0) {          // the staging buffer of the store two boxes back must have been read
+              if (lane == 0) {
+                if (OUT_F32) ptx::bulk_wait_group_read<0>();
+                else ptx::bulk_wait_group_read<1>();
+              }
+              __syncwarp();
+            }
+            if (valid) {
+              float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col + j < p.N) f[j] += __ldg(bias + col + j);
-          }
-        }
-        if (ACT == 1) {
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+              if (bias != nullptr) {
+                if (full_slice) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (p.residual != nullptr && row_ok) {
-          if (full_slice) {
-#pragma unroll
-            for (int j4 = 0; j4 < 2; ++j4) {
-              const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float2 x = unpack2(w[q], p.fmt);
-                if (ACT == 2) {
-                  f[j4 * 8 + q * 2] *= gelu_erf_grad(x.x);
-                  f[j4 * 8 + q * 2 + 1] *= gelu_erf_grad(x.y);
+                  for (int j = 0; j < 4; ++j) {
+                    f[4 * j] += b4[j].x;
+                    f[4 * j + 1] += b4[j].y;
+                    f[4 * j + 2] += b4[j].z;
+                    f[4 * j + 3] += b4[j].w;
+                  }
                 } else {
-                  f[j4 * 8 + q * 2] += x.x;
-                  f[j4 * 8 + q * 2 + 1] += x.y;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (col + j < p.N) f[j] += __ldg(bias + col + j);
+                }
+              }
+              if (ACT == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+              }
+              if (p.residual != nullptr && row_ok) {
+                if (full_slice) {
+#pragma unroll
+                  for (int j4 = 0; j4 < 2; ++j4) {
+                    const uint32_t w[4] = {r4[j4].x, r4[j4].y, r4[j4].z, r4[j4].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float2 x = unpack2(w[q], p.fmt);
+                      if (ACT == 2) {
+                        f[j4 * 8 + q * 2] *= gelu_erf_grad(x.x);
+                        f[j4 * 8 + q * 2 + 1] *= gelu_erf_grad(x.y);
+                      } else {
+                        f[j4 * 8 + q * 2] += x.x;
+                        f[j4 * 8 + q * 2 + 1] += x.y;
+                      }
+                    }
+                  }
+                } else {
+                  const uint16_t* r16 = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col;
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    if (col + j < p.N) {
+                      const float x = unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
+                      if (ACT == 2) f[j] *= gelu_erf_grad(x);
+                      else f[j] += x;
+                    }
+                }
+              }
+              // stage the slice into its half of the 32 x 32 box (swizzled exactly as the output tensor map expects)
+              if (OUT_F32) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  *reinterpret_cast<float4*>(buf + lane * 128 + (((hs * 4 + j) ^ (lane & 7)) << 4)) =
+                      make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  uint4 w;
+                  w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
+                  w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
+                  w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
+                  w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
+                  *reinterpret_cast<uint4*>(buf + lane * 64 + (((hs * 2 + j) ^ ((lane >> 1) & 3)) << 4)) = w;
                 }
               }
             }
-          } else {
-            const uint16_t* r16 = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + col;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (col + j < p.N) {
-                const float x = unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
-                if (ACT == 2) f[j] *= gelu_erf_grad(x);
-                else f[j] += x;
+            if (hs == 1) {   // box complete (columns past N, if any, are clipped by the TMA store)
+              ptx::fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                const int bcol = tile_col + bx * 32;
+                if (RED) ptx::tma_reduce_add_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
+                else ptx::tma_store_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
+                ptx::bulk_commit_group();
               }
+              ++nstore;
+            }
           }
-        }
-        // stage the slice into its half of the 32 x 32 box (swizzled exactly as the output tensor map expects)
-        const int hs = sl & 1;
-        if (hs == 0) {
-          buf = OUT_F32 ? staging : staging + (nstore & 1u) * (SM::kStagingPerWarp / 2);
-          if (lane == 0) {
-            if (OUT_F32) ptx::bulk_wait_group_read<0>();
-            else ptx::bulk_wait_group_read<1>();
-          }
-          __syncwarp();
-        }
-        if (OUT_F32) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(buf + lane * 128 + (((hs * 4 + j) ^ (lane & 7)) << 4)) =
-                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 w;
-            w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
-            w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
-            w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
-            w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
-            *reinterpret_cast<uint4*>(buf + lane * 64 + (((hs * 2 + j) ^ ((lane >> 1) & 3)) << 4)) = w;
-          }
-        }
-        if (hs == 1 || sl + 1 == nslices) {   // box complete (or the N edge cuts it short: the TMA store clips)
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            const int bcol = col_base + (sl >> 1) * 32;
-            if (RED) ptx::tma_reduce_add_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
-            else ptx::tma_store_2d(&tmap_out, buf, bcol, m_tile * kBM + quarter * 32);
-            ptx::bulk_commit_group();
-          }
-          ++nstore;
         }
       }
       as ^= 1;
