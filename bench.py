@@ -441,6 +441,37 @@ def run_ours(args):
                 lat[f"graph_equals_eager_batch{qb}"] = same
                 del gr
             online["e2e_latency"] = lat
+    # ---- index-build side of the path: UNITER-base image tower over synthetic region features
+    index_build = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        from lightningdot_b200.bi_encoder import UniterEncoder
+        img_model = UniterEncoder(TowerConfig(vocab_size=synth.VOCAB), project_dim=D)
+        img_model.load_state_dict(synth.random_tower_state("img", seed=43), strict=True)
+        img_model.to(dev).eval()
+        nb_img, regions = 4096, 36
+        ib = {k_: (v.to(dev) if torch.is_tensor(v) else v) for k_, v in synth.image_batch(nb_img, regions, seed=5).items()}
+
+        def encode_images():
+            with torch.no_grad():
+                return img_model(ib["input_ids"], ib["attention_mask"], ib["position_ids"], ib["img_feat"],
+                                 ib["img_pos_feat"], None, ib["gather_index"], need_sequence=False)[1]
+        for _ in range(2):
+            encode_images()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            img_emb = encode_images()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_img = e0.elapsed_time(e1) / 5
+        index_build = {"images_per_s": nb_img / (ms_img * 1e-3), "ms_per_batch": ms_img, "batch_images": nb_img,
+                       "regions": regions, "feat_dim": 2048,
+                       "model_tflops": 6.45e9 * nb_img / (ms_img * 1e-3) / 1e12,
+                       "note": "UniterEncoder.forward on device-resident fp32 region features (36 x 2048 + 7 box "
+                               "coordinates per image), 6.45 GFLOP per image (SURVEY 8); a 1M-image index = "
+                               f"{1e6 / (nb_img / (ms_img * 1e-3)):.1f} s on one GPU"}
+        del img_model, ib, img_emb
     barrier()
 
     if rank != 0:
@@ -486,6 +517,7 @@ def run_ours(args):
         "roofline": roofline,
         "roofline_search": roof_search,
         "roofline_online": online,
+        "index_build": index_build,
         "kernel_shares": shares,
         "parity": {"recall_planted": recall, "scores_sorted": sorted_ok, "flagged_queries_last_step": int(flagged),
                    "certificate": cert},

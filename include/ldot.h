@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LDOT_ABI_VERSION 3
+#define LDOT_ABI_VERSION 4
 
 #define LDOT_OK 0
 #define LDOT_ERR_ARG (-1)
@@ -128,6 +128,14 @@ int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_
 int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
                    int32_t heads, int32_t q_rows, int32_t dtype, void* stream);
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream);
+/* Training-mode dropout of the towers (bi_encoder.py:97-99 -> hidden_dropout_prob, attention_probs_dropout_prob): masks
+ * are a counter-based function of (seed, site, element index) - csrc/dropout.cuh - regenerated by the backward kernels.
+ * ldot_attention_train  ldot_attention (q_rows = S) with dropout of the attention probabilities (layer.py:93)
+ * ldot_dropout          d_out = dropout(d_x) (+ d_res): 16-bit [rows, cols], row pitch ld, in place allowed (layer.py:113,154) */
+int ldot_attention_train(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
+                         int32_t heads, float drop_p, uint64_t seed, int32_t site, int32_t dtype, void* stream);
+int ldot_dropout(const void* d_x, const void* d_res, void* d_out, int64_t rows, int32_t cols, int64_t ld, float p,
+                 uint64_t seed, int32_t site, int32_t dtype, void* stream);
 
 /* ---- in-batch-negative NLL: replaces BiEncoderNllLoss.calc (dvl/models/bi_encoder.py:615-656) -------------------
  * ldot_split16     fp32 [rows, K] -> fp16 [rows, 3 K] hi/lo split, side 0: [hi | lo | hi], side 1: [hi | hi | lo];
@@ -159,7 +167,8 @@ int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap
  *                    d_dxsum != NULL also dxsum[H] += sum_rows dx (the bias gradient of the Linear that produced x).
  *                    *_f32 flags: the tensor is fp32 instead of 16-bit.  H = 256 * {1,2,3,4,6}
  * ldot_attention_bwd d_dqkv [B * S, 3 H] = backward of ldot_attention (q_rows = S) given d_dctx [B * S, H]; the
- *                    probabilities are recomputed from the saved d_qkv, d_ctx is the saved forward output
+ *                    probabilities are recomputed from the saved d_qkv, d_ctx is the saved forward output; drop_p / seed /
+ *                    site = the attention dropout of the matching ldot_attention_train call (0 = none)
  * ldot_gelu / ldot_gelu_bwd      elementwise erf-GELU (16-bit) and dx = dy * GELU'(x); n % 8 == 0
  * ldot_colsum16      d_out[N] += column sums of a 16-bit [rows, N] matrix (bias gradients)
  * ldot_embed_text_sum / ldot_embed_scatter   text-embedding backward (uniter_model/model/model.py:233-246): the fp32
@@ -180,7 +189,8 @@ int ldot_layernorm_bwd(const void* d_dy, int64_t ld_dy, int32_t dy_f32, const vo
                        const float* d_gamma, void* d_dx, int64_t ld_dx, int32_t dx_f32, float* d_dgamma,
                        float* d_dbeta, float* d_dxsum, int64_t rows, int32_t H, int32_t dtype, void* stream);
 int ldot_attention_bwd(const void* d_qkv, const int64_t* d_mask, const void* d_ctx, const void* d_dctx, void* d_dqkv,
-                       int32_t B, int32_t S, int32_t H, int32_t heads, int32_t dtype, void* stream);
+                       int32_t B, int32_t S, int32_t H, int32_t heads, float drop_p, uint64_t seed, int32_t site,
+                       int32_t dtype, void* stream);
 int ldot_gelu(const void* d_x, void* d_out, int64_t n, int32_t dtype, void* stream);
 int ldot_gelu_bwd(const void* d_x, const void* d_dy, void* d_dx, int64_t n, int32_t dtype, void* stream);
 int ldot_colsum16(const void* d_in, int64_t ld, int64_t rows, int32_t N, float* d_out, int32_t dtype, void* stream);

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
 
-ABI_VERSION = 3   # LDOT_ABI_VERSION of include/ldot.h
+ABI_VERSION = 4   # LDOT_ABI_VERSION of include/ldot.h
 COARSE_FP16 = 0
 COARSE_BF16 = 1
 
@@ -79,7 +79,11 @@ SIGNATURES = {
     "ldot_layernorm_bwd": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64,
                                      c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p]),
     "ldot_attention_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
-                                     c_int32, c_void_p]),
+                                     c_float, ctypes.c_uint64, c_int32, c_int32, c_void_p]),
+    "ldot_attention_train": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_float,
+                                       ctypes.c_uint64, c_int32, c_int32, c_void_p]),
+    "ldot_dropout": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int64, c_float, ctypes.c_uint64, c_int32,
+                               c_int32, c_void_p]),
     "ldot_gelu": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "ldot_gelu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "ldot_colsum16": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int32, c_void_p]),

@@ -193,7 +193,6 @@ def _make_proj(hidden, project_dim):
 
 class _TowerBase(nn.Module):
     KIND = None
-    _warned = False
 
     def __init__(self, config, project_dim: int = 0):
         super().__init__()
@@ -256,11 +255,6 @@ class _TowerBase(nn.Module):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def _train_forward(self, kind, inputs):
-        c = self.config
-        if self.training and (c.hidden_dropout_prob > 0 or c.attention_probs_dropout_prob > 0) and not _TowerBase._warned:
-            logger.warning("training forward: dropout (hidden %.2f / attention %.2f) is not applied by the CUDA path; "
-                           "the deterministic network is trained", c.hidden_dropout_prob, c.attention_probs_dropout_prob)
-            _TowerBase._warned = True
         return run_tower_training(self, self.engine(), kind, inputs)
 
 

@@ -199,7 +199,7 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
 #include "encoder_params.h"
 namespace ldot {
 int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows, int fmt,
-                  void* stream);
+                  void* stream, float drop_p = 0.f, unsigned long long seed = 0, int site = 0);
 int layernorm_run(const void* in, long long ld_in, int in_f32, const float* gamma, const float* beta, void* out,
                   long long ld_out, long long rows, int H, int fmt, void* stream);
 int embed_text_run(const long long* ids, const long long* pos_ids, long long pos_batch_stride, const void* word,
@@ -389,6 +389,21 @@ int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_
   return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, q_rows, dtype, stream);
 }
 
+int ldot_attention_train(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
+                         int32_t heads, float drop_p, uint64_t seed, int32_t site, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_qkv && d_mask && d_ctx, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, S, dtype, stream, drop_p,
+                       seed, site);
+}
+
+int ldot_dropout(const void* d_x, const void* d_res, void* d_out, int64_t rows, int32_t cols, int64_t ld, float p,
+                 uint64_t seed, int32_t site, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_x && d_out, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return dropout_run(d_x, d_res, d_out, rows, cols, ld, p, seed, site, dtype, stream);
+}
+
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream) {
   LDOT_REQUIRE(d_in && d_out, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
@@ -431,11 +446,12 @@ int ldot_layernorm_bwd(const void* d_dy, int64_t ld_dy, int32_t dy_f32, const vo
 }
 
 int ldot_attention_bwd(const void* d_qkv, const int64_t* d_mask, const void* d_ctx, const void* d_dctx, void* d_dqkv,
-                       int32_t B, int32_t S, int32_t H, int32_t heads, int32_t dtype, void* stream) {
+                       int32_t B, int32_t S, int32_t H, int32_t heads, float drop_p, uint64_t seed, int32_t site,
+                       int32_t dtype, void* stream) {
   LDOT_REQUIRE(d_qkv && d_mask && d_ctx && d_dctx && d_dqkv, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
   return attention_bwd_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, d_dctx, d_dqkv, B, S, H, heads,
-                           dtype, stream);
+                           dtype, stream, drop_p, seed, site);
 }
 
 int ldot_gelu(const void* d_x, void* d_out, int64_t n, int32_t dtype, void* stream) {

@@ -16,6 +16,7 @@
 #include "encoder_params.h"
 #include "rowops.cuh"
 #include "mma_sync.cuh"
+#include "dropout.cuh"
 
 namespace ldot {
 
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 // last layer of a tower whose caller only reads the [CLS] row (dvl/models/bi_encoder.py:120,188).
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
-                                                              uint16_t* __restrict__ ctx, int S, int H, int q_rows) {
+                                                              uint16_t* __restrict__ ctx, int S, int H, int q_rows,
+                                                              const DropKey drop) {
   extern __shared__ __align__(16) uint16_t att_smem[];
   uint16_t* sQ = att_smem;
   uint16_t* sK = sQ + SPAD * kRowPad;
@@ -246,6 +248,20 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
   sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 1);
   sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
 
+  if (drop.thr != 0) {
+    // attention-probability dropout (training, uniter_model/model/layer.py:93): dropped probabilities leave the P V
+    // product, the survivors' 1 / (1 - p) is folded into the final normalisation
+    const unsigned long long base = (static_cast<unsigned long long>(b) * gridDim.x + head) * S;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = n * 8 + t * 2 + j;
+        if (!drop_keep(drop, (base + qrow0 + g) * S + col)) sc[n][j] = 0.f;
+        if (!drop_keep(drop, (base + qrow0 + g + 8) * S + col)) sc[n][2 + j] = 0.f;
+      }
+    }
+  }
   float o[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
@@ -266,7 +282,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
       mma16816<FMT>(o[2 * d2 + 1], pa, vb[2], vb[3]);
     }
   }
-  const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
+  const float inv0 = drop.inv_keep / sum0, inv1 = drop.inv_keep / sum1;
   // stage this warp's 16 x 64 output in its own (now dead) Q rows, then 16-byte coalesced stores
   __syncwarp();
 #pragma unroll
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
 // ================================================================================================ host side
 template <int FMT>
 static int attention_launch(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows,
-                            cudaStream_t st) {
+                            const DropKey& drop, cudaStream_t st) {
   const int spad = (S + 15) / 16 * 16;
   const dim3 grid(heads, B);
   const size_t smem = static_cast<size_t>(3) * spad * kRowPad * sizeof(uint16_t);
@@ -296,7 +312,7 @@ static int attention_launch(const void* qkv, const long long* mask, void* ctx, i
   case SP: {                                                                                                      \
     auto kern = attention_kernel<SP, FMT>;                                                                        \
     if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), S, H, q_rows);  \
+    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), S, H, q_rows, drop);  \
     break;                                                                                                        \
   }
   switch (spad) {
@@ -317,7 +333,7 @@ static int attention_launch(const void* qkv, const long long* mask, void* ctx, i
 }
 
 int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows, int fmt,
-                  void* stream) {
+                  void* stream, float drop_p, unsigned long long seed, int site) {
   LDOT_REQUIRE(B >= 1 && S >= 1 && S <= 128, "attention: bad shape B=%d S=%d (S <= 128)", B, S);
   LDOT_REQUIRE(q_rows >= 1 && q_rows <= S, "attention: q_rows %d must be in [1, S = %d]", q_rows, S);
   LDOT_REQUIRE(H == heads * kHeadDim && H % 8 == 0, "attention: hidden %d must be heads (%d) x 64", H, heads);
@@ -325,8 +341,10 @@ int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope ks(kKcAttention, st, 4.0 * B * static_cast<double>(q_rows) * S * H,
                  static_cast<double>(B) * (static_cast<double>(S) * H * 4.0 + static_cast<double>(q_rows) * H * 4.0));
-  return fmt == 1 ? attention_launch<1>(qkv, mask, ctx, B, S, H, heads, q_rows, st)
-                  : attention_launch<0>(qkv, mask, ctx, B, S, H, heads, q_rows, st);
+  LDOT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention: dropout probability %f out of [0, 1)", drop_p);
+  const DropKey drop = make_drop_key(drop_p, seed, site);
+  return fmt == 1 ? attention_launch<1>(qkv, mask, ctx, B, S, H, heads, q_rows, drop, st)
+                  : attention_launch<0>(qkv, mask, ctx, B, S, H, heads, q_rows, drop, st);
 }
 
 #define LDOT_NV_DISPATCH(H, CALL)                                   \

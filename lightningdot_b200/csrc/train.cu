@@ -21,6 +21,7 @@
 #include "prof.h"
 #include "rowops.cuh"
 #include "mma_sync.cuh"
+#include "dropout.cuh"
 #include "gelu.cuh"
 #include "train_params.h"
 
@@ -180,7 +181,7 @@ __device__ __forceinline__ uint16_t f2h(float f, int fmt) {
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
                                                                   const uint16_t* __restrict__ dctx, uint16_t* __restrict__ dqkv,
-                                                                  int S, int H) {
+                                                                  int S, int H, const DropKey drop) {
   constexpr int PP = SPAD + 8;          // pitch of the P / dS tiles (odd multiple of 16 B: conflict-free ldmatrix)
   constexpr int NT = SPAD / 8;
   extern __shared__ __align__(16) uint16_t ab_smem[];
@@ -300,12 +301,23 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
     sum1 += __shfl_xor_sync(0xFFFFFFFFu, sum1, 2);
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     float d0 = 0.f, d1 = 0.f;
+    // with attention dropout (mask M, keep scale c): O = (P o M c) V, so dP = (dO V^T) o M c.  mc() regenerates M c of
+    // one element (hashing twice is cheaper than 4 NT live registers)
+    const unsigned long long dbase = (static_cast<unsigned long long>(b) * gridDim.x + head) * S;
+    auto mc = [&](int n, int e) -> float {   // e: 0, 1 = row g; 2, 3 = row g + 8
+      const int col = n * 8 + t * 2 + (e & 1);
+      return drop_keep(drop, (dbase + row0 + g + 8 * (e >> 1)) * S + col) ? drop.inv_keep : 0.f;
+    };
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         sc[n][j] *= inv0;
         sc[n][2 + j] *= inv1;
+        if (drop.thr != 0) {
+          dp[n][j] *= mc(n, j);
+          dp[n][2 + j] *= mc(n, 2 + j);
+        }
         d0 = fmaf(sc[n][j], dp[n][j], d0);
         d1 = fmaf(sc[n][2 + j], dp[n][2 + j], d1);
       }
@@ -320,7 +332,15 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
     for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
-      const uint32_t p_lo = pk2<FMT>(sc[n][0], sc[n][1]), p_hi = pk2<FMT>(sc[n][2], sc[n][3]);
+      // (dV = (P o M c)^T dO reads the DROPPED probabilities)
+      uint32_t p_lo, p_hi;
+      if (drop.thr != 0) {
+        p_lo = pk2<FMT>(sc[n][0] * mc(n, 0), sc[n][1] * mc(n, 1));
+        p_hi = pk2<FMT>(sc[n][2] * mc(n, 2), sc[n][3] * mc(n, 3));
+      } else {
+        p_lo = pk2<FMT>(sc[n][0], sc[n][1]);
+        p_hi = pk2<FMT>(sc[n][2], sc[n][3]);
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         dp[n][j] = sc[n][j] * (dp[n][j] - d0) * 0.125f;
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
 
 template <int FMT>
 static int attention_bwd_launch(const void* qkv, const long long* mask, const void* dctx, void* dqkv, int B, int S, int H,
-                                int heads, cudaStream_t st) {
+                                int heads, const DropKey& drop, cudaStream_t st) {
   const int spad = (S + 15) / 16 * 16;
   const dim3 grid(heads, B);
   const size_t smem = (static_cast<size_t>(4) * spad * kRowPad + static_cast<size_t>(2) * spad * (spad + 8) +
@@ -399,7 +419,7 @@ static int attention_bwd_launch(const void* qkv, const long long* mask, const vo
     auto kern = attention_bwd_kernel<SP, FMT>;                                                                     \
     if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<const uint16_t*>(dctx),  \
-                                      static_cast<uint16_t*>(dqkv), S, H);                                         \
+                                      static_cast<uint16_t*>(dqkv), S, H, drop);                                   \
     break;                                                                                                         \
   }
   switch (spad) {
@@ -420,15 +440,64 @@ static int attention_bwd_launch(const void* qkv, const long long* mask, const vo
 }
 
 int attention_bwd_run(const void* qkv, const long long* mask, const void* ctx, const void* dctx, void* dqkv, int B, int S,
-                      int H, int heads, int fmt, void* stream) {
+                      int H, int heads, int fmt, void* stream, float drop_p, unsigned long long seed, int site) {
   (void)ctx;   // (D_i = dO_i . O_i is evaluated as sum_j P_ij dP_ij from the recomputed probabilities)
   LDOT_REQUIRE(B >= 1 && S >= 1 && S <= 128, "attention_bwd: bad shape B=%d S=%d (S <= 128)", B, S);
   LDOT_REQUIRE(H == heads * kHeadDim, "attention_bwd: hidden %d must be heads (%d) x 64", H, heads);
   LDOT_REQUIRE(B <= 65535, "attention_bwd: batch %d > 65535 (split the batch)", B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope ks(kKcAttention, st, 10.0 * B * static_cast<double>(S) * S * H, static_cast<double>(B) * S * H * 16.0);
-  return fmt == 1 ? attention_bwd_launch<1>(qkv, mask, dctx, dqkv, B, S, H, heads, st)
-                  : attention_bwd_launch<0>(qkv, mask, dctx, dqkv, B, S, H, heads, st);
+  LDOT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention_bwd: dropout probability %f out of [0, 1)", drop_p);
+  const DropKey drop = make_drop_key(drop_p, seed, site);
+  return fmt == 1 ? attention_bwd_launch<1>(qkv, mask, dctx, dqkv, B, S, H, heads, drop, st)
+                  : attention_bwd_launch<0>(qkv, mask, dctx, dqkv, B, S, H, heads, drop, st);
+}
+
+static unsigned flat_grid(long long n_vec) {
+  long long b = (n_vec + 255) / 256;
+  const long long cap = 148 * 16;
+  return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ------------------------------------------------------------------------------------------------ dropout (elementwise)
+// out = dropout(x) (+ res): hidden-state dropout of the towers (layer.py:113,154; model.py:245,272) applied to a 16-bit
+// [rows, cols] matrix (row pitch ld, cols % 8 == 0); the same call masks the gradient in backward (res = null).
+__global__ void __launch_bounds__(256) dropout_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ res,
+                                                      uint16_t* __restrict__ out, long long rows, int cols, long long ld,
+                                                      int fmt, const DropKey drop) {
+  const int c8 = cols / 8;
+  const long long n8 = rows * c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / c8;
+    const int c = static_cast<int>(i - r * c8) * 8;
+    float f[8];
+    ld8(x, r * ld + c, 0, fmt, f);
+    const unsigned long long idx = static_cast<unsigned long long>(r) * cols + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = drop_keep(drop, idx + j) ? f[j] * drop.inv_keep : 0.f;
+    if (res != nullptr) {
+      float g[8];
+      ld8(res, r * ld + c, 0, fmt, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+    st8(out, r * ld + c, 0, fmt, f);
+  }
+}
+
+int dropout_run(const void* x, const void* res, void* out, long long rows, int cols, long long ld, float p,
+                unsigned long long seed, int site, int fmt, void* stream) {
+  LDOT_REQUIRE(rows >= 0 && cols >= 8 && cols % 8 == 0 && ld % 8 == 0 && ld >= cols, "dropout: bad shape rows=%lld cols=%d", rows, cols);
+  LDOT_REQUIRE(p > 0.f && p < 1.f, "dropout: probability %f out of (0, 1)", p);
+  if (rows == 0) return kOk;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KernelScope ks(kKcCast, st, 0.0, static_cast<double>(rows) * cols * (res ? 6.0 : 4.0));
+  dropout_kernel<<<flat_grid(rows * (cols / 8)), 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(res),
+                                                             static_cast<uint16_t*>(out), rows, cols, ld, fmt,
+                                                             make_drop_key(p, seed, site));
+  LDOT_CHECK_LAUNCH();
+  return kOk;
 }
 
 // ------------------------------------------------------------------------------------------------ GELU (elementwise)
@@ -451,11 +520,6 @@ __global__ void __launch_bounds__(256) gelu_kernel(const uint16_t* __restrict__ 
   }
 }
 
-static unsigned flat_grid(long long n_vec) {
-  long long b = (n_vec + 255) / 256;
-  const long long cap = 148 * 16;
-  return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
-}
 
 int gelu_run(const void* x, const void* dy, void* out, long long n, int mode, int fmt, void* stream) {
   LDOT_REQUIRE(n >= 0 && n % 8 == 0, "gelu: element count %lld must be a multiple of 8", n);

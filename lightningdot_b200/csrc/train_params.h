@@ -37,7 +37,9 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
              int epi, int out_f32, int accumulate, void* stream);
 int ln_bwd_run(const LnBwdParams& p, int H, void* stream);
 int attention_bwd_run(const void* qkv, const long long* mask, const void* ctx, const void* dctx, void* dqkv, int B, int S,
-                      int H, int heads, int fmt, void* stream);
+                      int H, int heads, int fmt, void* stream, float drop_p = 0.f, unsigned long long seed = 0, int site = 0);
+int dropout_run(const void* x, const void* res, void* out, long long rows, int cols, long long ld, float p,
+                unsigned long long seed, int site, int fmt, void* stream);
 int gelu_run(const void* x, const void* dy, void* out, long long n, int mode, int fmt, void* stream);
 int colsum16_run(const void* in, long long ld, long long rows, int N, float* out, int fmt, void* stream);
 int embed_text_sum_run(const long long* ids, const long long* pos_ids, long long pos_batch_stride, const void* word,

@@ -15,8 +15,11 @@ dvl/models/bi_encoder.py:589-601).  Here one autograd node per tower call owns t
 Activations and activation gradients are bf16 (fp16 when setup_for_distributed_mode(fp16=True) selected it - without
 loss scaling fp16 gradients underflow, so bf16 is the default and the recommended training dtype); parameter gradients
 are fp32 under the reference's parameter names, so torch optimisers, clip_grad_norm_ and state_dict() keep working.
-Dropout (hidden_dropout_prob / attention_probs_dropout_prob, bi_encoder.py:97-99) is NOT applied by this path yet:
-training runs the deterministic network.
+Dropout (hidden_dropout_prob / attention_probs_dropout_prob, bi_encoder.py:97-99) is applied when the module is in
+train() mode: after the embedding LayerNorm, on the attention probabilities, and on the BertSelfOutput / BertOutput dense
+outputs before the residual add (uniter_model/model/layer.py:93,113,154; model.py:245,272).  Masks are a counter-based
+function of (seed drawn from torch's CPU generator per tower call, site, element index) - csrc/dropout.cuh - so the
+backward kernels regenerate them instead of storing them.  eval() mode (or probabilities 0) runs the deterministic network.
 """
 import torch
 
@@ -26,7 +29,10 @@ from . import _lib
 class _Tape(object):
     """Activations one forward keeps for its backward."""
     __slots__ = ("kind", "B", "S", "Lt", "R", "ids", "pos", "mask", "layers", "h_last", "x0", "x1", "x2", "feat16",
-                 "lin", "box", "h0")
+                 "lin", "box", "h0", "p_hidden", "p_attn", "seed")
+
+
+SITE_EMB = 0x7E0   # dropout site of the embedding output; layer l uses 4 l + {0: probabilities, 1: self-output, 2: output}
 
 
 class _GradSinks(dict):
@@ -76,8 +82,17 @@ class _GradSinks(dict):
 class TowerTrainer(object):
     """Runs a TowerEngine's weights in training mode.  `engine.w` holds the 16-bit copies of the parameters."""
 
-    def __init__(self, engine):
+    def __init__(self, engine, p_hidden=0.0, p_attn=0.0, seed=None):
         self.e = engine
+        self.p_hidden, self.p_attn = float(p_hidden), float(p_attn)
+        if (self.p_hidden > 0 or self.p_attn > 0) and seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # torch's CPU generator: torch.manual_seed reproduces it
+        self.seed = int(seed or 0)
+
+    def _dropout(self, x, out, site, rows, cols, res=None):
+        """out = dropout(x) (+ res) over the first `rows` rows (row pitch = x.stride(0) for all three)."""
+        _lib.check(_lib.load().ldot_dropout(_lib.ptr(x), _lib.ptr(res), _lib.ptr(out), rows, cols, x.stride(0), self.p_hidden,
+                                            self.seed, site, self.e.fmt, _lib.stream_ptr()))
 
     # ------------------------------------------------------------------------------------------------ primitives
     def _gemm(self, a, lda, a_mn, b, ldb, b_mn, out, ldo, M, N, K, bias=None, aux=None, ld_aux=0, epi=0, accumulate=False):
@@ -119,6 +134,10 @@ class TowerTrainer(object):
         T, H, F, dt, dev, w = B * S, e.H, e.ffn, e.dtype, h.device, e.w
         stream = _lib.stream_ptr()
         tape.layers = []
+        tape.p_hidden, tape.p_attn, tape.seed = self.p_hidden, self.p_attn, self.seed
+        ph = self.p_hidden > 0
+        if ph:
+            self._dropout(h, h, SITE_EMB, T, H)
         for i in range(e.layers):
             qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
             ctx = torch.empty((T, H), dtype=dt, device=dev)
@@ -129,12 +148,21 @@ class TowerTrainer(object):
             pre2 = torch.empty((T, H), dtype=dt, device=dev)
             out = torch.empty((T, H), dtype=dt, device=dev)
             e._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
-            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, e.heads, S, e.fmt, stream))
-            e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T, residual=h)
+            _lib.check(lib.ldot_attention_train(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, e.heads, self.p_attn,
+                                                self.seed, 4 * i, e.fmt, stream))
+            if ph:   # dense -> dropout -> + residual (layer.py:111-115)
+                e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T)
+                self._dropout(pre1, pre1, 4 * i + 1, T, H, res=h)
+            else:
+                e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T, residual=h)
             e._layernorm(pre1, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
             e._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, T)
             self._gelu(fpre, f)
-            e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T, residual=a)
+            if ph:
+                e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T)
+                self._dropout(pre2, pre2, 4 * i + 2, T, H, res=a)
+            else:
+                e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T, residual=a)
             e._layernorm(pre2, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out, T, H)
             tape.layers.append((h, qkv, ctx, pre1, a, fpre, f, pre2))
             h = out
@@ -250,6 +278,8 @@ class TowerTrainer(object):
         else:
             d_h.view(B, S, H)[:, 0, :] = d_pooled.to(dt)
 
+        ph = tape.p_hidden > 0
+        self.p_hidden, self.p_attn, self.seed = tape.p_hidden, tape.p_attn, tape.seed   # (the forward's masks)
         for i in reversed(range(e.layers)):
             x, qkv, ctx, pre1, a, fpre, f, pre2 = tape.layers[i]
             p = f"bert.encoder.layer.{i}."
@@ -258,12 +288,20 @@ class TowerTrainer(object):
             g.z(p + "output.LayerNorm.weight", H)
             g.z(p + "output.LayerNorm.bias", H)
             g.z(p + "output.dense.bias", H)
+            # (with hidden dropout the dense output's gradient is the MASKED d_pre2 - its bias gradient cannot come from
+            # the LayerNorm kernel's column sums; the residual branch keeps the unmasked one)
             self._ln_bwd(d_h, pre2, w[f"ln2_g{i}"], d_pre2, g[p + "output.LayerNorm.weight"],
-                         g[p + "output.LayerNorm.bias"], g[p + "output.dense.bias"], T, H)
+                         g[p + "output.LayerNorm.bias"], None if ph else g[p + "output.dense.bias"], T, H)
+            d_o2 = d_pre2
+            if ph:
+                d_o2 = buf(T, H)
+                self._dropout(d_pre2, d_o2, 4 * i + 2, T, H)
+                self._colsum(d_o2, g[p + "output.dense.bias"], T)
             g.z(p + "output.dense.weight", H, F)
-            self._wgrad(d_pre2, f, g[p + "output.dense.weight"], T)
+            self._wgrad(d_o2, f, g[p + "output.dense.weight"], T)
             d_fpre = buf(T, F)
-            self._dgrad(d_pre2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=2)
+            self._dgrad(d_o2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=2)
+            del d_o2
             # BertIntermediate
             g.z(p + "intermediate.dense.weight", F, H)
             g.z(p + "intermediate.dense.bias", F)
@@ -278,15 +316,23 @@ class TowerTrainer(object):
             g.z(p + "attention.output.LayerNorm.bias", H)
             g.z(p + "attention.output.dense.bias", H)
             self._ln_bwd(d_a, pre1, w[f"ln1_g{i}"], d_pre1, g[p + "attention.output.LayerNorm.weight"],
-                         g[p + "attention.output.LayerNorm.bias"], g[p + "attention.output.dense.bias"], T, H)
+                         g[p + "attention.output.LayerNorm.bias"], None if ph else g[p + "attention.output.dense.bias"],
+                         T, H)
+            d_o1 = d_pre1
+            if ph:
+                d_o1 = buf(T, H)
+                self._dropout(d_pre1, d_o1, 4 * i + 1, T, H)
+                self._colsum(d_o1, g[p + "attention.output.dense.bias"], T)
             g.z(p + "attention.output.dense.weight", H, H)
-            self._wgrad(d_pre1, ctx, g[p + "attention.output.dense.weight"], T)
+            self._wgrad(d_o1, ctx, g[p + "attention.output.dense.weight"], T)
             d_ctx = buf(T, H)
-            self._dgrad(d_pre1, w[f"o_w{i}"], d_ctx, T)
+            self._dgrad(d_o1, w[f"o_w{i}"], d_ctx, T)
+            del d_o1
             # self-attention
             d_qkv = buf(T, 3 * H)
             _lib.check(lib.ldot_attention_bwd(_lib.ptr(qkv), _lib.ptr(tape.mask), _lib.ptr(ctx), _lib.ptr(d_ctx),
-                                              _lib.ptr(d_qkv), B, S, H, e.heads, e.fmt, stream))
+                                              _lib.ptr(d_qkv), B, S, H, e.heads, tape.p_attn, tape.seed, 4 * i, e.fmt,
+                                              stream))
             dwqkv = g.z3([p + f"attention.self.{nm}.weight" for nm in ("query", "key", "value")], H, H)
             dbqkv = g.z3([p + f"attention.self.{nm}.bias" for nm in ("query", "key", "value")], H)
             self._wgrad(d_qkv, x, dwqkv, T)
@@ -297,6 +343,8 @@ class TowerTrainer(object):
             d_h = d_x
             tape.layers[i] = None   # release this layer's activations
 
+        if ph:
+            self._dropout(d_h, d_h, SITE_EMB, T, H)
         self._backward_embeddings(tape, d_h, g)
         return g
 
@@ -404,8 +452,12 @@ UNUSED_PARAMETERS = ("bert.pooler.", "bert.img_embeddings.mask_embedding.")
 
 def run_tower_training(module, engine, kind, inputs):
     """module: BertEncoder / UniterEncoder (parameters under the reference names); returns pooled fp32 [B, D] attached
-    to the autograd graph."""
-    trainer = TowerTrainer(engine)
+    to the autograd graph.  Dropout as the module's mode says: train() -> config probabilities, eval() -> none;
+    `module.dropout_seed` (tests) pins the mask seed of the next calls."""
+    c = module.config
+    on = module.training
+    trainer = TowerTrainer(engine, c.hidden_dropout_prob if on else 0.0, c.attention_probs_dropout_prob if on else 0.0,
+                           getattr(module, "dropout_seed", None))
     named = [(n, p) for n, p in module.named_parameters() if not n.startswith(UNUSED_PARAMETERS)]
     names = tuple(n for n, _ in named)
     if kind == "txt":

@@ -41,8 +41,13 @@ def extended_mask(attention_mask, dtype=torch.float32):
     return (1.0 - attention_mask[:, None, None, :].to(dtype)) * -10000.0
 
 
-def bert_layer(h, ext_mask, sd, p, heads):
-    """One post-LN transformer layer; p = 'bert.encoder.layer.{i}.'"""
+def _no_drop(site, x, attention=False):
+    return x
+
+
+def bert_layer(h, ext_mask, sd, p, heads, drop=_no_drop, layer=0):
+    """One post-LN transformer layer; p = 'bert.encoder.layer.{i}.'.  drop(site, x): training-mode dropout hook
+    (layer.py:93,113,154; identity in eval mode), sites 4 * layer + {0: probabilities, 1: self-output, 2: output}."""
     B, S, H = h.shape
     dh = H // heads
 
@@ -53,12 +58,12 @@ def bert_layer(h, ext_mask, sd, p, heads):
     k = split(linear(h, sd, p + "attention.self.key"))
     v = split(linear(h, sd, p + "attention.self.value"))
     scores = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh) + ext_mask
-    probs = torch.softmax(scores, dim=-1)
+    probs = drop(4 * layer, torch.softmax(scores, dim=-1), attention=True)
     ctx = torch.matmul(probs, v).permute(0, 2, 1, 3).contiguous().view(B, S, H)
-    a = layer_norm(linear(ctx, sd, p + "attention.output.dense") + h,
+    a = layer_norm(drop(4 * layer + 1, linear(ctx, sd, p + "attention.output.dense")) + h,
                    sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"])
     i = gelu(linear(a, sd, p + "intermediate.dense"))
-    return layer_norm(linear(i, sd, p + "output.dense") + a,
+    return layer_norm(drop(4 * layer + 2, linear(i, sd, p + "output.dense")) + a,
                       sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"])
 
 
@@ -69,9 +74,9 @@ def num_layers(sd):
     return n
 
 
-def encoder(h, ext_mask, sd, heads=12, collect=None):
+def encoder(h, ext_mask, sd, heads=12, collect=None, drop=_no_drop):
     for i in range(num_layers(sd)):
-        h = bert_layer(h, ext_mask, sd, f"bert.encoder.layer.{i}.", heads)
+        h = bert_layer(h, ext_mask, sd, f"bert.encoder.layer.{i}.", heads, drop, i)
         if collect is not None:
             collect.append(h)
     return h
@@ -100,24 +105,31 @@ def projection_head(pooled, sd):
     return linear(x, sd, "encode_proj.3")
 
 
-def text_tower(sd, input_ids, attention_mask, position_ids, heads=12, collect=None):
-    """-> (sequence_output [B, L, H], pooled [B, D])"""
-    h = text_embeddings(sd, input_ids, position_ids)
+SITE_EMB = 0x7E0   # (oracle/dropout.py)
+
+
+def text_tower(sd, input_ids, attention_mask, position_ids, heads=12, collect=None, drop=_no_drop):
+    """-> (sequence_output [B, L, H], pooled [B, D]).  drop: training-mode dropout hook (identity = eval mode); the
+    embedding dropout of model.py:245 is site SITE_EMB."""
+    h = drop(SITE_EMB, text_embeddings(sd, input_ids, position_ids))
     if collect is not None:
         collect.append(h)
-    h = encoder(h, extended_mask(attention_mask), sd, heads, collect)
+    h = encoder(h, extended_mask(attention_mask), sd, heads, collect, drop)
     return h, projection_head(h[:, 0, :], sd)
 
 
 def image_tower(sd, input_ids, attention_mask, position_ids, img_feat, img_pos_feat, gather_index=None, heads=12,
-                collect=None):
-    """-> (sequence_output [B, 1 + R, H], pooled [B, D])"""
+                collect=None, drop=_no_drop):
+    """-> (sequence_output [B, 1 + R, H], pooled [B, D]).  The reference applies one nn.Dropout to the text embedding and
+    one to the region embeddings (model.py:245,272) before concatenating them; with iid masks that is one dropout over
+    the concatenated [B, 1 + R, H] input, which is how the hook (site SITE_EMB) is applied."""
     t = text_embeddings(sd, input_ids, position_ids)
     r = image_embeddings(sd, img_feat, img_pos_feat)
     h = torch.cat([t, r], dim=1)
     if gather_index is not None:
         h = torch.gather(h, 1, gather_index.unsqueeze(-1).expand(-1, -1, h.shape[-1]))
+    h = drop(SITE_EMB, h)
     if collect is not None:
         collect.append(h)
-    h = encoder(h, extended_mask(attention_mask), sd, heads, collect)
+    h = encoder(h, extended_mask(attention_mask), sd, heads, collect, drop)
     return h, projection_head(h[:, 0, :], sd)

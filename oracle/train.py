@@ -41,15 +41,17 @@ def train_step(sd_txt, sd_img, txt, img):
     return loss.detach(), correct, gt, gi
 
 
-def tower_vjp(kind, sd, batch, upstream):
+def tower_vjp(kind, sd, batch, upstream, drop=None):
     """-> (pooled, {name: grad}) of one tower for a given upstream gradient d(pooled): the vector-Jacobian product the
-    tower's backward computes, isolated from the loss (whose softmax amplifies forward rounding)."""
+    tower's backward computes, isolated from the loss (whose softmax amplifies forward rounding).  drop: training-mode
+    dropout hook (oracle/dropout.py: Dropper), None = eval mode."""
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    kw = {} if drop is None else {"drop": drop}
     if kind == "txt":
-        _, pooled = towers.text_tower(p, batch["input_ids"], batch["attention_mask"], batch["position_ids"])
+        _, pooled = towers.text_tower(p, batch["input_ids"], batch["attention_mask"], batch["position_ids"], **kw)
     else:
         _, pooled = towers.image_tower(p, batch["input_ids"], batch["attention_mask"], batch["position_ids"],
-                                       batch["img_feat"], batch["img_pos_feat"], batch["gather_index"])
+                                       batch["img_feat"], batch["img_pos_feat"], batch["gather_index"], **kw)
     pooled.backward(upstream)
     g = p["bert.embeddings.word_embeddings.weight"].grad
     if g is not None:

@@ -30,7 +30,7 @@ def test_binding_covers_header():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 4
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = lib.ldot_topk_merge(None, None, 2, 4, 10, None, None, None)
     assert rc == -1

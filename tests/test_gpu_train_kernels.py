@@ -3,6 +3,7 @@ the tcgen05 GEMM in its backward forms (MN-major operands, split-K accumulation,
 attention / GELU backward, bias column sums, embedding backward pieces, NLL backward, AdamW."""
 import math
 
+import numpy as np
 import pytest
 import torch
 
@@ -143,10 +144,70 @@ def test_attention_bwd(cuda_lib, B, S, fmt):
     _lib.check(cuda_lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, heads, S, fmt, _lib.stream_ptr()))
     dqkv = torch.full((B * S, 3 * H), float("nan"), device="cuda", dtype=DT[fmt])
     _lib.check(cuda_lib.ldot_attention_bwd(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), _lib.ptr(dctx), _lib.ptr(dqkv), B, S,
-                                           H, heads, fmt, _lib.stream_ptr()))
+                                           H, heads, 0.0, 0, 0, fmt, _lib.stream_ptr()))
     x = qkv.double().requires_grad_(True)
     attention_ref(x, mask, B, S, H, heads).backward(dctx.double())
     tol = dict(atol=2e-2, rtol=3e-2) if fmt == 1 else dict(atol=3e-3, rtol=4e-3)
+    torch.testing.assert_close(dqkv.double(), x.grad, **tol)
+
+
+# ----------------------------------------------------------------------------------------------------------- dropout
+@pytest.mark.parametrize("rows,cols,p", [(37, 768, 0.1), (1000, 3072, 0.25), (3, 8, 0.5)])
+def test_dropout_kernel_matches_oracle_mask(cuda_lib, rows, cols, p):
+    """ldot_dropout against the CPU restatement of the mask function (oracle/dropout.py): the SAME elements are dropped,
+    survivors are scaled by 1 / (1 - p), the residual is added after; the keep rate is 1 - p."""
+    from oracle import dropout as odrop
+    g = gen(21)
+    seed, site = 0x1234_5678_9ABC, 9
+    x = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    res = torch.randn(rows, cols, device="cuda", generator=g).to(torch.bfloat16)
+    out = torch.empty_like(x)
+    _lib.check(cuda_lib.ldot_dropout(_lib.ptr(x), _lib.ptr(res), _lib.ptr(out), rows, cols, cols, p, seed, site, 1,
+                                     _lib.stream_ptr()))
+    keep = odrop.keep_mask((rows, cols), p, seed, site)
+    want = (x.float().cpu() * keep / (1.0 - float(np.float32(p))) + res.float().cpu()).to(torch.bfloat16)
+    torch.testing.assert_close(out.cpu().float(), want.float(), atol=0, rtol=2 ** -7)
+    if rows * cols > 10000:
+        assert abs(keep.float().mean().item() - (1 - p)) < 4 * (p * (1 - p) / (rows * cols)) ** 0.5 + 1e-3
+    # masks of different sites / seeds are different functions
+    assert not torch.equal(keep, odrop.keep_mask((rows, cols), p, seed, site + 1)) or rows * cols < 64
+    # in place, no residual (the gradient-masking call of the backward)
+    y = x.clone()
+    _lib.check(cuda_lib.ldot_dropout(_lib.ptr(y), None, _lib.ptr(y), rows, cols, cols, p, seed, site, 1, _lib.stream_ptr()))
+    assert (y.cpu() == 0).eq(~keep | (x.cpu() == 0)).all()
+
+
+def attention_ref_drop(qkv, mask, B, S, H, heads, keep, p):
+    q, k, v = qkv.view(B, S, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.to(qkv.dtype))[:, None, None, :] * -10000.0
+    pr = torch.softmax(s, dim=-1) * keep.to(qkv.dtype) / (1.0 - p)
+    return (pr @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+
+
+@pytest.mark.parametrize("B,S", [(3, 32), (2, 37), (1, 128)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_attention_dropout_fwd_bwd(cuda_lib, B, S, fmt):
+    """ldot_attention_train / ldot_attention_bwd with attention-probability dropout against torch autograd (fp64) over the
+    same mask (uniter_model/model/layer.py:93)."""
+    from oracle import dropout as odrop
+    H, heads, p, seed, site = 768, 12, 0.1, 77, 4
+    g = gen(6)
+    qkv = (torch.randn(B * S, 3 * H, device="cuda", generator=g) * 1.2).to(DT[fmt])
+    dctx = (torch.randn(B * S, H, device="cuda", generator=g) * 0.3).to(DT[fmt])
+    lens = torch.randint(max(1, S // 2), S + 1, (B,), device="cuda", generator=g)
+    mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).to(torch.int64)
+    ctx = torch.empty((B * S, H), device="cuda", dtype=DT[fmt])
+    _lib.check(cuda_lib.ldot_attention_train(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, heads, p, seed, site, fmt,
+                                             _lib.stream_ptr()))
+    dqkv = torch.full((B * S, 3 * H), float("nan"), device="cuda", dtype=DT[fmt])
+    _lib.check(cuda_lib.ldot_attention_bwd(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), _lib.ptr(dctx), _lib.ptr(dqkv), B, S,
+                                           H, heads, p, seed, site, fmt, _lib.stream_ptr()))
+    keep = odrop.keep_mask((B, heads, S, S), p, seed, site).cuda()
+    x = qkv.double().requires_grad_(True)
+    ref = attention_ref_drop(x, mask, B, S, H, heads, keep, float(np.float32(p)))
+    ref.backward(dctx.double())
+    tol = dict(atol=2e-2, rtol=3e-2) if fmt == 1 else dict(atol=3e-3, rtol=4e-3)
+    torch.testing.assert_close(ctx.double(), ref.detach(), **tol)
     torch.testing.assert_close(dqkv.double(), x.grad, **tol)
 
 

@@ -21,6 +21,7 @@ from lightningdot_b200.bi_encoder import (BertEncoder, BiEncoder, BiEncoderNllLo
                                           get_optimizer, get_schedule_linear)
 from lightningdot_b200.training import FusedAdamW
 from lightningdot_b200.utils import _calc_loss
+from oracle import dropout as odrop
 from oracle import train as otrain
 
 pytestmark = pytest.mark.gpu
@@ -31,7 +32,9 @@ def towers(layers, sd_t, sd_i):
     mi = UniterEncoder(TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=layers), project_dim=768)
     mt.load_state_dict(sd_t, strict=True)
     mi.load_state_dict(sd_i, strict=True)
-    return mt.cuda().train(), mi.cuda().train()
+    # eval(): dropout off - the deterministic network the oracle and the reference fixture (eval-mode modules) compute;
+    # gradients are recorded whenever grad mode is on.  Dropout has its own tests below.
+    return mt.cuda().eval(), mi.cuda().eval()
 
 
 def gpu_step(mt, mi, tb, ib, batch):
@@ -100,19 +103,23 @@ def test_train_step_gradients_vs_oracle_and_reference(cuda_lib, golden_dir, dtyp
                 + 2e-4 * top, (tag, n)
 
 
+@pytest.mark.parametrize("drop", [False, True])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("kind", ["txt", "img"])
-def test_tower_backward_vjp_vs_oracle(cuda_lib, dtype, kind):
+def test_tower_backward_vjp_vs_oracle(cuda_lib, dtype, kind, drop):
     """The tower's hand-written backward against torch autograd over the fp32 oracle for the SAME upstream gradient
-    d(pooled): isolates the backward kernels from the loss's conditioning."""
+    d(pooled): isolates the backward kernels from the loss's conditioning.  drop=True: train() mode with
+    hidden_dropout_prob = attention_probs_dropout_prob = 0.1 (bi_encoder.py:97-99) against the oracle applying the same
+    masks (oracle/dropout.py) at the reference's dropout sites."""
     layers, seed, batch = 2, 311, 6
     sd = synth.random_tower_state(kind, seed=seed, perturb=True, layers=layers)
     b = synth.text_batch(batch, 32, seed=seed, ragged=True) if kind == "txt" else synth.image_batch(batch, 36, seed=seed, ragged=True)
     cls = BertEncoder if kind == "txt" else UniterEncoder
     m = cls(TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=layers), project_dim=768)
     m.load_state_dict(sd, strict=True)
-    m = m.cuda().train()
+    m = m.cuda().train() if drop else m.cuda().eval()
     m.compute_dtype = dtype
+    m.dropout_seed = 4242
     up = torch.randn(batch, 768, generator=torch.Generator().manual_seed(seed)) * 0.05
     if kind == "txt":
         _, pooled, _ = m(b["input_ids"], b["attention_mask"], b["position_ids"], need_sequence=False)
@@ -120,7 +127,8 @@ def test_tower_backward_vjp_vs_oracle(cuda_lib, dtype, kind):
         _, pooled, _ = m(b["input_ids"], b["attention_mask"], b["position_ids"], b["img_feat"], b["img_pos_feat"], None,
                          b["gather_index"], need_sequence=False)
     pooled.backward(up.cuda())
-    want_pooled, want = otrain.tower_vjp(kind, sd, b, up)
+    dropper = odrop.Dropper(0.1, 0.1, 4242) if drop else None
+    want_pooled, want = otrain.tower_vjp(kind, sd, b, up, dropper)
     ftol = 2e-2 if dtype == torch.bfloat16 else 3e-3
     assert (pooled.detach().cpu() - want_pooled).norm() <= ftol * want_pooled.norm()
     check_grads(m, want, kind, 0.05 if dtype == torch.bfloat16 else 0.015)
@@ -233,6 +241,7 @@ def test_training_reduces_the_loss_and_refreshes_inference_weights(cuda_lib):
     model = BiEncoder(args, project_dim=768)
     opt = get_optimizer(model, learning_rate=2e-5, weight_decay=0.01)   # built on the host, as train_itm.py does
     model.cuda().train()
+    model.txt_model.dropout_seed, model.img_model.dropout_seed = 5, 6   # train() mode: dropout on, same masks every step
     sched = get_schedule_linear(opt, 2, 100)
     B = 8
     batch = {"txts": synth.text_batch(B, 24, seed=1, ragged=True), "imgs": synth.image_batch(B, 20, seed=2, ragged=True),
@@ -275,6 +284,7 @@ def test_fast_path_matches_plain_path(cuda_lib):
     opt = get_optimizer(model, learning_rate=1e-6, weight_decay=0.01)
     assert isinstance(opt, FusedAdamW)
     model.cuda().train()
+    model.txt_model.dropout_seed, model.img_model.dropout_seed = 5, 6   # (dropout on, masks pinned: backward() repeats)
     B = 8
     batch = {"txts": synth.text_batch(B, 24, seed=1, ragged=True), "imgs": synth.image_batch(B, 20, seed=2, ragged=True),
              "caps": {"input_ids": None}, "sample_size": B, "pos_ctx_indices": list(range(B)), "neg_ctx_indices": []}
