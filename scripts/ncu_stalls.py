@@ -15,6 +15,14 @@ for line in out.splitlines():
         blocks.append(cur)
     elif cur is not None and line.startswith('"'):
         cur["rows"].append(line)
+# (the CSV source page lists every captured launch twice - SASS view and source-correlated view carry the same rows -:
+# collapse exact consecutive duplicates so that block i is launch i of the capture)
+dedup = []
+for blk in blocks:
+    if dedup and dedup[-1]["name"] == blk["name"] and dedup[-1]["rows"] == blk["rows"]:
+        continue
+    dedup.append(blk)
+blocks = dedup
 b = blocks[kidx]
 print(b["name"][:160])
 rows = list(csv.reader(b["rows"]))
