@@ -1,0 +1,111 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[1] and configs[2] on one B200 (the parity-test configurations that are not the bench line).
+
+    python scripts/run_configs.py [cfg2] [cfg3]      -> one JSON line per configuration
+
+cfg2  "1xB200 encode+index": 5 000 images (36 regions x 2048-d) and 25 000 captions (seq_len 32) through the full
+      12-layer towers via eval_model_on_dataloader (dvl/trainer.py:113-190 mirror): encode both sides, in-batch loss,
+      build both indexes, search both directions with top-100, Recall@1/5/10.  Timed end to end (host wall clock, inputs
+      on the host in pinned memory, results as Python dicts - what eval_itm.py gets back).
+cfg3  "MSCOCO-scale": X [123 287, 768], Q [617 000, 768] synthetic embeddings with planted neighbours, exact top-100;
+      device-resident inputs, CUDA events; per-kernel accounting (ldot_prof_*) and Recall@1/5/10 against the planted rows.
+"""
+import json
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from lightningdot_b200 import _lib, synth, trainer  # noqa: E402
+from lightningdot_b200.bi_encoder import BiEncoder, TowerConfig  # noqa: E402
+from lightningdot_b200.indexer import FlatIPIndex  # noqa: E402
+
+
+def cfg2():
+    n_img, cap_per_img, bs, L, R = 5000, 5, 400, 32, 36
+    n_cap = n_img * cap_per_img
+    args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(vocab_size=synth.VOCAB),
+                                 img_checkpoint=None, txt_model_type='bert-base',
+                                 txt_model_config=TowerConfig(vocab_size=synth.VOCAB), txt_checkpoint=None)
+    torch.manual_seed(42)
+    model = BiEncoder(args, project_dim=768).cuda().eval()
+    tb = synth.text_batch(n_cap, L, seed=1, ragged=True)
+    ib = synth.image_batch(n_img, R, seed=2)
+
+    def pin(t):
+        return t.pin_memory() if torch.is_tensor(t) else t
+    batches = []
+    for b0 in range(0, n_cap, bs):
+        rows = torch.arange(b0, min(b0 + bs, n_cap))
+        img_rows = rows // cap_per_img      # the reference's loader repeats the image of every caption
+        txts = {k: (pin(v[rows].contiguous()) if torch.is_tensor(v) and v.shape[0] == n_cap else v) for k, v in tb.items()}
+        imgs = {k: (pin(v[img_rows].contiguous()) if torch.is_tensor(v) and v.shape[0] == n_img else v) for k, v in ib.items()}
+        batches.append({"txts": txts, "imgs": imgs, "caps": {"input_ids": None}, "sample_size": len(rows),
+                        "txt_index": [str(int(j)) for j in rows], "img_fname": [f"img_{int(i):07d}.npz" for i in img_rows]})
+    img2txt = {f"img_{i:07d}.npz": [str(i * cap_per_img + c) for c in range(cap_per_img)] for i in range(n_img)}
+    eargs = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    trainer.eval_model_on_dataloader(model, batches[:2], eargs, img2txt, 100)      # warm-up (kernel attributes, workspaces)
+    torch.cuda.synchronize()
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    t0 = time.perf_counter()
+    loss, acc, _, (r_txt, r_img), (rank_txt, rank_img) = trainer.eval_model_on_dataloader(model, batches, eargs, img2txt, 100)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    _lib.prof_enable(False)
+    prof = _lib.prof_read()
+    kern = {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]}
+    return {"config": "BASELINE configs[1]: 5000 images x 25000 captions, encode + index + search both directions, top-100",
+            "seconds_end_to_end": dt, "captions_per_s": n_cap / dt, "image_encodings": n_cap,
+            "note": "images are re-encoded once per caption, as the reference's eval loader does (SURVEY 3.2)",
+            "loss": loss, "in_batch_acc": acc, "recall_txt2img": r_txt, "recall_img2txt": r_img,
+            "kernel_ms": kern, "kernel_ms_total": round(sum(kern.values()), 1),
+            "ranked_lists": [len(rank_txt), len(rank_img)]}
+
+
+def cfg3():
+    n, nq, d, k = 123287, 617000, 768, 100
+    x = synth.gaussian_index(n, d, seed=42)
+    q, gt = synth.planted_queries(x, nq, sigma=2.0, seed=43)
+    xd, qd, gtd = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda(), torch.from_numpy(gt).cuda()
+    ix = FlatIPIndex(d)
+    ix.add(xd)
+    ix.search_device(qd[:32768], k)
+    torch.cuda.synchronize()
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    scores, labels = ix.search_device(qd, k)
+    e1.record()
+    torch.cuda.synchronize()
+    _lib.prof_enable(False)
+    ms = e0.elapsed_time(e1)
+    prof = _lib.prof_read()
+    c = prof["coarse_score_topk"]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tc = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    hit = labels == gtd[:, None]
+    rec = {str(t): float(hit[:, :t].any(dim=1).float().mean().item()) for t in (1, 5, 10)}
+    # oracle check on a sample: exact ids
+    from oracle import flatip
+    m = 64
+    os_, oi = flatip.search(q[:m], x, k)
+    return {"config": "BASELINE configs[2]: 617000 queries x 123287-row index, exact top-100 (search only)",
+            "ms": ms, "queries_per_s": nq / (ms * 1e-3), "flagged_queries": int(ix.last_flagged),
+            "coarse_ms": c["ms"], "coarse_tflops": c["flops"] / (c["ms"] * 1e-3) / 1e12, "coarse_frac_of_tensor_peak": c["flops"] / (c["ms"] * 1e-3) / 1e12 / tc,
+            "kernel_ms": {k_: round(v["ms"], 2) for k_, v in prof.items() if v["launches"]},
+            "recall_planted": rec, "ids_identical_to_oracle_sample": bool(np.array_equal(labels[:m].cpu().numpy(), oi)),
+            "scores_max_rel_err_sample": float(np.max(np.abs(scores[:m].cpu().numpy() - os_) / np.maximum(np.abs(os_), 1e-30)))}
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["cfg2", "cfg3"]
+    for w in which:
+        print(json.dumps({"cfg2": cfg2, "cfg3": cfg3}[w]()), flush=True)
