@@ -160,35 +160,17 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in,
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// grid (heads, B); block = (SPAD / 16) warps; warp w owns query rows [16 w, 16 w + 16).  Only the first q_rows query
+// One (sequence, head) item: block = (SPAD / 16) warps; warp w owns query rows [16 w, 16 w + 16).  Only the first q_rows query
 // positions of each sequence are computed and written (ctx is [B * q_rows, H]): q_rows = S for a full layer, 1 for the
 // last layer of a tower whose caller only reads the [CLS] row (dvl/models/bi_encoder.py:120,188).
 template <int SPAD, int FMT>
-__global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
-                                                              uint16_t* __restrict__ ctx, int S, int H, int q_rows,
-                                                              const DropKey drop) {
-  extern __shared__ __align__(16) uint16_t att_smem[];
-  uint16_t* sQ = att_smem;
-  uint16_t* sK = sQ + SPAD * kRowPad;
-  uint16_t* sV = sK + SPAD * kRowPad;
-  const int head = blockIdx.x, b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long tok0 = static_cast<long long>(b) * S;
-  const int ld = 3 * H;
-
-  // stage Q, K, V head slices [S, 64] (rows >= S zero-filled): 8 lanes x 16 B per row
-  for (int i = threadIdx.x; i < SPAD * 8 * 3; i += blockDim.x) {
-    const int mat = i / (SPAD * 8), rem = i - mat * SPAD * 8;
-    const int r = rem >> 3, c = (rem & 7) * 8;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < S) v = __ldg(reinterpret_cast<const uint4*>(qkv + (tok0 + r) * ld + mat * H + head * kHeadDim + c));
-    *reinterpret_cast<uint4*>(att_smem + mat * SPAD * kRowPad + r * kRowPad + c) = v;
-  }
-  __syncthreads();
-
+__device__ __forceinline__ void attention_item(uint16_t* sQ, const uint16_t* sK, const uint16_t* sV,
+                                               const long long* smask, uint16_t* __restrict__ ctx, int b,
+                                               int head, int heads, long long tok0, int S, int H, int q_rows,
+                                               const DropKey& drop, int warp, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int qrow0 = warp * 16;
-  if (qrow0 >= q_rows) return;  // (no block-wide synchronisation past this point)
+  if (qrow0 >= q_rows) return;  // (the caller synchronises the block after every item)
   uint32_t qa[4][4];
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) {
@@ -221,7 +203,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
       const int col = n * 8 + t * 2 + j;
       float add;
       if (col >= S) add = -INFINITY;
-      else add = mask[tok0 + col] != 0 ? 0.f : -10000.f;
+      else add = smask[col] != 0 ? 0.f : -10000.f;   // (the sequence's attention_mask row, staged with Q / K / V)
       sc[n][j] = fmaf(sc[n][j], 0.125f, add);
       sc[n][2 + j] = fmaf(sc[n][2 + j], 0.125f, add);
       mx0 = fmaxf(mx0, sc[n][j]);
@@ -251,7 +233,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
   if (drop.thr != 0) {
     // attention-probability dropout (training, uniter_model/model/layer.py:93): dropped probabilities leave the P V
     // product, the survivors' 1 / (1 - p) is folded into the final normalisation
-    const unsigned long long base = (static_cast<unsigned long long>(b) * gridDim.x + head) * S;
+    const unsigned long long base = (static_cast<unsigned long long>(b) * heads + head) * S;
 #pragma unroll
     for (int n = 0; n < NT; ++n) {
 #pragma unroll
@@ -301,18 +283,86 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
   }
 }
 
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
+// PERSISTENT over (sequence, head) items: a grid of resident CTAs strides over the B * heads items with two
+// shared-memory buffers - the Q / K / V head slices of the next item arrive by cp.async while the current item is
+// computed.  (One CTA per item made 120 000 64-thread CTAs per launch at 10 000 captions: launch-rate bound.)
+template <int SPAD, int FMT>
+__global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
+                                                              uint16_t* __restrict__ ctx, int B, int S, int H, int heads,
+                                                              int q_rows, const DropKey drop) {
+  extern __shared__ __align__(16) uint16_t att_smem_all[];
+  constexpr int kBuf = 3 * SPAD * kRowPad + SPAD * 4;   // 16-bit elements per buffer: Q | K | V | int64 mask row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = 3 * H;
+  const int total = B * heads;
+
+  // stage Q, K, V head slices [S, 64] of `item` (rows >= S zero-filled): 8 lanes x 16 B per row
+  auto prefetch = [&](int item, int buf) {
+    const int b_ = item / heads, head_ = item - b_ * heads;
+    const long long tok0_ = static_cast<long long>(b_) * S;
+    uint16_t* dst = att_smem_all + buf * kBuf;
+    for (int i = threadIdx.x; i < SPAD * 8 * 3; i += blockDim.x) {
+      const int mat = i / (SPAD * 8), rem = i - mat * SPAD * 8;
+      const int r = rem >> 3, c = (rem & 7) * 8;
+      const int rs = r < S ? r : S - 1;
+      cp_async16_zfill(dst + mat * SPAD * kRowPad + r * kRowPad + c,
+                       qkv + (tok0_ + rs) * ld + mat * H + head_ * kHeadDim + c, r < S);
+    }
+    if (threadIdx.x < SPAD) {   // attention_mask[b, :] (int64): read right after the score MMAs, so it rides along
+      const int j = threadIdx.x < S ? threadIdx.x : S - 1;
+      const uint32_t dstm = static_cast<uint32_t>(__cvta_generic_to_shared(dst + 3 * SPAD * kRowPad + threadIdx.x * 4));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dstm), "l"(mask + tok0_ + j) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int buf = 0;
+  if (static_cast<int>(blockIdx.x) < total) prefetch(blockIdx.x, 0);
+  for (int item = blockIdx.x; item < total; item += gridDim.x, buf ^= 1) {
+    const int nxt = item + gridDim.x;
+    if (nxt < total) {
+      prefetch(nxt, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int b = item / heads, head = item - b * heads;
+    const long long tok0 = static_cast<long long>(b) * S;
+    uint16_t* sQ = att_smem_all + buf * kBuf;
+    uint16_t* sK = sQ + SPAD * kRowPad;
+    uint16_t* sV = sK + SPAD * kRowPad;
+    attention_item<SPAD, FMT>(sQ, sK, sV, reinterpret_cast<const long long*>(sV + SPAD * kRowPad), ctx, b, head, heads,
+                              tok0, S, H, q_rows, drop, warp, lane);
+    __syncthreads();   // every warp is done with this buffer before the prefetch of item + 2 * gridDim.x lands in it
+  }
+}
+
+
 // ================================================================================================ host side
 template <int FMT>
 static int attention_launch(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows,
                             const DropKey& drop, cudaStream_t st) {
   const int spad = (S + 15) / 16 * 16;
-  const dim3 grid(heads, B);
-  const size_t smem = static_cast<size_t>(3) * spad * kRowPad * sizeof(uint16_t);
+  const size_t smem = static_cast<size_t>(2) * (3 * spad * kRowPad + spad * 4) * sizeof(uint16_t);   // two buffers
+  int sms = 0;
+  if (int e = device_sm_count(&sms)) return e;
+  long long per_sm = (200 * 1024) / static_cast<long long>(smem);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 16 ? 16 : per_sm);
+  const long long items = static_cast<long long>(B) * heads;
+  const unsigned grid = static_cast<unsigned>(items < per_sm * sms ? items : per_sm * sms);
 #define LDOT_ATT_CASE(SP)                                                                                         \
   case SP: {                                                                                                      \
     auto kern = attention_kernel<SP, FMT>;                                                                        \
     if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), S, H, q_rows, drop);  \
+    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), B, S, H, heads, q_rows, drop);  \
     break;                                                                                                        \
   }
   switch (spad) {

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
   uint16_t* sP = sdO + SPAD * kRowPad;
   uint16_t* sdS = sP + SPAD * PP;
   uint16_t* sOut = sdS + SPAD * PP;     // [warps][16][kRowPad] output staging
+  float* sAdd = reinterpret_cast<float*>(sOut + (SPAD / 16) * 16 * kRowPad);   // additive mask per key column
   const int head = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long tok0 = static_cast<long long>(b) * S;
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
     }
     *reinterpret_cast<uint4*>(ab_smem + mat * SPAD * kRowPad + r * kRowPad + c) = v;
   }
+  for (int j = threadIdx.x; j < SPAD; j += blockDim.x)
+    sAdd[j] = j >= S ? -INFINITY : (mask[tok0 + j] != 0 ? 0.f : -10000.f);
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
@@ -270,10 +273,7 @@ __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t*
     for (int n = 0; n < NT; ++n) {
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int col = n * 8 + t * 2 + j;
-        float add;
-        if (col >= S) add = -INFINITY;
-        else add = mask[tok0 + col] != 0 ? 0.f : -10000.f;
+        const float add = sAdd[n * 8 + t * 2 + j];
         sc[n][j] = fmaf(sc[n][j], 0.125f, add);
         sc[n][2 + j] = fmaf(sc[n][2 + j], 0.125f, add);
         mx0 = fmaxf(mx0, sc[n][j]);
@@ -413,7 +413,7 @@ static int attention_bwd_launch(const void* qkv, const long long* mask, const vo
   const int spad = (S + 15) / 16 * 16;
   const dim3 grid(heads, B);
   const size_t smem = (static_cast<size_t>(4) * spad * kRowPad + static_cast<size_t>(2) * spad * (spad + 8) +
-                       static_cast<size_t>(spad / 16) * 16 * kRowPad) * sizeof(uint16_t);
+                       static_cast<size_t>(spad / 16) * 16 * kRowPad) * sizeof(uint16_t) + static_cast<size_t>(spad) * sizeof(float);
 #define LDOT_ATTB_CASE(SP)                                                                                         \
   case SP: {                                                                                                       \
     auto kern = attention_bwd_kernel<SP, FMT>;                                                                     \
