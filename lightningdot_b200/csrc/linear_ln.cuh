@@ -11,8 +11,8 @@
 // same A tile at the same time, so it is served from L2 once), then its eight epilogue warps make TWO passes over
 // the accumulator in TMEM:
 //   pass 1   x = acc + bias + residual  ->  per-row partial (sum x, sum x^2) over the warp's 128 columns, written
-//            into the statistics table of EVERY CTA of the cluster (st.shared::cluster) and signalled with a
-//            cluster-scope mbarrier arrive;
+//            into the statistics table of EVERY CTA of the cluster with st.async, each store signalling the destination
+//            CTA's mbarrier (complete_tx) itself;
 //   pass 2   once all 2 C partials of a row have arrived: mean / rstd, x recomputed from TMEM, normalised, scaled,
 //            packed to 16 bit, staged (swizzled) in shared memory and written with one TMA store per 32 x 32 box.
 // The residual is added BY THE TENSOR CORE: after the K loop the producer streams the [128 x 256] residual tile as four
@@ -92,7 +92,7 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
       ptx::mbar_init(&tempty[i], kLinEpiWarps);
-      ptx::mbar_init(&sbar[i], static_cast<uint32_t>(C * kLinEpiWarps * 32));  // every epilogue lane of every CTA
+      ptx::mbar_init(&sbar[i], 1);  // armed per tile with expect_tx of the C * 8 * 32 partials (8 B each) it will receive
     }
     ptx::fence_mbar_init();
   }
@@ -234,11 +234,13 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       {
         const uint32_t slot = ptx::smem_u32(stats + (as * 2 * kLnMaxCluster + rank * 2 + half) * kBM + row);
         const uint32_t bar = ptx::smem_u32(&sbar[as]);
-        for (int c = 0; c < C; ++c) ptx::st_cluster_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2);
-        ptx::fence_acq_rel_cluster();  // one release fence for all C remote stores, then unordered arrives
-        for (int c = 0; c < C; ++c) ptx::mbar_arrive_cluster_relaxed(ptx::mapa(bar, static_cast<uint32_t>(c)));
+        // st.async: every partial carries its own complete_tx to the destination CTA's barrier - no release fence on
+        // this side, no cluster-scope acquire polling on the other
+        if (warp == 2 && lane == 0) ptx::mbar_arrive_expect_tx(&sbar[as], static_cast<uint32_t>(C * kLinEpiWarps * 32 * 8));
+        for (int c = 0; c < C; ++c)
+          ptx::st_async_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2, ptx::mapa(bar, static_cast<uint32_t>(c)));
       }
-      ptx::mbar_wait_cluster(&sbar[as], aphase);
+      ptx::mbar_wait(&sbar[as], aphase);
       float t1 = 0.f, t2 = 0.f;
       for (int i = 0; i < 2 * C; ++i) {
         const float2 s = stats[(as * 2 * kLnMaxCluster + i) * kBM + row];

@@ -94,6 +94,13 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
 __device__ __forceinline__ void st_cluster_f32x2(uint32_t cluster_addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(cluster_addr), "f"(a), "f"(b) : "memory");
 }
+// 8-byte store into the shared memory of any CTA of the cluster that SIGNALS the destination CTA's mbarrier itself
+// (complete_tx of its 8 bytes): data + notification in one asynchronous operation, so the sender needs no release
+// fence and the receiver - who armed the barrier with expect_tx of the total - waits with a plain CTA-scope try_wait.
+__device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, float b, uint32_t cluster_bar_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "f"(a), "f"(b), "r"(cluster_bar_addr) : "memory");
+}
 // arrive on an mbarrier of any CTA of the cluster; orders this thread's earlier (remote) stores before it
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
