@@ -493,7 +493,7 @@ def run_ours(args):
                 "us_per_launch": 1e3 * v["ms"] / max(1, v["timed"]), "peak_source": peaks["source"] + " (sustained bf16)"}
 
     dominant = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
-    roof_lin = tensor_roof(lin, "linear_tcgen05 (gemm_tc_kernel<EpiStore>)")
+    roof_lin = tensor_roof(lin, "linear_tcgen05 (linear_tc_kernel + linear_ln_kernel)")
     roof_search = tensor_roof(coarse, "coarse_score_topk (coarse_ts_kernel<EpiTopK>)")
     roof_search["queries_per_pass"] = nq
     roofline = roof_lin if dominant == "linear_tcgen05" else roof_search
