@@ -245,7 +245,7 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
     const uint16_t* eye = nullptr;
     if (int e = eye_pointer(fmt, st, &eye)) return e;
     if (int e = make_tmap_kmajor_16b(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, kBM)) return e;
-    if (int e = make_tmap_kmajor_16b(&te, eye, kLinBN, kLinBN, kLinBN * 2, kLinBN)) return e;
+    if (int e = make_tmap_kmajor_16b(&te, eye, kLinBN, kLinBN, kLinBN * 2, kBK)) return e;   // 64 x 64 box: I_64
   }
 
   static bool configured = false;
@@ -280,6 +280,7 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
   s.res_blocks = residual ? kLinBN / kBK : 0;
   s.num_clusters = s.m_tiles < max_clusters[C] ? s.m_tiles : max_clusters[C];
   s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM, kLinBN);
+  s.idesc_res = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM, kBK);
   LnParams p;
   p.bias = bias;
   p.gamma = gamma;

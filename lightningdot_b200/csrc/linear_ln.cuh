@@ -16,7 +16,8 @@
 //   pass 2   once all 2 C partials of a row have arrived: mean / rstd, x recomputed from TMEM, normalised, scaled,
 //            packed to 16 bit, staged (swizzled) in shared memory and written with one TMA store per 32 x 32 box.
 // The residual is added BY THE TENSOR CORE: after the K loop the producer streams the [128 x 256] residual tile as four
-// more K blocks of A against a 256 x 256 identity matrix as B (1.0 * r accumulates exactly in fp32), so it arrives
+// more 64-wide K blocks of A, each multiplied by the 64 x 64 identity into ITS 64 accumulator columns (N = 64 MMAs:
+// 1.0 * r accumulates exactly in fp32; one K-block-equivalent of tensor work for the whole tile), so it arrives
 // through coalesced, prefetched TMA loads instead of per-row loads in the epilogue.
 // Statistics are exact fp32 sums of the fp32 x (nothing is rounded to 16 bit before the normalisation).
 // Warp roles and pipelines are those of linear_tc.cuh (warp 0 TMA, warp 1 MMA, warps 2..9 epilogue).
@@ -32,6 +33,7 @@ struct LnSched {
   int m_tiles, k_blocks, num_clusters, cluster;  // cluster = C
   int res_blocks;                                // 64-column residual blocks appended to the K loop (0 or 4)
   uint32_t idesc;
+  uint32_t idesc_res;                            // 128 x 64 x 16 instruction of the residual blocks
 };
 
 struct LnParams {
@@ -129,17 +131,17 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int m_tile = cluster_id; m_tile < sched.m_tiles; m_tile += sched.num_clusters) {
         for (int kb = 0; kb < sched.k_blocks + sched.res_blocks; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], SM::kStageBytes);
+          ptx::mbar_arrive_expect_tx(&full[stage], kb < sched.k_blocks ? SM::kStageBytes : SM::kABytes + kBK * kBK * 2);
           if (kb < sched.k_blocks) {
             ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_a, &full[stage], kb * kBK, m_tile * kBM,
                              ptx::kEvictNormal);
             ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_w, &full[stage], kb * kBK, rank * kLinBN,
                              ptx::kEvictLast);
-          } else {  // residual block j of this n-tile against block j of the identity
+          } else {  // residual columns [64 j, 64 j + 64) of this n-tile against the 64 x 64 identity
             const int j = kb - sched.k_blocks;
             ptx::tma_load_2d(smem_a + stage * SM::kABytes, &tmap_res, &full[stage], rank * kLinBN + j * kBK,
                              m_tile * kBM, ptx::kEvictNormal);
-            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_eye, &full[stage], j * kBK, 0, ptx::kEvictLast);
+            ptx::tma_load_2d(smem_b + stage * SM::kBBytes, &tmap_eye, &full[stage], 0, 0, ptx::kEvictLast);
           }
           if (++stage == kLinStages) {
             stage = 0;
@@ -165,9 +167,18 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ptx::tc_fence_after();
           const uint64_t adesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_a + stage * SM::kABytes));
           const uint64_t bdesc = ptx::make_smem_desc_sw128(ptx::smem_u32(smem_b + stage * SM::kBBytes));
+          if (kb < sched.k_blocks) {
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k)
-            ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              ptx::mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, sched.idesc, (kb | k) != 0 ? 1u : 0u);
+          } else {
+            // residual block j only touches accumulator columns [64 j, 64 j + 64): a 128 x 64 x 64 product with I_64
+            // (a quarter of the 128 x 256 x 64 it would cost against a 256-column slice of the identity)
+            const uint32_t tmem_dj = tmem_d + static_cast<uint32_t>((kb - sched.k_blocks) * kBK);
+#pragma unroll
+            for (int k = 0; k < kBK / kUmmaK; ++k)
+              ptx::mma_f16_ss(tmem_dj, adesc + 2 * k, bdesc + 2 * k, sched.idesc_res, 1u);
+          }
           ptx::mma_commit(&empty[stage]);
           if (++stage == kLinStages) {
             stage = 0;
