@@ -46,8 +46,8 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--seq-len", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=256, help="queries of the cpu_baseline sample")
-    ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of --impl reference")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="queries of the cpu_baseline sample (~10 s of CPU work)")
+    ap.add_argument("--ref-sample", type=int, default=256, help="queries per step of --impl reference (~1.5 s of CPU work per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -180,8 +180,8 @@ def cpu_text_tower(sd, ids, mask, pos, batch=64):
     return torch.cat(out, 0)
 
 
-def cpu_search_f32(q, x, k, q_block=4096):
-    """faiss IndexFlatIP.search restated for timing: fp32 sgemm over query blocks + top-k (oracle/flatip.py docstring)."""
+def cpu_search_f32(q, x, k, q_block=512):
+    """faiss IndexFlatIP.search restated for timing: fp32 sgemm over 512-query blocks (2 GB of scores at 1M rows) + top-k (oracle/flatip.py docstring)."""
     import torch
     s_out, i_out = [], []
     with torch.no_grad():
