@@ -32,6 +32,10 @@ from lightningdot_b200.utils import _calc_loss  # noqa: E402
 
 
 def main():
+    # stdout carries exactly one JSON line (NCCL prints its version banner there): everything else goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--per-gpu-batch", type=int, default=512)
     ap.add_argument("--seq-len", type=int, default=32)
@@ -110,7 +114,9 @@ def main():
 
     check = None
     if a.check and world > 1:
-        # distributed gradients (averaged over ranks) vs the same global batch on one rank alone
+        # distributed gradients (averaged over ranks) vs the same global batch on one rank alone; eval() mode = dropout
+        # off (the two runs would otherwise draw different masks), gradients are recorded all the same
+        model.eval()
         loss_d = step(model, None, None, batch, largs)
         opt.sync_gradients()
         g_dist = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
@@ -129,7 +135,8 @@ def main():
             num, den = num + d * d, den + w * w
             if w > 0 and d / w > worst[1] and w > 1e-6:
                 worst = (n, d / w)
-        check = {"loss_distributed_mean": loss_mean.item(), "loss_single_process": loss_s.item(),
+        model.train()
+        check = {"dropout": "off for the check (eval mode)", "loss_distributed_mean": loss_mean.item(), "loss_single_process": loss_s.item(),
                  "grad_rel_l2_all_params": (num / den) ** 0.5, "worst_param": worst[0], "worst_param_rel": worst[1]}
         model.zero_grad()
         opt.zero_grad()
@@ -178,7 +185,8 @@ def main():
             "loss_first_last": [losses[0].item(), losses[-1].item()],
             "peak_tflops": peak, "distributed_check": check,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
