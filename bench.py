@@ -281,6 +281,7 @@ def run_ours(args):
     ids_d, mask_d, pos_d = ids_h.to(dev), mask_h.to(dev), pos_h.to(dev)
     qb = shard_bounds(nq, world)
     q_lo, q_hi = qb[rank], qb[rank + 1]
+    q_counts = [qb[r + 1] - qb[r] for r in range(world)]
 
     # ---- index: synthetic gaussian rows + one planted row per query (needs the query embeddings once)
     with torch.no_grad():
@@ -301,7 +302,7 @@ def run_ours(args):
     def step_device():
         with torch.no_grad():
             _, emb, _ = txt_model(ids_d[q_lo:q_hi], mask_d[q_lo:q_hi], pos_d, need_sequence=False)
-            q_all = indexer.gather_queries(emb)
+            q_all = indexer.gather_queries(emb, q_counts)
             return indexer.search_device(q_all, k)
 
     def step_e2e(api="search"):
@@ -312,7 +313,7 @@ def run_ours(args):
             ids = ids_pin[q_lo:q_hi].to(dev, non_blocking=True)
             mask = mask_pin[q_lo:q_hi].to(dev, non_blocking=True)
             _, emb, _ = txt_model(ids, mask, pos_d, need_sequence=False)   # (as BiEncoder.forward calls it)
-            q_all = indexer.gather_queries(emb)
+            q_all = indexer.gather_queries(emb, q_counts)
             return indexer.search(q_all, k) if api == "search" else indexer.search_knn(q_all, k)
 
     # ---- value: device-resident inputs, CUDA events, per-kernel accounting on

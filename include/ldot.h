@@ -81,7 +81,8 @@ int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n,
                       void* stream);
 
 /* Merge the exact top-k lists of `world` index shards (after the NCCL all-gather):
- * d_scores [world, nq, k], d_idx [world, nq, k] (global ids) -> d_out_* [nq, k], same ranking rule.             */
+ * d_scores [world, nq, k], d_idx [world, nq, k] (global ids; every list ranked as ldot_flatip_search returns it:
+ * (score desc, id asc), label -1 entries last) -> d_out_* [nq, k], same ranking rule.                            */
 int ldot_topk_merge(const float* d_scores, const int64_t* d_idx, int32_t world, int64_t nq, int32_t k,
                     float* d_out_scores, int64_t* d_out_idx, void* stream);
 

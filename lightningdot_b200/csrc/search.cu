@@ -699,29 +699,46 @@ __global__ void __launch_bounds__(1024) exact_merge_kernel(const unsigned long l
 // ================================================================================================
 // multi-GPU: merge W shard results (already exact, global ids) into the global top-k, same ranking rule
 // ================================================================================================
+// Every shard list arrives RANKED ((score desc, id asc); label -1 entries at the end), and keys are unique (global ids),
+// so the global rank of entry r of list w is r + sum over the other lists of how many of their entries beat it:
+// W - 1 binary searches per entry in shared memory and one synchronisation, instead of a bitonic sort of all W k keys.
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx,
-                                                    int W, int nq, int k, int pad, float* __restrict__ out_scores,
+                                                    int W, int nq, int k, float* __restrict__ out_scores,
                                                     long long* __restrict__ out_idx) {
-  extern __shared__ unsigned long long mg_keys[];  // [pad]
+  extern __shared__ unsigned long long mg_keys[];  // [W * k]
   const int q = blockIdx.x;
   const int total = W * k;
-  for (int i = threadIdx.x; i < pad; i += blockDim.x) {
-    unsigned long long e = 0ull;
-    if (i < total) {
-      const int w = i / k, r = i - w * k;
-      const size_t o = (static_cast<size_t>(w) * nq + q) * k + r;
-      const long long id = idx[o];
-      if (id >= 0) e = rank_key(scores[o], static_cast<uint32_t>(id));
-    }
-    mg_keys[i] = e;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int w = i / k, r = i - w * k;
+    const size_t o = (static_cast<size_t>(w) * nq + q) * k + r;
+    const long long id = idx[o];
+    mg_keys[i] = id >= 0 ? rank_key(scores[o], static_cast<uint32_t>(id)) : 0ull;
+  }
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {   // (fewer than k valid entries in total: the tail stays empty)
+    out_scores[static_cast<size_t>(q) * k + r] = -FLT_MAX;
+    out_idx[static_cast<size_t>(q) * k + r] = -1ll;
   }
   __syncthreads();
-  block_bitonic_desc(mg_keys, pad);
-  for (int r = threadIdx.x; r < k; r += blockDim.x) {
-    const unsigned long long e = mg_keys[r];
-    const bool ok = e != 0ull;
-    out_scores[static_cast<size_t>(q) * k + r] = ok ? rank_key_score(e) : -FLT_MAX;
-    out_idx[static_cast<size_t>(q) * k + r] = ok ? static_cast<long long>(rank_key_id(e)) : -1ll;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const unsigned long long e = mg_keys[i];
+    if (e == 0ull) continue;
+    const int w = i / k;
+    int pos = i - w * k;
+    for (int w2 = 0; w2 < W && pos < k; ++w2) {
+      if (w2 == w) continue;
+      const unsigned long long* l = mg_keys + w2 * k;
+      int lo = 0, hi = k;   // first position of list w2 whose key is <= e  (= number of its entries that beat e)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (l[mid] > e) lo = mid + 1;
+        else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < k) {
+      out_scores[static_cast<size_t>(q) * k + pos] = rank_key_score(e);
+      out_idx[static_cast<size_t>(q) * k + pos] = static_cast<long long>(rank_key_id(e));
+    }
   }
 }
 
@@ -1202,14 +1219,13 @@ int merge_run(const float* scores, const long long* idx, int W, long long nq, in
               long long* out_idx, void* stream) {
   LDOT_REQUIRE(W >= 1 && W <= 64 && nq >= 0 && k >= 1 && k <= 1024, "bad merge shape W=%d nq=%lld k=%d", W, nq, k);
   if (nq == 0) return kOk;
-  const int pad = next_pow2(W * k);
-  const size_t smem = static_cast<size_t>(pad) * sizeof(unsigned long long);
+  const size_t smem = static_cast<size_t>(W) * k * sizeof(unsigned long long);
   LDOT_REQUIRE(smem <= 200 * 1024, "W*k=%d too large for the merge kernel", W * k);
   LDOT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   {
     KernelScope ks(kKcMerge, static_cast<cudaStream_t>(stream), 0.0, static_cast<double>(nq) * k * 12.0 * (W + 1));
     merge_kernel<<<static_cast<int>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        scores, idx, W, static_cast<int>(nq), k, pad, out_scores, out_idx);
+        scores, idx, W, static_cast<int>(nq), k, out_scores, out_idx);
   }
   LDOT_CHECK_LAUNCH();
   return kOk;

@@ -86,13 +86,22 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         return FlatIPIndex(self.vector_sz, row_offset=row_offset, **self._index_kw)
 
     # -- searching ----------------------------------------------------------------------------------------------
-    def gather_queries(self, local_queries):
+    def gather_queries(self, local_queries, counts=None):
         """Each rank holds a contiguous slice of the query matrix (equal sizes except possibly the last ranks
-        shorter): all-gather -> the full [nq, d] matrix in rank order."""
+        shorter): all-gather -> the full [nq, d] matrix in rank order.  `counts`: rows per rank when the caller knows
+        them (shard_bounds of a known total): skips the count exchange and its host synchronisation, so the search
+        kernels queue up behind the tower without a bubble."""
         if self.world == 1:
             return local_queries
-        counts = self._all_gather_counts(local_queries.shape[0], local_queries.device)
+        if counts is None:
+            counts = self._all_gather_counts(local_queries.shape[0], local_queries.device)
+        elif len(counts) != self.world or counts[self.rank] != local_queries.shape[0]:
+            raise ValueError(f"counts {counts} do not match the local block of {local_queries.shape[0]} rows on rank {self.rank}")
         m = max(counts)
+        if min(counts) == m:   # equal blocks: one collective straight into the result
+            out = local_queries.new_empty((m * self.world, local_queries.shape[1]))
+            dist.all_gather_into_tensor(out, local_queries.contiguous(), group=self.group)
+            return out
         padded = local_queries.new_zeros((m, local_queries.shape[1]))
         padded[:local_queries.shape[0]] = local_queries
         parts = [torch.empty_like(padded) for _ in range(self.world)]
@@ -114,9 +123,9 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         nq = queries.shape[0]
         gs = torch.empty((self.world, nq, k), dtype=torch.float32, device=ls.device)
         gi = torch.empty((self.world, nq, k), dtype=torch.int64, device=ls.device)
-        # lists of views into one [W, nq, k] buffer: NCCL gathers in place, gloo (CPU tests) accepts the same call
-        dist.all_gather(list(gs.unbind(0)), ls.contiguous(), group=self.group)
-        dist.all_gather(list(gi.unbind(0)), li.contiguous(), group=self.group)
+        # one collective each, straight into the [W, nq, k] buffers (gloo in the CPU tests accepts the same calls)
+        dist.all_gather_into_tensor(gs.view(self.world * nq, k), ls.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(gi.view(self.world * nq, k), li.contiguous(), group=self.group)
         return self._merge(gs, gi, k)
 
     def _local_search(self, queries, k):

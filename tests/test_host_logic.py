@@ -184,6 +184,14 @@ def _sharded_worker(rank, world, port, n, nq, k, tmp):
         qb = sharded.shard_bounds(nq, world)
         q_all = ix.gather_queries(torch.from_numpy(q[qb[rank]:qb[rank + 1]]))
         assert np.array_equal(q_all.numpy(), q)
+        # caller-supplied counts (no count exchange / host sync): ragged blocks, and equal blocks in one collective
+        counts = [qb[r + 1] - qb[r] for r in range(world)]
+        assert np.array_equal(ix.gather_queries(torch.from_numpy(q[qb[rank]:qb[rank + 1]]), counts).numpy(), q)
+        even = (nq // world) * world
+        eb = even // world
+        if eb:
+            got = ix.gather_queries(torch.from_numpy(q[rank * eb:(rank + 1) * eb]), [eb] * world)
+            assert np.array_equal(got.numpy(), q[:even])
         res = ix.search_knn(q_all, k)
         os_, oi = flatip.search(q, x, k)
         want = [[ids[j] if j >= 0 else ids[-1] for j in row] for row in oi]
