@@ -43,14 +43,13 @@ __device__ __forceinline__ void st8(void* base, long long idx, int f32, int fmt,
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
 
-// one warp per row, rows strided over the grid; per-lane column partials live in registers, are combined per block in
-// shared memory and leave with one atomicAdd per column per block
+// one warp per row, rows strided over the grid; per-lane column partials live in registers, are laid side by side in
+// shared memory ([warp][3 H], plain stores), summed over the warps column-wise, and leave with one atomicAdd per
+// column per block
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
   constexpr int H = NV * 256;
-  extern __shared__ float ln_red[];   // [3][H]
-  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) ln_red[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float ln_red[];   // [8 warps][3][H]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float ag[NV][8], ab[NV][8], ax[NV][8];
 #pragma unroll
@@ -110,20 +109,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
       st8(p.dx, row * p.ld_dx + (v * 32 + lane) * 8, p.dx_f32, p.fmt, dx);
     }
   }
+  float* mine = ln_red + warp * 3 * H;
 #pragma unroll
-  for (int v = 0; v < NV; ++v)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col = (v * 32 + lane) * 8 + j;
-      atomicAdd(&ln_red[col], ag[v][j]);
-      atomicAdd(&ln_red[H + col], ab[v][j]);
-      atomicAdd(&ln_red[2 * H + col], ax[v][j]);
-    }
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    *reinterpret_cast<float4*>(mine + col) = make_float4(ag[v][0], ag[v][1], ag[v][2], ag[v][3]);
+    *reinterpret_cast<float4*>(mine + col + 4) = make_float4(ag[v][4], ag[v][5], ag[v][6], ag[v][7]);
+    *reinterpret_cast<float4*>(mine + H + col) = make_float4(ab[v][0], ab[v][1], ab[v][2], ab[v][3]);
+    *reinterpret_cast<float4*>(mine + H + col + 4) = make_float4(ab[v][4], ab[v][5], ab[v][6], ab[v][7]);
+    *reinterpret_cast<float4*>(mine + 2 * H + col) = make_float4(ax[v][0], ax[v][1], ax[v][2], ax[v][3]);
+    *reinterpret_cast<float4*>(mine + 2 * H + col + 4) = make_float4(ax[v][4], ax[v][5], ax[v][6], ax[v][7]);
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < H; i += blockDim.x) {
-    atomicAdd(p.dgamma + i, ln_red[i]);
-    atomicAdd(p.dbeta + i, ln_red[H + i]);
-    if (p.dxsum) atomicAdd(p.dxsum + i, ln_red[2 * H + i]);
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ln_red[w * 3 * H + i];
+    if (i < H) atomicAdd(p.dgamma + i, t);
+    else if (i < 2 * H) atomicAdd(p.dbeta + i - H, t);
+    else if (p.dxsum) atomicAdd(p.dxsum + i - 2 * H, t);
   }
 }
 
@@ -139,9 +143,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
 
 static unsigned row_grid(long long rows) {
   long long b = (rows + 7) / 8;
-  // two resident blocks per SM: each block ends with 3 H global atomics, so fewer, longer-running blocks keep the
-  // contention on the H column accumulators low
-  const long long cap = 148 * 2;
+  // three resident blocks per SM (72 KB of partial tables each at H = 768); every block ends with 3 H global atomics
+  const long long cap = 148 * 3;
   return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
@@ -150,8 +153,14 @@ int ln_bwd_run(const LnBwdParams& p, int H, void* stream) {
   LDOT_REQUIRE(p.ld_dy % 8 == 0 && p.ld_x % 8 == 0 && p.ld_dx % 8 == 0, "layernorm_bwd: row pitches must be multiples of 8");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope ks(kKcLayerNorm, st, 0.0, static_cast<double>(p.rows) * H * 6.0);
-  const size_t smem = static_cast<size_t>(3) * H * sizeof(float);
-  LDOT_NV_DISPATCH(H, (ln_bwd_kernel<NV><<<row_grid(p.rows), 256, smem, st>>>(p)))
+  const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
+  LDOT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: hidden size %d too large", H);
+#define LDOT_LNB(NVV) \
+  { static bool cfgd = false; \
+    if (!cfgd) { LDOT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfgd = true; } \
+    ln_bwd_kernel<NVV><<<row_grid(p.rows), 256, smem, st>>>(p); }
+  LDOT_NV_DISPATCH(H, LDOT_LNB(NV))
+#undef LDOT_LNB
   LDOT_CHECK_LAUNCH();
   return kOk;
 }
