@@ -1,5 +1,6 @@
 """Development probe run under gpurun: checks the tcgen05 GEMM and the search pipeline step by step and prints
-diagnostics (not a test, not a benchmark).  Usage: python scripts/gpu_probe.py [gemm] [search] [time]"""
+diagnostics (not a test, not a benchmark).  Usage: python tests/gpu_probe_tool.py [gemm] [search] [time]
+(Lives under tests/ because it runs the oracle as its checker; pytest does not collect it.)"""
 import os
 import sys
 import time
@@ -7,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from lightningdot_b200 import _lib, synth  # noqa: E402
 from lightningdot_b200.indexer import FlatIPIndex  # noqa: E402
 from oracle import flatip  # noqa: E402  (probe only: the oracle is the checker)

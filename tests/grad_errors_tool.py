@@ -1,12 +1,12 @@
 """Per-parameter gradient error of the GPU training step against the CPU oracle (diagnostic).
-python scripts/grad_errors.py [bf16|fp16] [layers]"""
+python tests/grad_errors_tool.py [bf16|fp16] [layers]   (lives under tests/: it runs the oracle as the checker)"""
 import os
 import sys
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from lightningdot_b200 import synth  # noqa: E402
 from oracle import train as otrain  # noqa: E402
 import test_gpu_training as T  # noqa: E402
