@@ -219,6 +219,48 @@ def evalloop_case():
                    "rank_img_top10": {k: list(v[:10]) for k, v in list(rank_img.items())[:20]}}, f)
 
 
+def options_case():
+    """dvl/options.py: what the reference's own parser yields for an empty command line and for its shipped config
+    JSONs (the config files' CONTENT is not stored - only the parsed namespaces, which is the surface to match)."""
+    import argparse
+    from dvl import options as ropt
+    cfg_dir = "/root/reference/config"
+
+    def parser():
+        p = argparse.ArgumentParser()
+        ropt.default_params(p)
+        ropt.add_itm_params(p)
+        ropt.add_logging_params(p)
+        ropt.add_kd_params(p)
+        return p
+    argv = sys.argv
+    out = {}
+    try:
+        sys.argv = ["prog"]
+        out["empty"] = vars(ropt.parse_with_config(parser(), []))
+        for name in ("flickr30k_eval_config.json", "flickr30k_ft_config.json", "coco_ft_config.json", "coco_eval_config.json"):
+            path = os.path.join(cfg_dir, name)
+            out[name] = vars(ropt.parse_with_config(parser(), ["--config", path]))
+            out[name]["config"] = name
+        # a flag given on the command line wins over the JSON value (override_keys looks at sys.argv)
+        sys.argv = ["prog", "--seed=7", "--num_bb", "50"]
+        path = os.path.join(cfg_dir, "flickr30k_eval_config.json")
+        ns = vars(ropt.parse_with_config(parser(), ["--config", path, "--seed=7", "--num_bb", "50"]))
+        ns["config"] = "flickr30k_eval_config.json"
+        out["override"] = ns
+        # map_db_dirs
+        a = types.SimpleNamespace(pretrain_mapping="/mnt/pre", txt_db_mapping="/mnt/db", img_db_mapping=None,
+                                  val_txt_db="/db/val.db", val_img_db="/img/flickr", teacher_checkpoint="/pretrain/x.pt",
+                                  seed=3, train_img_dbs=["/img/a", "/img/b"], train_txt_dbs=["/db/a", "/other/b"])
+        ropt.map_db_dirs(a)
+        out["map_db_dirs"] = vars(a)
+    finally:
+        sys.argv = argv
+    with open(os.path.join(GOLD, "options_surface.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("options surface:", {k: len(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -228,6 +270,7 @@ def main():
     train_case("l2", 2, 201, 6)
     indexer_case()
     evalloop_case()
+    options_case()
     print("golden fixtures written to", GOLD)
 
 

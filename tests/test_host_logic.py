@@ -339,3 +339,54 @@ def test_hard_negative_sampling_logic(tmp_path, monkeypatch):
     assert sorted(s2i[dbs[1]]) == ["b.npz", "c.npz"] and sorted(s2t[dbs[1]]) == ["2", "3", "4"]
     negs = hn.random_hard_neg({"b.npz": "b.npz", "c.npz": "c.npz"}, 1, i2s, s2i)   # (a one-image set would never end)
     assert negs["b.npz"] == ["c.npz"] and negs["c.npz"] == ["b.npz"]
+
+
+def test_options_surface_matches_reference(golden_dir, tmp_path, monkeypatch):
+    """lightningdot_b200/options.py against the namespaces the reference's own dvl/options.py parser produced
+    (tests/golden/options_surface.json, minted by oracle/make_golden.py): every flag, default, type and choice, the
+    --config JSON semantics (file values apply unless the flag is on the command line) and map_db_dirs."""
+    import argparse
+    import json as _json
+    import sys as _sys
+    from lightningdot_b200 import options as opt
+    gold = _json.load(open(os.path.join(golden_dir, "options_surface.json")))
+
+    def parser():
+        p = argparse.ArgumentParser()
+        opt.default_params(p)
+        opt.add_itm_params(p)
+        opt.add_logging_params(p)
+        opt.add_kd_params(p)
+        return p
+    monkeypatch.setattr(_sys, "argv", ["prog"])
+    assert vars(opt.parse_with_config(parser(), [])) == gold["empty"]
+    for name in ("flickr30k_eval_config.json", "flickr30k_ft_config.json", "coco_ft_config.json", "coco_eval_config.json"):
+        want = dict(gold[name])
+        # the config file as the reference ships it, up to keys that equal the defaults: rebuilt from the parsed result
+        cfg = {k: v for k, v in want.items() if k != "config" and (k not in gold["empty"] or gold["empty"][k] != v)}
+        path = tmp_path / name
+        _json.dump(cfg, open(path, "w"))
+        got = vars(opt.parse_with_config(parser(), ["--config", str(path)]))
+        got["config"] = name
+        assert got == want, name
+    # command-line flags win over the file
+    cfg = {"seed": 42, "num_bb": 36, "project_dim": 768, "fp16": True}
+    path = tmp_path / "o.json"
+    _json.dump(cfg, open(path, "w"))
+    monkeypatch.setattr(_sys, "argv", ["prog", "--seed=7", "--num_bb", "50"])
+    got = opt.parse_with_config(parser(), ["--config", str(path), "--seed=7", "--num_bb", "50"])
+    assert (got.seed, got.num_bb, got.project_dim, got.fp16) == (7, 50, 768, True)
+    assert (gold["override"]["seed"], gold["override"]["num_bb"]) == (7, 50)
+    with pytest.raises(SystemExit):
+        parser().parse_args(["--retrieval_mode", "nonsense"])
+    # map_db_dirs
+    a = types.SimpleNamespace(pretrain_mapping="/mnt/pre", txt_db_mapping="/mnt/db", img_db_mapping=None,
+                              val_txt_db="/db/val.db", val_img_db="/img/flickr", teacher_checkpoint="/pretrain/x.pt",
+                              seed=3, train_img_dbs=["/img/a", "/img/b"], train_txt_dbs=["/db/a", "/other/b"])
+    opt.map_db_dirs(a)
+    assert vars(a) == gold["map_db_dirs"]
+    # set_seed / setup_args_gpu on a CPU-only host
+    ns = types.SimpleNamespace(seed=5, n_gpu=0, local_rank=-1, no_cuda=True, fp16=False)
+    opt.set_seed(ns)
+    opt.setup_args_gpu(ns)
+    assert ns.device.type == "cpu" and ns.distributed_world_size == int(os.environ.get("WORLD_SIZE", "1"))
