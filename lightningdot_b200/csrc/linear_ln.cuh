@@ -94,7 +94,9 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
       ptx::mbar_init(&tempty[i], kLinEpiWarps);
-      ptx::mbar_init(&sbar[i], 1);  // armed per tile with expect_tx of the C * 8 * 32 partials (8 B each) it will receive
+      // C > 1: armed per tile with expect_tx of the C * 8 * 32 partials (8 B each) it will receive through st.async;
+      // C == 1 (N <= 256, not a cluster launch): every epilogue lane stores locally and arrives
+      ptx::mbar_init(&sbar[i], C > 1 ? 1u : static_cast<uint32_t>(kLinEpiWarps * 32));
     }
     ptx::fence_mbar_init();
   }
@@ -247,9 +249,14 @@ linear_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t bar = ptx::smem_u32(&sbar[as]);
         // st.async: every partial carries its own complete_tx to the destination CTA's barrier - no release fence on
         // this side, no cluster-scope acquire polling on the other
-        if (warp == 2 && lane == 0) ptx::mbar_arrive_expect_tx(&sbar[as], static_cast<uint32_t>(C * kLinEpiWarps * 32 * 8));
-        for (int c = 0; c < C; ++c)
-          ptx::st_async_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2, ptx::mapa(bar, static_cast<uint32_t>(c)));
+        if (C > 1) {
+          if (warp == 2 && lane == 0) ptx::mbar_arrive_expect_tx(&sbar[as], static_cast<uint32_t>(C * kLinEpiWarps * 32 * 8));
+          for (int c = 0; c < C; ++c)
+            ptx::st_async_f32x2(ptx::mapa(slot, static_cast<uint32_t>(c)), s1, s2, ptx::mapa(bar, static_cast<uint32_t>(c)));
+        } else {
+          stats[(as * 2 * kLnMaxCluster + half) * kBM + row] = make_float2(s1, s2);
+          ptx::mbar_arrive(&sbar[as]);   // (release.cta: orders the store above)
+        }
       }
       ptx::mbar_wait(&sbar[as], aphase);
       float t1 = 0.f, t2 = 0.f;
