@@ -274,3 +274,28 @@ def test_graphed_retriever_matches_eager_path(cuda_lib):
     want = ix.search_knn(e1, k)
     assert res[0][0] == want[0][0]
     np.testing.assert_allclose(res[0][1], want[0][1], rtol=1e-3)
+
+
+def test_prefetch_loader_moves_nested_batches(cuda_lib):
+    """loader.PrefetchLoader (uniter_model/data/loader.py mirror): nested itm_fast_collate batches arrive on the GPU in
+    order, non-tensor members untouched, len() and attribute pass-through as the reference's."""
+    from lightningdot_b200.loader import PrefetchLoader
+
+    class Src(list):
+        tag = "dataset-attr"
+    batches = Src()
+    for i in range(4):
+        tb, ib = synth.text_batch(3, 8, seed=i), synth.image_batch(3, 5, seed=i)
+        tb = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in tb.items()}
+        batches.append({"txts": tb, "imgs": ib, "caps": {"input_ids": None}, "sample_size": 3, "txt_index": ["a", "b", "c"],
+                        "pos_ctx_indices": [0, 1, 2]})
+    pl = PrefetchLoader(batches)
+    assert len(pl) == 4 and pl.tag == "dataset-attr"
+    seen = 0
+    for got, want in zip(pl, batches):
+        assert got["txts"]["input_ids"].is_cuda and got["imgs"]["img_feat"].is_cuda
+        assert torch.equal(got["txts"]["input_ids"].cpu(), want["txts"]["input_ids"])
+        assert torch.equal(got["imgs"]["img_feat"].cpu(), want["imgs"]["img_feat"])
+        assert got["caps"]["input_ids"] is None and got["txt_index"] == ["a", "b", "c"] and got["pos_ctx_indices"] == [0, 1, 2]
+        seen += 1
+    assert seen == 4
