@@ -20,7 +20,6 @@ training backward.
 """
 import json
 import logging
-import math
 import os
 from collections import defaultdict
 from typing import Tuple

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from lightningdot_b200 import _lib, sharded, synth, trainer
-from lightningdot_b200.bi_encoder import BertEncoder, BiEncoder, BiEncoderNllLoss, TowerConfig, UniterEncoder, \
+from lightningdot_b200.bi_encoder import BertEncoder, BiEncoder, BiEncoderNllLoss, TowerConfig, \
     dot_product_scores
 from lightningdot_b200.indexer import DenseFlatIndexer
 from lightningdot_b200.utils import _calc_loss
