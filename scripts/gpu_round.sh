@@ -30,4 +30,10 @@ if [[ "$what" == *ncu* ]]; then
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_ -s 8 -c 4 -f -o gpurun_out/prof_linear \
     python scripts/profile_tower.py 4096 1 > gpurun_out/ncu_linear.out 2>&1; echo "ncu linear rc=$?"
 fi
+if [[ "$what" == *trainprof* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_train.csv \
+    python scripts/bench_train.py --steps 1 --warmup 1 > gpurun_out/launches_train.out 2>&1; echo "train launches rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 14 -c 1 -f -o gpurun_out/prof_attention \
+    python scripts/profile_tower.py 10000 1 > gpurun_out/ncu_attention.out 2>&1; echo "ncu attention rc=$?"
+fi
 ls -la gpurun_out | head -40

@@ -32,8 +32,8 @@ def short(name):
     return re.sub(r"\(.*", "", name).replace("void ", "").strip()[:110]
 
 
-def launches(tag):
-    src = os.path.join(SRC, "launches_bench.csv")
+def launches(tag, name="launches_bench", what="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e"):
+    src = os.path.join(SRC, name + ".csv")
     if not os.path.exists(src):
         return
     with open(src) as f:
@@ -45,11 +45,11 @@ def launches(tag):
         a[0] += 1
         a[1] += float(row["Metric Value"])
     tot = sum(v[1] for v in agg.values())
-    dst = os.path.join(OUT, f"{tag}_launches_bench.csv")
+    dst = os.path.join(OUT, f"{tag}_{name}.csv")
     with open(dst, "w", newline="") as f:
         w = csv.writer(f)
-        w.writerow(["# ncu --metrics gpu__time_duration.sum --clock-control none ... python bench.py --steps 2 --warmup 1 "
-                    "--no-cpu-baseline --no-e2e (cold-cache, serialised: compare SHARES, not absolutes)"])
+        w.writerow([f"# ncu --metrics gpu__time_duration.sum --clock-control none ... {what} "
+                    "(cold-cache, serialised: compare SHARES, not absolutes)"])
         w.writerow(["kernel", "grid", "block", "launches", "total_ms", "mean_us", "share"])
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             w.writerow([k[0], k[1], k[2], v[0], f"{v[1] / 1e6:.3f}", f"{v[1] / v[0] / 1e3:.1f}", f"{v[1] / tot:.4f}"])
@@ -96,11 +96,13 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
+    launches(tag, "launches_train", "python scripts/bench_train.py --steps 1 --warmup 1 (warm-up step included)")
     traffic = {}
     ncu_report(tag, "prof_coarse_10k.ncu-rep", "coarse_score_topk_nq10k", "coarse_score_topk", 0, traffic)
     ncu_report(tag, "prof_coarse_128.ncu-rep", "coarse_score_topk_nq128", "coarse_score_topk_online", 0, traffic)
     for i, nm in enumerate(["linear_qkv", "linear_oproj", "linear_ffn1_gelu", "linear_ffn2", "linear_next"]):
         ncu_report(tag, "prof_linear.ncu-rep", nm, "linear_tcgen05" if nm == "linear_ffn1_gelu" else None, i, traffic)
+    ncu_report(tag, "prof_attention.ncu-rep", "attention_fwd", None, 0, None)
     if traffic:
         with open(os.path.join(OUT, "traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
