@@ -340,3 +340,50 @@ def test_fast_path_matches_plain_path(cuda_lib):
     with torch.no_grad():
         torch.testing.assert_close(model(batch)[0], fresh(batch)[0], rtol=0, atol=0)
         torch.testing.assert_close(model(batch)[1], fresh(batch)[1], rtol=0, atol=0)
+
+
+def test_fp16_training_with_amp_shim(cuda_lib):
+    """train_itm.py's fp16 branch (train_itm.py:252-258) through lightningdot_b200.amp: scaled backward, in-place unscale,
+    clip on amp.master_params, step; an overflowing loss skips the step, halves the scale and leaves the weights alone."""
+    from lightningdot_b200 import amp
+    from lightningdot_b200.bi_encoder import setup_for_distributed_mode
+    args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(num_hidden_layers=2),
+                                 img_checkpoint=None, txt_model_type='bert-base',
+                                 txt_model_config=TowerConfig(num_hidden_layers=2), txt_checkpoint=None)
+    torch.manual_seed(1)
+    model = BiEncoder(args, project_dim=768)
+    opt = get_optimizer(model, learning_rate=2e-5, weight_decay=0.01)
+    model, opt = setup_for_distributed_mode(model, opt, torch.device("cuda"), 1, -1, fp16=True)
+    model.eval()                                        # (deterministic network; gradients are recorded all the same)
+    assert model.txt_model.compute_dtype == torch.float16 and opt.shadow_dtype == torch.float16
+    sched = get_schedule_linear(opt, 1, 100)
+    B = 8
+    batch = {"txts": synth.text_batch(B, 24, seed=1, ragged=True), "imgs": synth.image_batch(B, 20, seed=2, ragged=True),
+             "caps": {"input_ids": None}, "sample_size": B, "pos_ctx_indices": list(range(B)), "neg_ctx_indices": []}
+    largs = types.SimpleNamespace(caption_score_weight=0.0)
+
+    def one_step(poison=False):
+        t, i, _ = model(batch)
+        l1, _, _ = _calc_loss(largs, BiEncoderNllLoss(), i, t, None, batch["pos_ctx_indices"], None)
+        l2, _, _ = _calc_loss(largs, BiEncoderNllLoss(), t, i, None, batch["pos_ctx_indices"], None)
+        loss = 0.5 * l1 + 0.5 * l2
+        if poison:
+            loss = loss * float("inf")
+        with amp.scale_loss(loss, opt) as scaled_loss:
+            scaled_loss.backward()
+        torch.nn.utils.clip_grad_norm_(amp.master_params(opt), 2.0)
+        opt.step()
+        sched.step()
+        model.zero_grad()
+        return float(loss.detach())
+
+    losses = [one_step() for _ in range(10)]
+    sc = opt._amp_scaler
+    assert sc.enabled and sc.skipped == 0 and sc.scale == amp.INIT_SCALE
+    assert losses[-1] < 0.9 * losses[1], losses
+    w = model.txt_model.bert.encoder.layer[0].intermediate.dense.weight
+    before = w.detach().clone()
+    one_step(poison=True)
+    assert sc.skipped == 1 and sc.scale == amp.INIT_SCALE / 2 and torch.equal(w.detach(), before)
+    one_step()
+    assert not torch.equal(w.detach(), before) and torch.isfinite(w).all()
