@@ -299,3 +299,52 @@ def test_prefetch_loader_moves_nested_batches(cuda_lib):
         assert got["caps"]["input_ids"] is None and got["txt_index"] == ["a", "b", "c"] and got["pos_ctx_indices"] == [0, 1, 2]
         seen += 1
     assert seen == 4
+
+
+def test_full_pipeline_recall_vs_oracle_towers(cuda_lib):
+    """BASELINE configs[0] in miniature, end to end: both CUDA towers (fp16, what `fp16: true` of the eval configs selects)
+    -> eval_model_on_dataloader (encode, de-dup, index, two searches, Recall@1/5/10) against the fp32 CPU oracle towers ->
+    oracle eval loop on the same inputs.  Random-init towers give nearly collinear embeddings, so ranks are decided by
+    ~1e-3 relative score differences: the recalls must agree to +-0.01 absolute (they are near chance level anyway), the
+    ranked top-10 lists must overlap by >= 97 % on average and >= 97 % of the top-1 hits must be the same image
+    (measured on B200: recalls 0.006 / 0.052 / 0.104 vs 0.006 / 0.052 / 0.102 text->image, identical image->text;
+    top-10 overlap 0.994 / 0.991; top-1 equal 0.992)."""
+    from oracle import evalloop
+    layers, n_img, cap_per_img, bs, L, R = 4, 100, 5, 50, 24, 20
+    n_cap = n_img * cap_per_img
+    sd_t = synth.random_tower_state("txt", seed=31, perturb=True, layers=layers)
+    sd_i = synth.random_tower_state("img", seed=32, perturb=True, layers=layers)
+    model = _small_biencoder(layers)
+    model.txt_model.load_state_dict(sd_t, strict=True)
+    model.img_model.load_state_dict(sd_i, strict=True)
+    model.cuda().eval()
+    model.txt_model.compute_dtype = model.img_model.compute_dtype = torch.float16
+    tb = synth.text_batch(n_cap, L, seed=7, ragged=True)
+    ib = synth.image_batch(n_img, R, seed=8, ragged=True)
+    txt_ids = [str(j) for j in range(n_cap)]
+    img_ids = [f"img_{j // cap_per_img:07d}.npz" for j in range(n_cap)]
+    img2txt = {f"img_{i:07d}.npz": [str(i * cap_per_img + c) for c in range(cap_per_img)] for i in range(n_img)}
+    batches = []
+    for b0 in range(0, n_cap, bs):
+        rows = torch.arange(b0, b0 + bs)
+        irows = rows // cap_per_img
+        batches.append({"txts": {k: (v[rows] if torch.is_tensor(v) and v.shape[0] == n_cap else v) for k, v in tb.items()},
+                        "imgs": {k: (v[irows] if torch.is_tensor(v) and v.shape[0] == n_img else v) for k, v in ib.items()},
+                        "caps": {"input_ids": None}, "sample_size": bs, "txt_index": txt_ids[b0:b0 + bs],
+                        "img_fname": img_ids[b0:b0 + bs]})
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    _, _, _, (r_txt, r_img), (rank_txt, rank_img) = trainer.eval_model_on_dataloader(model, batches, args, img2txt, 50)
+    with torch.no_grad():
+        _, ot = otowers.text_tower(sd_t, tb["input_ids"], tb["attention_mask"], tb["position_ids"])
+        _, oi = otowers.image_tower(sd_i, ib["input_ids"], ib["attention_mask"], ib["position_ids"], ib["img_feat"],
+                                    ib["img_pos_feat"], ib["gather_index"])
+    o_img = oi.numpy()[np.arange(n_cap) // cap_per_img]
+    or_txt, or_img, orank_txt, orank_img = evalloop.recall_from_embeddings(ot.numpy(), o_img, txt_ids, img_ids, img2txt, 50)
+    ov_txt = np.mean([len(set(rank_txt[q][:10]) & set(orank_txt[q][:10])) / 10 for q in txt_ids])
+    ov_img = np.mean([len(set(rank_img[q][:10]) & set(orank_img[q][:10])) / 10 for q in img2txt])
+    top1 = np.mean([rank_txt[q][0] == orank_txt[q][0] for q in txt_ids])
+    msg = f"recall txt {r_txt} vs {or_txt}; img {r_img} vs {or_img}; top-10 overlap {ov_txt:.3f} / {ov_img:.3f}; top-1 equal {top1:.3f}"
+    print(msg)
+    for k in (1, 5, 10):
+        assert abs(r_txt[k] - or_txt[k]) <= 0.01 and abs(r_img[k] - or_img[k]) <= 0.01, msg
+    assert ov_txt >= 0.97 and ov_img >= 0.97 and top1 >= 0.97, msg
