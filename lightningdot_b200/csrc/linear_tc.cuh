@@ -37,8 +37,9 @@ constexpr int kLinEpiWarps = 8;
 constexpr int kLinThreads = 32 * (2 + kLinEpiWarps);
 // The erf-GELU epilogue (FFN-up: K = 768 behind 3072 output columns) is paced by per-warp instruction latency, not by
 // a pipe: it runs with 16 epilogue warps (4 per scheduler, 96 registers each) and pays for their staging buffers with
-// two pipeline stages.  Measured at 320k tokens: 8 warps 879, 12 warps 1004, 16 warps 1076 TFLOP/s.
-__host__ __device__ constexpr int lin_epi_warps(int act) { return act == 1 ? 16 : 8; }
+// two pipeline stages.  Measured at 320k tokens: 8 warps 879, 12 warps 1004, 16 warps 1076 TFLOP/s.  The GELU' form of
+// the backward (ACT = 2, heavier per element, 128 registers) runs with 12.
+__host__ __device__ constexpr int lin_epi_warps(int act) { return act == 1 ? 16 : act == 2 ? 12 : 8; }
 __host__ __device__ constexpr int lin_threads(int act) { return 32 * (2 + lin_epi_warps(act)); }
 
 struct LinSched {
@@ -73,7 +74,8 @@ struct LinSmemT {
 };
 using LinSmem = LinSmemT<1>;
 static_assert(LinSmemT<1>::kDynamic <= 227 * 1024 && LinSmemT<2>::kDynamic <= 227 * 1024 &&
-              LinSmemT<1, 16>::kDynamic <= 227 * 1024 && LinSmemT<2, 16>::kDynamic <= 227 * 1024, "linear kernel shared memory");
+              LinSmemT<1, 16>::kDynamic <= 227 * 1024 && LinSmemT<2, 16>::kDynamic <= 227 * 1024 &&
+              LinSmemT<1, 12>::kDynamic <= 227 * 1024 && LinSmemT<2, 12>::kDynamic <= 227 * 1024, "linear kernel shared memory");
 
 __device__ __forceinline__ uint32_t pack2(float a, float b, int fmt) {
   if (fmt == 1) {
