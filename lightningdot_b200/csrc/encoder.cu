@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cmath>
+#include <cstdlib>
 #include "host_common.h"
 #include "prof.h"
 #include "encoder_params.h"
@@ -296,7 +297,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
                                                               uint16_t* __restrict__ ctx, int B, int S, int H, int heads,
-                                                              int q_rows, const DropKey drop) {
+                                                              int q_rows, const DropKey drop, int bufs) {
   extern __shared__ __align__(16) uint16_t att_smem_all[];
   constexpr int kBuf = 3 * SPAD * kRowPad + SPAD * 4;   // 16-bit elements per buffer: Q | K | V | int64 mask row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,11 +324,16 @@ __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __r
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
+  // bufs == 2: the next item's slices arrive while this one is computed; bufs == 1: one buffer, twice the resident CTAs
+  // per SM (the loads of other CTAs overlap instead)
   int buf = 0;
-  if (static_cast<int>(blockIdx.x) < total) prefetch(blockIdx.x, 0);
-  for (int item = blockIdx.x; item < total; item += gridDim.x, buf ^= 1) {
+  if (bufs == 2 && static_cast<int>(blockIdx.x) < total) prefetch(blockIdx.x, 0);
+  for (int item = blockIdx.x; item < total; item += gridDim.x, buf ^= (bufs - 1)) {
     const int nxt = item + gridDim.x;
-    if (nxt < total) {
+    if (bufs == 1) {
+      prefetch(item, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (nxt < total) {
       prefetch(nxt, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
@@ -351,7 +357,12 @@ template <int FMT>
 static int attention_launch(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows,
                             const DropKey& drop, cudaStream_t st) {
   const int spad = (S + 15) / 16 * 16;
-  const size_t smem = static_cast<size_t>(2) * (3 * spad * kRowPad + spad * 4) * sizeof(uint16_t);   // two buffers
+  static int bufs = 0;
+  if (bufs == 0) {
+    const char* e = getenv("LDOT_ATT_BUFS");   // (measurement switch; one buffer measured ~4 % faster per clock at L = 32)
+    bufs = e && atoi(e) == 2 ? 2 : 1;
+  }
+  const size_t smem = static_cast<size_t>(bufs) * (3 * spad * kRowPad + spad * 4) * sizeof(uint16_t);
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   long long per_sm = (200 * 1024) / static_cast<long long>(smem);
@@ -362,7 +373,7 @@ static int attention_launch(const void* qkv, const long long* mask, void* ctx, i
   case SP: {                                                                                                      \
     auto kern = attention_kernel<SP, FMT>;                                                                        \
     if (smem > 48 * 1024) LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), B, S, H, heads, q_rows, drop);  \
+    kern<<<grid, SP * 2, smem, st>>>(static_cast<const uint16_t*>(qkv), mask, static_cast<uint16_t*>(ctx), B, S, H, heads, q_rows, drop, bufs);  \
     break;                                                                                                        \
   }
   switch (spad) {
