@@ -258,6 +258,24 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t cta_mask
                ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
 }
+// the same for cta_group::1 kernels inside a cluster: one arrive on the barrier at this shared-memory offset in EVERY CTA
+// of `cta_mask` once the MMAs issued so far have completed (cluster-wide "stage consumed" for multicast TMA rings)
+__device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+// 2-D tiled load that lands at the same shared-memory offset in every CTA of `cta_mask` and completes its bytes on the
+// mbarrier at the same offset in each of them (one L2 read feeds the whole cluster)
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1,
+                                                      uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
+      "h"(cta_mask), "l"(policy)
+      : "memory");
+}
 // TMA load into THIS CTA's shared memory whose completion bytes are credited to an mbarrier that may live in the
 // other CTA of the pair: `cluster_bar_addr` is a shared::cluster address (mapa of the leader's barrier)
 __device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint32_t cluster_bar_addr, int c0,
