@@ -390,3 +390,51 @@ def test_options_surface_matches_reference(golden_dir, tmp_path, monkeypatch):
     opt.set_seed(ns)
     opt.setup_args_gpu(ns)
     assert ns.device.type == "cpu" and ns.distributed_world_size == int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def test_amp_standin_scaler_logic():
+    """lightningdot_b200.amp (stand-in for the apex.amp calls of train_itm.py:252-258): dynamic scale bookkeeping, the
+    identity path for optimisers that do not run fp16 towers, master_params, and the skipped step after an overflow."""
+    from lightningdot_b200 import amp
+    sc = amp.LossScaler(enabled=True)
+    assert sc.scale == amp.INIT_SCALE
+    sc.update(True)
+    assert sc.scale == amp.INIT_SCALE / 2 and sc.skipped == 1
+    for _ in range(amp.GROWTH_INTERVAL):
+        sc.update(False)
+    assert sc.scale == amp.INIT_SCALE
+    off = amp.LossScaler(enabled=False)
+    off.update(True)
+    assert off.scale == 1.0 and off.skipped == 0
+    # plain torch optimiser on the CPU: no fp16 towers -> scale_loss is the identity, nothing is skipped
+    lin = torch.nn.Linear(4, 2)
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    assert [id(p) for p in amp.master_params(opt)] == [id(p) for p in lin.parameters()]
+    model, opt2 = amp.initialize(lin, opt, opt_level="O1")
+    assert model is lin and opt2 is opt and amp.initialize(lin) is lin
+    loss = lin(torch.ones(3, 4)).sum()
+    with amp.scale_loss(loss, opt) as scaled:
+        assert scaled is loss
+        scaled.backward()
+    before = lin.weight.detach().clone()
+    opt.step()
+    assert not torch.equal(lin.weight.detach(), before)
+    # forced fp16 bookkeeping on the CPU: an overflowing gradient zeroes the grads, halves the scale, skips ONE step
+    opt.shadow_dtype = torch.float16
+    opt._amp_scaler = None
+    opt.zero_grad()
+    loss = lin(torch.ones(3, 4)).sum() * float("inf")
+    with amp.scale_loss(loss, opt) as scaled:
+        scaled.backward()
+    assert opt._amp_scaler.skipped == 1 and opt._amp_scaler.scale == amp.INIT_SCALE / 2
+    assert all(not p.grad.any() for p in lin.parameters())
+    before = lin.weight.detach().clone()
+    opt.step()                                   # skipped
+    assert torch.equal(lin.weight.detach(), before)
+    loss = lin(torch.ones(3, 4)).sum()
+    with amp.scale_loss(loss, opt) as scaled:
+        scaled.backward()
+    g = lin.weight.grad.clone()
+    assert torch.allclose(g, torch.full_like(g, 3.0))     # unscaled in place: d/dW of sum over 3 rows of ones
+    opt.step()
+    assert not torch.equal(lin.weight.detach(), before)
