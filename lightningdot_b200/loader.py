@@ -1,73 +1,72 @@
-"""Host-side mirror of uniter_model/data/loader.py's PrefetchLoader (eval_itm.py:16, train_itm.py): wraps a dataloader
-and moves batch i + 1 to the GPU on a side stream while batch i is being computed (uniter_model/data/loader.py:80-160).
+"""Host-side counterpart of uniter_model/data/loader.py's PrefetchLoader (eval_itm.py:16, train_itm.py): wraps a
+dataloader and moves batch i + 1 to the GPU on a side stream while batch i is being computed.
 
-The nested itm_fast_collate batch (dict of dicts / lists / tensors / None, dvl/data/itm.py:203-288) is walked recursively;
-tensors are copied with non_blocking=True (pinned sources overlap with compute) and `record_stream`-ed on the consumer's
-stream when handed out, so the caching allocator does not recycle them while kernels of the main stream still read them -
-the kernels of this package launch on torch's current stream, which is what makes this composition valid.
+The nested itm_fast_collate batch (dict of dicts / lists / tensors / None, dvl/data/itm.py:203-288) is mapped leaf by
+leaf; tensors are copied with non_blocking=True (pinned sources overlap with compute).  Every staged batch carries a CUDA
+event: the consumer's stream waits for that event (not for the whole side stream) and the tensors are `record_stream`-ed
+on it, so the caching allocator does not recycle them while kernels of the main stream still read them - the kernels of
+this package launch on torch's current stream, which is what makes this composition valid.
+Same surface as the reference class: iterate, len(), attribute pass-through to the wrapped loader.
 """
 import torch
 
 
+def _map_tensors(fn, obj):
+    """Apply fn to every tensor leaf of a nest of dicts / lists / tuples; other leaves are returned as they are."""
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map_tensors(fn, v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_map_tensors(fn, v) for v in obj)
+    return obj
+
+
 def move_to_cuda(batch, device=None):
-    if isinstance(batch, torch.Tensor):
-        return batch.cuda(device, non_blocking=True)
-    if isinstance(batch, list):
-        return [move_to_cuda(t, device) for t in batch]
-    if isinstance(batch, tuple):
-        return tuple(move_to_cuda(t, device) for t in batch)
-    if isinstance(batch, dict):
-        return {n: move_to_cuda(t, device) for n, t in batch.items()}
-    return batch
+    return _map_tensors(lambda t: t.cuda(device, non_blocking=True), batch)
 
 
-def record_cuda_stream(batch):
-    if isinstance(batch, torch.Tensor):
-        batch.record_stream(torch.cuda.current_stream())
-    elif isinstance(batch, (list, tuple)):
-        for t in batch:
-            record_cuda_stream(t)
-    elif isinstance(batch, dict):
-        for t in batch.values():
-            record_cuda_stream(t)
+def record_cuda_stream(batch, stream=None):
+    stream = stream if stream is not None else torch.cuda.current_stream()
+
+    def mark(t):
+        if t.is_cuda:
+            t.record_stream(stream)
+        return t
+    _map_tensors(mark, batch)
 
 
 class PrefetchLoader(object):
-    """Same interface and hand-out order as uniter_model/data/loader.py:80-160: iterate, len(), attribute pass-through."""
-
     def __init__(self, loader, device=None):
         self.loader = loader
         self.device = device
         self.stream = torch.cuda.Stream(device=device)
-        self.batch = None
+
+    def _stage(self, it):
+        """Queue the H2D copies of the next batch on the side stream -> (device batch, event) or None at the end."""
+        try:
+            host_batch = next(it)
+        except StopIteration:
+            return None
+        with torch.cuda.stream(self.stream):
+            batch = move_to_cuda(host_batch, self.device)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        return batch, ready
 
     def __iter__(self):
         it = iter(self.loader)
-        self.preload(it)
-        batch = self.next(it)
-        while batch is not None:
+        staged = self._stage(it)
+        while staged is not None:
+            batch, ready = staged
+            consumer = torch.cuda.current_stream(self.device)
+            consumer.wait_event(ready)
+            record_cuda_stream(batch, consumer)
+            staged = self._stage(it)      # the next batch's copies are in flight while this one is consumed
             yield batch
-            batch = self.next(it)
 
     def __len__(self):
         return len(self.loader)
-
-    def preload(self, it):
-        try:
-            self.batch = next(it)
-        except StopIteration:
-            self.batch = None
-            return
-        with torch.cuda.stream(self.stream):
-            self.batch = move_to_cuda(self.batch, self.device)
-
-    def next(self, it):
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        batch = self.batch
-        if batch is not None:
-            record_cuda_stream(batch)
-        self.preload(it)
-        return batch
 
     def __getattr__(self, name):
         return getattr(self.loader, name)
