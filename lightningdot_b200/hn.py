@@ -12,7 +12,6 @@ k <= 1024).  Only the dataset plumbing differs from the reference: its load_data
 databases (lmdb, lz4 - not available here), so the per-dataset dataloaders are passed in.
 """
 import collections
-import itertools
 import json
 import logging
 import os
@@ -25,32 +24,39 @@ logger = logging.getLogger()
 
 
 def random_hard_neg(fname2id, num_hard_negatives, id2set, set2id):
-    """dvl/hn.py:17-27 (num_hard_negatives must be very small: rejection sampling)."""
-    hard_negs = dict()
-    for i in fname2id:
-        while True:
-            hard_neg = random.choices(set2id[id2set[i]], k=num_hard_negatives)
-            if fname2id[i] not in hard_neg:
-                break
-        hard_negs[i] = hard_neg
-    return hard_negs
+    """dvl/hn.py:17-27: for every key, `num_hard_negatives` ids drawn (with replacement) from the key's own dataset,
+    redrawn until the key's own id is not among them (rejection sampling: meant for very small counts)."""
+    out = {}
+    for key, own_id in fname2id.items():
+        pool = set2id[id2set[key]]
+        draw = random.choices(pool, k=num_hard_negatives)
+        while own_id in draw:
+            draw = random.choices(pool, k=num_hard_negatives)
+        out[key] = draw
+    return out
 
 
 def get_img_txt_mappings(train_txt_dbs):
-    """dvl/hn.py:30-44 -> (img2txt, txt2img, img2set, txt2set, set2img, set2txt)."""
-    train_json = []
-    for db_folder in train_txt_dbs:
-        with open(os.path.join(db_folder, 'img2txts.json')) as f:
-            train_json.append(json.load(f))
-    train_img2txt = dict(ChainMap(*train_json))
-    train_txt2img = dict(itertools.chain(*[[(v, k) for v in vals] for k, vals in train_img2txt.items()]))
-    train_img2set = dict(ChainMap(*[{k: v for k in tj} for tj, v in zip(train_json, train_txt_dbs)]))
-    train_txt2set = {txt_id: train_img2set[img_id] for txt_id, img_id in train_txt2img.items()}
-    train_set2img, train_set2txt = collections.defaultdict(list), collections.defaultdict(list)
-    for img_id, set_id in train_img2set.items():
-        train_set2img[set_id].append(img_id)
-        train_set2txt[set_id] += train_img2txt[img_id]
-    return train_img2txt, train_txt2img, train_img2set, train_txt2set, train_set2img, train_set2txt
+    """dvl/hn.py:30-44 -> (img2txt, txt2img, img2set, txt2set, set2img, set2txt) from the img2txts.json of every text
+    database folder.  When an image appears in several folders the FIRST folder wins (ChainMap lookup order), and the
+    per-dataset lists follow that resolved assignment."""
+    per_db = []
+    for folder in train_txt_dbs:
+        with open(os.path.join(folder, 'img2txts.json')) as f:
+            per_db.append(json.load(f))
+    img2txt, img2set = {}, {}
+    for folder, mapping in reversed(list(zip(train_txt_dbs, per_db))):   # later folders first, earlier ones overwrite
+        for img, txts in mapping.items():
+            img2txt[img] = txts
+            img2set[img] = folder
+    # (dict(ChainMap(...)) iterates the maps from the last to the first: reproduce that key order)
+    txt2img = {t: img for img, txts in img2txt.items() for t in txts}
+    txt2set = {t: img2set[img] for t, img in txt2img.items()}
+    set2img, set2txt = collections.defaultdict(list), collections.defaultdict(list)
+    for img, folder in img2set.items():
+        set2img[folder].append(img)
+        set2txt[folder].extend(img2txt[img])
+    return img2txt, txt2img, img2set, txt2set, set2img, set2txt
 
 
 def num_hard_sampled(num_hard_negatives):

@@ -337,6 +337,16 @@ def test_hard_negative_sampling_logic(tmp_path, monkeypatch):
     i2t, t2i, i2s, t2s, s2i, s2t = hn.get_img_txt_mappings(dbs)
     assert i2t == img2txt and t2i == txt2img and i2s["c.npz"] == dbs[1] and t2s["1"] == dbs[0]
     assert sorted(s2i[dbs[1]]) == ["b.npz", "c.npz"] and sorted(s2t[dbs[1]]) == ["2", "3", "4"]
+    # an image listed by two folders belongs to the FIRST one (the reference resolves through a ChainMap); expected values
+    # below were produced by the reference's own get_img_txt_mappings on the same files
+    for name, part in (("e0", {"a": ["0", "1"], "b": ["2"]}), ("e1", {"b": ["9"], "c": ["3", "4"]}), ("e2", {"d": ["5"]})):
+        os.makedirs(tmp_path / name)
+        _json.dump(part, open(tmp_path / name / "img2txts.json", "w"))
+    e = [str(tmp_path / n) for n in ("e0", "e1", "e2")]
+    m = hn.get_img_txt_mappings(e)
+    assert list(m[0].items()) == [("d", ["5"]), ("b", ["2"]), ("c", ["3", "4"]), ("a", ["0", "1"])]
+    assert m[2] == {"d": e[2], "b": e[0], "c": e[1], "a": e[0]} and "9" not in m[1]
+    assert dict(m[4]) == {e[2]: ["d"], e[0]: ["b", "a"], e[1]: ["c"]} and dict(m[5]) == {e[2]: ["5"], e[0]: ["2", "0", "1"], e[1]: ["3", "4"]}
     negs = hn.random_hard_neg({"b.npz": "b.npz", "c.npz": "c.npz"}, 1, i2s, s2i)   # (a one-image set would never end)
     assert negs["b.npz"] == ["c.npz"] and negs["c.npz"] == ["b.npz"]
 
