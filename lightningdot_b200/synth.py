@@ -163,3 +163,61 @@ def planted_queries(x, nq, sigma=1.0, seed=43, scale=1.0):
     noise = rng.standard_normal((nq, d), dtype=np.float32) / np.float32(math.sqrt(d))
     q = (x[gt] + np.float32(sigma) * noise) * np.float32(scale)
     return q.astype(np.float32), gt.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The itm_fast_collate batch (dvl/data/itm.py:203-288) - the input contract of BiEncoder.forward
+# ---------------------------------------------------------------------------------------------------------------
+def itm_samples(batch, seq_len=32, num_bb=36, seed=0, ragged=True):
+    """Per-sample tuples exactly as the reference's ItmFastDataset.__getitem__ hands them to itm_fast_collate
+    (dvl/data/itm.py:68-131): (input_ids [len], img_feat [nbb, 2048], img_pos_feat [nbb, 7], img_input_ids [1],
+    attn_masks_text [len], attn_masks_img [1 + nbb], txt id, image file name, neg_imgs, neg_txts, caption_ids,
+    attn_masks_captions) - un-padded, no hard negatives, no captions.  Caption j belongs to image j // 5."""
+    tb = text_batch(batch, seq_len, seed=seed, ragged=ragged)
+    ib = image_batch(batch, num_bb, seed=seed, ragged=ragged)
+    out = []
+    for j in range(batch):
+        tl = int(tb["attention_mask"][j].sum())
+        nbb = int(ib["attention_mask"][j].sum()) - 1
+        out.append((tb["input_ids"][j, :tl].clone(), ib["img_feat"][j, :nbb].clone(), ib["img_pos_feat"][j, :nbb].clone(),
+                    torch.tensor([101], dtype=torch.long), torch.ones(tl, dtype=torch.long),
+                    torch.ones(nbb + 1, dtype=torch.long), str(j), f"img_{j // 5:07d}.npz", None, None, None, None))
+    return out
+
+
+def itm_batch(batch, seq_len=32, num_bb=36, seed=0, ragged=True):
+    """The nested batch itm_fast_collate builds from itm_samples(...) (same arguments): tensors padded to the longest
+    member of the batch, `position_ids` [1, L], identity `gather_index`, the bookkeeping lists.  Pinned against the
+    reference's own collate function by oracle/make_golden.py (tests/golden/itm_batch_schema.json)."""
+    tb = text_batch(batch, seq_len, seed=seed, ragged=ragged)
+    ib = image_batch(batch, num_bb, seed=seed, ragged=ragged)
+    tl = int(tb["attention_mask"].sum(1).max())
+    nbb = int(ib["attention_mask"].sum(1).max()) - 1
+    none5 = {"img_feat": None, "img_pos_feat": None, "img_masks": None, "gather_index": None}
+    txts = {"input_ids": tb["input_ids"][:, :tl].contiguous(), "position_ids": torch.arange(tl, dtype=torch.long)[None, :],
+            "attention_mask": tb["attention_mask"][:, :tl].contiguous(), **none5}
+    imgs = {"input_ids": ib["input_ids"], "position_ids": torch.zeros(1, 1, dtype=torch.long),
+            "attention_mask": ib["attention_mask"][:, :nbb + 1].contiguous(),
+            "img_feat": ib["img_feat"][:, :nbb].contiguous(), "img_pos_feat": ib["img_pos_feat"][:, :nbb].contiguous(),
+            "img_masks": None, "gather_index": torch.arange(nbb + 1, dtype=torch.long)[None, :].repeat(batch, 1)}
+    caps = {"input_ids": None, "position_ids": None, "attention_mask": None, **none5}
+    return {"txts": txts, "imgs": imgs, "caps": caps, "sample_size": batch, "pos_ctx_indices": list(range(batch)),
+            "neg_ctx_indices": [], "txt_index": [str(j) for j in range(batch)],
+            "img_fname": [f"img_{j // 5:07d}.npz" for j in range(batch)]}
+
+
+def describe_batch(b):
+    """Structure + content fingerprint of a nested batch: {path: [dtype, shape, sha1 of the bytes] | value}."""
+    import hashlib
+    out = {}
+
+    def walk(prefix, v):
+        if isinstance(v, dict):
+            for k, x in v.items():
+                walk(f"{prefix}.{k}" if prefix else k, x)
+        elif torch.is_tensor(v):
+            out[prefix] = [str(v.dtype), list(v.shape), hashlib.sha1(v.contiguous().numpy().tobytes()).hexdigest()]
+        else:
+            out[prefix] = v
+    walk("", b)
+    return out

@@ -219,6 +219,23 @@ def evalloop_case():
                    "rank_img_top10": {k: list(v[:10]) for k, v in list(rank_img.items())[:20]}}, f)
 
 
+def collate_case():
+    """dvl/data/itm.py:203-288: the reference's own itm_fast_collate on un-padded per-sample tuples; synth.itm_batch must
+    build the identical nested batch (keys, dtypes, shapes, values, bookkeeping lists)."""
+    from dvl.data.itm import itm_fast_collate
+    out = {}
+    for name, kw in (("ragged", dict(batch=7, seq_len=24, num_bb=20, seed=5, ragged=True)),
+                     ("full", dict(batch=4, seq_len=32, num_bb=36, seed=6, ragged=False))):
+        ref = itm_fast_collate(synth.itm_samples(**kw))
+        mine = synth.itm_batch(**kw)
+        d_ref, d_mine = synth.describe_batch(ref), synth.describe_batch(mine)
+        assert d_ref == d_mine, {k: (d_ref.get(k), d_mine.get(k)) for k in set(d_ref) | set(d_mine) if d_ref.get(k) != d_mine.get(k)}
+        out[name] = {"kwargs": kw, "batch": d_ref}
+    with open(os.path.join(GOLD, "itm_batch_schema.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("collate schema:", {k: len(v["batch"]) for k, v in out.items()})
+
+
 def options_case():
     """dvl/options.py: what the reference's own parser yields for an empty command line and for its shipped config
     JSONs (the config files' CONTENT is not stored - only the parsed namespaces, which is the surface to match)."""
@@ -271,6 +288,7 @@ def main():
     indexer_case()
     evalloop_case()
     options_case()
+    collate_case()
     print("golden fixtures written to", GOLD)
 
 

@@ -124,3 +124,23 @@ def test_oracle_train_step_matches_reference_gradients(golden_dir):
             assert abs(g.norm().item() - norm) <= 2e-4 * norm + 1e-6, n
             got = g.reshape(-1)[otrain.sample_index(g.numel())].numpy()
             assert np.abs(got - samples).max() <= 2e-4 * norm + 1e-7, n
+
+
+def test_itm_batch_matches_reference_collate(golden_dir):
+    """SURVEY 8 a1, the input contract: synth.itm_batch builds the nested batch the reference's own itm_fast_collate
+    (dvl/data/itm.py:203-288) built from the same un-padded samples - every key, dtype, shape and byte, and the
+    bookkeeping lists (tests/golden/itm_batch_schema.json, minted by oracle/make_golden.py)."""
+    import json
+    from lightningdot_b200 import synth
+    gold = json.load(open(os.path.join(golden_dir, "itm_batch_schema.json")))
+    for name, case in gold.items():
+        got = synth.describe_batch(synth.itm_batch(**case["kwargs"]))
+        assert got == case["batch"], name
+        assert set(k.split(".")[0] for k in got) == {"txts", "imgs", "caps", "sample_size", "pos_ctx_indices",
+                                                     "neg_ctx_indices", "txt_index", "img_fname"}
+    # the per-sample tuples have the layout ItmFastDataset.__getitem__ produces (12 members, un-padded)
+    s = synth.itm_samples(3, 16, 12, seed=1)
+    assert len(s) == 3 and all(len(t) == 12 for t in s)
+    ids, feat, pos, iid, m_t, m_i = s[0][:6]
+    assert ids[0] == 101 and ids[-1] == 102 and m_t.shape == ids.shape and feat.shape[1] == 2048 and pos.shape[1] == 7
+    assert iid.tolist() == [101] and m_i.shape[0] == feat.shape[0] + 1 and s[0][8] is None
