@@ -448,3 +448,50 @@ def test_amp_standin_scaler_logic():
     assert torch.allclose(g, torch.full_like(g, 3.0))     # unscaled in place: d/dW of sum over 3 rows of ones
     opt.step()
     assert not torch.equal(lin.weight.detach(), before)
+
+
+def test_load_biencoder_checkpoint_variants(tmp_path):
+    """dvl/models/bi_encoder.py:737-752 on the mirror: fine-tune checkpoints ({'model_dict': ...}), pre-training
+    checkpoints (every key prefixed with 'bert.', extra heads dropped, strict load), and the 'no checkpoint' spellings."""
+    from lightningdot_b200.bi_encoder import BiEncoder, TowerConfig, load_biencoder_checkpoint
+    args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(num_hidden_layers=1),
+                                 img_checkpoint=None, txt_model_type='bert-base',
+                                 txt_model_config=TowerConfig(num_hidden_layers=1), txt_checkpoint=None)
+    torch.manual_seed(0)
+    src = BiEncoder(args, project_dim=768)
+    sd = {k: v.clone() for k, v in src.state_dict().items()}
+
+    def fresh():
+        torch.manual_seed(1)
+        return BiEncoder(args, project_dim=768)
+
+    def same(model):
+        return all(torch.equal(v, sd[k]) for k, v in model.state_dict().items())
+    # fine-tune checkpoint as trainer._save_checkpoint writes it
+    p1 = str(tmp_path / "ft.pt")
+    torch.save({"model_dict": sd, "optimizer_dict": {}, "scheduler_dict": {}, "offset": 0, "epoch": 1, "encoder_params": None}, p1)
+    m = fresh()
+    assert not same(m)
+    load_biencoder_checkpoint(m, p1)
+    assert same(m)
+    # pre-training checkpoint: 'bert.' + key, plus heads the bi-encoder does not have
+    p2 = str(tmp_path / "pre.pt")
+    pre = {"bert." + k: v for k, v in sd.items()}
+    pre["cls.predictions.bias"] = torch.zeros(3)
+    pre["itm_output.weight"] = torch.zeros(2, 768)
+    torch.save(pre, p2)
+    m = fresh()
+    load_biencoder_checkpoint(m, p2)
+    assert same(m)
+    # a pre-training checkpoint that lacks a tensor fails loudly (strict load)
+    broken = dict(pre)
+    broken.pop("bert.txt_model.encode_proj.3.bias")
+    p3 = str(tmp_path / "broken.pt")
+    torch.save(broken, p3)
+    with pytest.raises(RuntimeError):
+        load_biencoder_checkpoint(fresh(), p3)
+    for none in (None, "", "none", "None"):
+        m = fresh()
+        before = {k: v.clone() for k, v in m.state_dict().items()}
+        load_biencoder_checkpoint(m, none)
+        assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
