@@ -1,0 +1,9 @@
+"""dvl/hn.py: hard-negative mining.
+
+Namesake of the reference module: importing it yields `lightningdot_b200.hn` itself (same object), so every name the
+reference's scripts import from here - private helpers included - is the B200 mirror's."""
+import sys
+
+import lightningdot_b200.hn as _mirror
+
+sys.modules[__name__] = _mirror

@@ -1,0 +1,9 @@
+"""dvl/options.py: command-line / config-JSON surface.
+
+Namesake of the reference module: importing it yields `lightningdot_b200.options` itself (same object), so every name the
+reference's scripts import from here - private helpers included - is the B200 mirror's."""
+import sys
+
+import lightningdot_b200.options as _mirror
+
+sys.modules[__name__] = _mirror

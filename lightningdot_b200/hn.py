@@ -8,8 +8,8 @@
 
 The device work is eval_model_on_dataloader (trainer.py): both towers over the whole training set, two exact top-k
 searches with k up to 1000 through the same fused score + top-k kernel as evaluation (ldot_flatip_search supports
-k <= 1024).  Only the dataset plumbing differs from the reference: its load_dataset / build_dataloader read LMDB
-databases (lmdb, lz4 - not available here), so the per-dataset dataloaders are passed in.
+k <= 1024).  The per-dataset evaluation loaders come from load_dataset / build_dataloader (trainer.py, data.py) exactly
+as in the reference; `train_dataloaders=` lets a caller pass ready-made loaders instead.
 """
 import collections
 import json
@@ -18,7 +18,7 @@ import os
 import random
 from collections import ChainMap
 
-from .trainer import eval_model_on_dataloader
+from .trainer import build_dataloader, eval_model_on_dataloader, load_dataset
 
 logger = logging.getLogger()
 
@@ -79,13 +79,14 @@ def filter_and_sample(hard_neg_img, hard_neg_txt, train_img2txt, train_txt2img, 
 
 def sampled_hard_negatives(all_img_dbs, args, collate_func, bi_encoder, train_img2txt, train_txt2img,
                            train_dataloaders=None):
-    """dvl/hn.py:47-68.  `train_dataloaders`: one evaluation-mode dataloader per training dataset (what the reference
-    builds from LMDB with load_dataset(..., True) + build_dataloader(dset, collate_func, True, args,
-    args.valid_batch_size)); required here."""
+    """dvl/hn.py:47-68.  `train_dataloaders` (optional): one dataloader per training dataset; by default they are built
+    as the reference does - load_dataset(..., is_train=True), new_epoch() without negatives, build_dataloader(dset,
+    collate_func, True, args, args.valid_batch_size)."""
     if train_dataloaders is None:
-        raise NotImplementedError(
-            "the LMDB-backed load_dataset / build_dataloader of dvl/trainer.py are outside this package (no lmdb / lz4): "
-            "pass train_dataloaders=[one eval-mode dataloader per training dataset]")
+        train_dataloaders = []
+        for dset in load_dataset(all_img_dbs, args.train_txt_dbs, args.train_img_dbs, args, True).datasets:
+            dset.new_epoch()
+            train_dataloaders.append(build_dataloader(dset, collate_func, True, args, args.valid_batch_size))
     hard_negs_txt_all, hard_negs_img_all = [], []
     for loader in train_dataloaders:
         logger.info(f'eval for train dataloader len (for hn) = {len(loader)}')

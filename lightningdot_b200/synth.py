@@ -221,3 +221,40 @@ def describe_batch(b):
             out[prefix] = v
     walk("", b)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Synthetic ITM databases on disk (the reference's text / image database layout, lightningdot_b200/data.py)
+# ---------------------------------------------------------------------------------------------------------------
+def make_itm_db(root, n_img, caps_per_img=5, seq_len=32, num_bb=36, seed=0, txt2img=None, name="val", conf_th=0.2,
+                max_bb=100, min_bb=10, compress=False, write_images=True):
+    """Write <root>/txt_<name>.db (tokenised captions) and <root>/img/ (region features) for n_img images and
+    n_img * caps_per_img captions drawn by text_batch / image_batch(ragged=True).  Caption j describes image
+    j // caps_per_img unless `txt2img` (list of image numbers, one per caption) says otherwise.  Image features are
+    stored as fp16 (like the reference's converter); boxes past an image's own count carry confidence 0 so that the
+    confidence-threshold rule (conf_th, min_bb, max_bb) recovers exactly that count.  -> (txt_db dir, img_db dir)."""
+    import os
+    from . import data
+    n_cap = n_img * caps_per_img
+    tb = text_batch(n_cap, seq_len, seed=seed, ragged=True)
+    lens = tb["attention_mask"].sum(1).tolist()
+    img_name = [f"img_{i:07d}.npz" for i in range(n_img)]
+    owner = [j // caps_per_img for j in range(n_cap)] if txt2img is None else [int(v) for v in txt2img]
+    records = {}
+    for j in range(n_cap):
+        body = tb["input_ids"][j, 1:lens[j] - 1].tolist()     # [CLS] / [SEP] are re-added by TxtTokLmdb.combine_inputs
+        records[str(j)] = {"input_ids": body, "img_fname": img_name[owner[j]], "id": str(j)}
+    txt_dir = data.write_txt_db(os.path.join(root, f"txt_{name}.db"), records, backend="flat")
+    img_dir = os.path.join(root, "img")
+    if write_images:
+        ib = image_batch(n_img, num_bb, seed=seed, ragged=True, min_bb=min_bb)
+        nbb = (ib["attention_mask"].sum(1) - 1).tolist()
+        feats = {}
+        for i in range(n_img):
+            conf = np.zeros(num_bb, dtype=np.float32)
+            conf[:nbb[i]] = 0.9
+            feats[img_name[i]] = {"features": ib["img_feat"][i].numpy(), "norm_bb": ib["img_pos_feat"][i, :, :6].numpy(),
+                                  "conf": conf}
+        data.write_img_db(img_dir, feats, conf_th=conf_th, max_bb=max_bb, min_bb=min_bb, num_bb=num_bb,
+                          compress=compress, backend="flat")
+    return txt_dir, img_dir

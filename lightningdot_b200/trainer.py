@@ -2,6 +2,8 @@
 
   eval_model_on_dataloader   dvl/trainer.py:113-190   same arguments, same 5-tuple return
   get_indexer                dvl/trainer.py:93-110
+  build_dataloader           dvl/trainer.py:28-37     DataLoader + PrefetchLoader over a dataset of data.py
+  load_dataset               dvl/trainer.py:193-209   text / image database folders -> ItmFastDataset(s)
   CheckpointState, _save_checkpoint, load_saved_state, load_states_from_checkpoint   dvl/trainer.py:18-20,44-90
 
 What differs from the reference is where the data lives, not what is computed: the reference copies every embedding
@@ -17,14 +19,47 @@ import os
 import numpy as np
 import torch
 
+from torch.utils.data import ConcatDataset, DataLoader
+
 from .bi_encoder import BiEncoderNllLoss
+from .data import ItmFastDataset, ItmValDataset, TxtTokLmdb, itm_fast_collate  # noqa: F401  (reference import surface)
 from .indexer import DenseFlatIndexer, DenseHNSWFlatIndexer
+from .loader import PrefetchLoader
 from .utils import _calc_loss
 
 logger = logging.getLogger()
 
 CheckpointState = collections.namedtuple(
     "CheckpointState", ['model_dict', 'optimizer_dict', 'scheduler_dict', 'offset', 'epoch', 'encoder_params'])
+
+
+class BiEncoderTrainer:
+    """Empty in the reference too (dvl/trainer.py:23-25); the scripts drive the functions below."""
+
+    def __init__(self, args):
+        pass
+
+
+def build_dataloader(dataset, collate_fn, is_train, opts, batch_size=None):
+    """dvl/trainer.py:28-37: shuffled (training) or sequential (evaluation) batches of opts.train_batch_size /
+    opts.valid_batch_size samples, collated on worker processes, moved to the GPU one batch ahead on a side stream."""
+    if batch_size is None:
+        batch_size = opts.train_batch_size if is_train else opts.valid_batch_size
+    loader = DataLoader(dataset, batch_size=batch_size, shuffle=is_train, drop_last=False, num_workers=opts.n_workers,
+                        pin_memory=opts.pin_mem, collate_fn=collate_fn)
+    return PrefetchLoader(loader)
+
+
+def load_dataset(all_img_dbs, txt_dbs, img_dbs, args, is_train):
+    """dvl/trainer.py:193-209.  Training: one ItmFastDataset per (text folder, image folder) pair, captions no longer than
+    args.max_txt_len, concatenated.  Evaluation: ONE dataset over a single folder pair with every caption kept (the
+    reference passes args.inf_minibatch_size in the hard-negative slot here; without mined negatives it has no effect)."""
+    if is_train:
+        return ConcatDataset([ItmFastDataset(TxtTokLmdb(txt_path, args.max_txt_len), all_img_dbs[img_path],
+                                             args.num_hard_negatives, args.img_meta, args.tokenizer)
+                              for txt_path, img_path in zip(txt_dbs, img_dbs)])
+    return ItmFastDataset(TxtTokLmdb(txt_dbs, -1), all_img_dbs[img_dbs], args.inf_minibatch_size, args.img_meta,
+                          args.tokenizer)
 
 
 def get_model_obj(model):

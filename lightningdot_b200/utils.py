@@ -6,11 +6,15 @@
   gather_embeddings / sync_gradients       the two exchange steps of global-batch training: a
                                            differentiable all-gather of the embeddings and the gradient average
   retrieve_query    dvl/utils.py:204-211   free-text query -> txt tower -> search_knn(., 100)
+  get_model_encoded_vecs   dvl/utils.py:214-234   encode a loader -> {id: embedding} dictionaries (the demo's index source)
+  all_gather_list   dvl/utils.py:51-111    arbitrary picklable data from every rank
   is_main_process / get_rank / get_world_size   dvl/utils.py:18-23,187-188 (horovod there; env / torch.distributed here)
   print_args, num_of_parameters, compare_models dvl/utils.py:26-38,172-184
 """
 import logging
 import os
+import pickle
+from collections import defaultdict
 
 import torch
 import torch.distributed as dist
@@ -150,3 +154,49 @@ def retrieve_query(model, query, indexer, args, top=10):
         _, query_vector, _ = model.txt_model(input_ids=input_ids, attention_mask=attn_mask, position_ids=pos_ids,
                                              need_sequence=False)
     return indexer.search_knn(query_vector, 100)
+
+
+def get_model_encoded_vecs(model, dataloader):
+    """dvl/utils.py:214-234 -> {'img_embed': {img id: vec}, 'caption_embed': {img id: vec}, 'txt_embed': {txt id: vec},
+    'img_name': ids of the LAST batch (the reference extends the list after the loop, :227)}.  One device -> host copy
+    per batch and tower instead of one per row; later encodings of an id overwrite earlier ones, as dict.update does."""
+    img_embedding, caption_embedding, query_embedding = dict(), dict(), defaultdict(list)
+    batch = None
+    for batch in dataloader:
+        with torch.no_grad():
+            q_vec, ctx_vec, cap_vec = model(batch)
+        for store, keys, vecs in ((img_embedding, batch['img_fname'], ctx_vec),
+                                  (caption_embedding, batch['img_fname'], cap_vec),
+                                  (query_embedding, batch['txt_index'], q_vec)):
+            if vecs is None:   # (no caption tower input: the reference would fail on zip(None); nothing to record)
+                continue
+            host = vecs.detach().float().cpu().numpy()
+            store.update({key: host[row] for row, key in enumerate(keys)})
+    return {'img_embed': img_embedding, 'caption_embed': caption_embedding, 'txt_embed': query_embedding,
+            'img_name': list(batch['img_fname']) if batch is not None else []}
+
+
+def all_gather_list(data, group=None, max_size=16384):
+    """dvl/utils.py:51-111: gather arbitrary picklable `data` from every rank -> list in rank order.  Same contract
+    (ValueError when the pickle plus its 4-byte length prefix exceeds max_size; every rank must call it), carried by one
+    all_gather of fixed-size byte rows (the reference all-reduces a zero-padded [world * max_size] CUDA byte buffer)."""
+    enc = pickle.dumps(data)
+    if len(enc) + 4 > max_size:
+        raise ValueError(f'encoded data exceeds max_size, this can be fixed by increasing buffer size: {len(enc)}')
+    if not (dist.is_available() and dist.is_initialized()):
+        return [pickle.loads(enc)]
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    row = torch.zeros(max_size, dtype=torch.uint8)
+    row[:4] = torch.tensor(list(len(enc).to_bytes(4, byteorder='big')), dtype=torch.uint8)
+    row[4:4 + len(enc)] = torch.frombuffer(bytearray(enc), dtype=torch.uint8)
+    row = row.to(dev)
+    rows = torch.empty((world, max_size), dtype=torch.uint8, device=dev)
+    dist.all_gather(list(rows.unbind(0)), row, group=group)
+    rows = rows.cpu()
+    out = []
+    for r in range(world):
+        n = int.from_bytes(bytes(rows[r, :4].tolist()), byteorder='big')
+        if n > 0:
+            out.append(pickle.loads(bytes(rows[r, 4:4 + n].numpy().tobytes())))
+    return out

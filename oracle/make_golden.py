@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE - mint tests/golden/* by running the UNMODIFIED reference from /root/reference.
 
-Run here (the container that has /root/reference):   python -m oracle.make_golden
+Run here (the container that has /root/reference):   python -m oracle.make_golden            (seconds-sized cases)
+                                                     python -m oracle.make_golden --configs0  (BASELINE configs[0], ~7 min)
 It (1) drives the reference's own classes / functions on seeded weights and inputs, (2) asserts that the oracle
 restatement (oracle/towers.py, loss.py, flatip.py, evalloop.py) reproduces them, (3) stores the REFERENCE outputs
 as small fixtures.  Weights are never stored: lightningdot_b200.synth regenerates them from the seed.
@@ -236,6 +237,163 @@ def collate_case():
     print("collate schema:", {k: len(v["batch"]) for k, v in out.items()})
 
 
+def _reference_itm_dataset(txt_dir, img_dir, compress, num_hard_negatives=0, max_txt_len=-1):
+    """The reference's own TxtTokLmdb / DetectFeatLmdb / ItmFastDataset over a database directory (lmdb stand-in of
+    ref_shims over the flat record file)."""
+    from dvl.data.itm import ItmFastDataset, TxtTokLmdb
+    from uniter_model.data import ImageLmdbGroup
+    group = ImageLmdbGroup(0.2, 100, 10, 36, compress)
+    return ItmFastDataset(TxtTokLmdb(txt_dir, max_txt_len), group[img_dir], num_hard_negatives, None, None)
+
+
+def dataset_case():
+    """dvl/data/itm.py:31-131,203-288 + uniter_model/data/data.py:44-251 over a synthetic database directory
+    (synth.make_itm_db): the reference's dataset + collate and the mirror's (lightningdot_b200/data.py) must yield
+    identical batches - plain, and with mined hard negatives for both modalities."""
+    import tempfile
+    from dvl.data.itm import itm_fast_collate
+    from lightningdot_b200 import data as mdata
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        kw = dict(n_img=12, caps_per_img=3, seq_len=24, num_bb=20, seed=9)
+        txt_dir, img_dir = synth.make_itm_db(d, compress=True, **kw)
+        n_cap = kw["n_img"] * kw["caps_per_img"]
+        hn_img = {str(j): [f"img_{(j // 3 + 1 + k) % 12:07d}.npz" for k in range(3)] for j in range(n_cap)}
+        hn_txt = {f"img_{i:07d}.npz": [str((3 * i + 5 + 2 * k) % n_cap) for k in range(3)] for i in range(12)}
+        for name, negs, rows in (("plain", 0, [0, 1, 2, 3, 4, 5, 6]), ("hardneg", 2, [4, 9, 17, 30, 35])):
+            ref = _reference_itm_dataset(txt_dir, img_dir, True, negs)
+            mine = mdata.ItmFastDataset(mdata.TxtTokLmdb(txt_dir, -1), mdata.ImageLmdbGroup(0.2, 100, 10, 36, True)[img_dir],
+                                        negs, None, None)
+            for ds in (ref, mine):
+                ds.new_epoch(hn_img, hn_txt) if negs else ds.new_epoch()
+            assert ref.ids == mine.ids and ref.lens == mine.lens and len(ref) == len(mine) == n_cap
+            d_ref = synth.describe_batch(itm_fast_collate([ref[i] for i in rows]))
+            d_mine = synth.describe_batch(mdata.itm_fast_collate([mine[i] for i in rows]))
+            assert d_ref == d_mine, {k: (d_ref.get(k), d_mine.get(k)) for k in set(d_ref) | set(d_mine)
+                                     if d_ref.get(k) != d_mine.get(k)}
+            out[name] = {"db": kw, "num_hard_negatives": negs, "rows": rows, "batch": d_ref}
+        out["hn_img"], out["hn_txt"] = hn_img, hn_txt
+    with open(os.path.join(GOLD, "itm_dataset.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+    print("[dataset] reference ItmFastDataset + itm_fast_collate == mirror, plain and with hard negatives")
+
+
+def _reference_biencoder(layers, seed_txt, seed_img):
+    """The reference's BiEncoder around two seeded towers (its own constructor needs the hub / checkpoint files)."""
+    from dvl.models.bi_encoder import BiEncoder
+    model = object.__new__(BiEncoder)
+    torch.nn.Module.__init__(model)
+    model.txt_model = build_reference_tower("txt", layers, synth.random_tower_state("txt", seed=seed_txt, perturb=True, layers=layers))
+    model.img_model = build_reference_tower("img", layers, synth.random_tower_state("img", seed=seed_img, perturb=True, layers=layers))
+    model.fix_img_encoder = model.fix_txt_encoder = False
+    model.project_dim = 768
+    return model.eval()
+
+
+def _reference_eval(txt_dir, img_dir, layers, seed_txt, seed_img, batch_size, compress=False):
+    """eval_itm.py:131-142 with the reference's own pieces on CPU: load_dataset's ItmFastDataset, itm_fast_collate, a
+    plain DataLoader (PrefetchLoader needs CUDA streams) and eval_model_on_dataloader (dvl/trainer.py:113-190)."""
+    from dvl.data.itm import itm_fast_collate
+    from dvl.trainer import eval_model_on_dataloader
+    from torch.utils.data import DataLoader
+    ds = _reference_itm_dataset(txt_dir, img_dir, compress, 400)
+    ds.new_epoch()
+    loader = DataLoader(ds, batch_size=batch_size, shuffle=False, drop_last=False, num_workers=0, collate_fn=itm_fast_collate)
+    with open(os.path.join(txt_dir, "img2txts.json")) as f:
+        img2txt = json.load(f)
+    args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+    return eval_model_on_dataloader(_reference_biencoder(layers, seed_txt, seed_img), loader, args, img2txt=img2txt)
+
+
+def _store_eval(path, res, extra=None):
+    loss, acc, _, (recall_txt, recall_img), (rank_txt, rank_img) = res
+    out = {"loss": float(loss), "acc": float(acc),
+           "recall_txt": {str(k): v for k, v in recall_txt.items()}, "recall_img": {str(k): v for k, v in recall_img.items()},
+           "rank_txt_top10": {k: list(v[:10]) for k, v in rank_txt.items()},
+           "rank_img_top10": {k: list(v[:10]) for k, v in rank_img.items()}}
+    out.update(extra or {})
+    with open(path, "w") as f:
+        json.dump(out, f)
+    return out
+
+
+def evalflow_case():
+    """The whole eval_itm.py flow at test size: 40 images x 5 captions in a database directory, 2-layer towers."""
+    import tempfile
+    kw = dict(n_img=40, caps_per_img=5, seq_len=32, num_bb=36, seed=3)
+    with tempfile.TemporaryDirectory() as d:
+        txt_dir, img_dir = synth.make_itm_db(d, compress=True, **kw)
+        res = _reference_eval(txt_dir, img_dir, 2, 301, 302, 16, compress=True)
+    out = _store_eval(os.path.join(GOLD, "evalflow_small.json"), res,
+                      {"db": kw, "layers": 2, "seed_txt": 301, "seed_img": 302, "batch_size": 16})
+    print(f"[evalflow] reference eval_model_on_dataloader over the database: loss {out['loss']:.5f} acc {out['acc']:.4f} "
+          f"recall_txt {out['recall_txt']} recall_img {out['recall_img']}")
+
+
+CONFIGS0 = dict(n_img=1000, caps_per_img=5, seq_len=32, num_bb=36, seed=0)
+CONFIGS0_MODEL = dict(layers=12, seed_txt=42, seed_img=43, batch_size=80)
+# score margins of the planted labels: > 2 x the largest ranking-relevant score error measured for the CUDA towers on this
+# very fixture (fp16: 0.08, bf16: 0.58 single-score / < 1.0 on adjacent ranks; scripts/probes/embed_noise.py)
+CONFIGS0_DELTA = {"fp16": 0.3, "bf16": 1.0}
+
+
+def configs0_case():
+    """BASELINE configs[0] at its stated size - 1 000 images x 5 000 captions, 12-layer seeded towers, both directions -
+    through the REFERENCE's eval loop on CPU (eval_itm.py:131-142 / dvl/trainer.py:113-190), once per planted labelling
+    (oracle/planted.py).  ~7 minutes on 8 cores.  Stores labels + the reference's recalls / loss / accuracy / top-10."""
+    import tempfile
+    import time
+    from oracle import planted
+    kw, mk = CONFIGS0, CONFIGS0_MODEL
+    n_cap = kw["n_img"] * kw["caps_per_img"]
+    t0 = time.time()
+    # planning pass: the reference towers over every caption and every image once
+    model = _reference_biencoder(mk["layers"], mk["seed_txt"], mk["seed_img"])
+    tb = synth.text_batch(n_cap, kw["seq_len"], seed=kw["seed"], ragged=True)
+    ib = synth.image_batch(kw["n_img"], kw["num_bb"], seed=kw["seed"], ragged=True)
+    ib["img_feat"] = ib["img_feat"].half().float()             # what the database stores (fp16) and hands back
+    ib["img_pos_feat"][..., :6] = ib["img_pos_feat"][..., :6].half().float()
+    ib["img_pos_feat"][..., 6] = ib["img_pos_feat"][..., 4] * ib["img_pos_feat"][..., 5]
+    T, I = [], []
+    with torch.no_grad():
+        for b in range(0, n_cap, 250):
+            sl = slice(b, b + 250)
+            L = int(tb["attention_mask"][sl].sum(1).max())
+            T.append(model.txt_model(tb["input_ids"][sl, :L], tb["attention_mask"][sl, :L], tb["position_ids"][:, :L])[1])
+        for b in range(0, kw["n_img"], 100):
+            sl = slice(b, b + 100)
+            I.append(model.img_model(ib["input_ids"][sl], ib["attention_mask"][sl], ib["position_ids"], ib["img_feat"][sl],
+                                     ib["img_pos_feat"][sl], None, ib["gather_index"][sl])[1])
+    S = torch.cat(T).numpy() @ torch.cat(I).numpy().T
+    print(f"[configs0] planning pass {time.time() - t0:.0f} s; score row std {S.std(1).mean():.3f}", flush=True)
+    out = {}
+    for tag, delta in CONFIGS0_DELTA.items():
+        owner, cls, forced = planted.plan(S, delta)
+        want_txt, want_img = planted.recalls(S, owner)
+        with tempfile.TemporaryDirectory() as d:
+            txt_dir, img_dir = synth.make_itm_db(d, txt2img=owner.tolist(), compress=True, **kw)
+            res = _reference_eval(txt_dir, img_dir, mk["layers"], mk["seed_txt"], mk["seed_img"], mk["batch_size"],
+                                  compress=True)
+        loss, acc, _, (recall_txt, recall_img), (rank_txt, rank_img) = res
+        assert recall_txt == want_txt and recall_img == want_img, (recall_txt, want_txt, recall_img, want_img)
+        print(f"[configs0/{tag}] delta {delta}: classes {np.bincount(cls, minlength=4).tolist()} forced {forced}; reference "
+              f"loss {loss:.5f} acc {acc:.4f} recall_txt {recall_txt} recall_img {recall_img} ({time.time() - t0:.0f} s)",
+              flush=True)
+        out[f"{tag}_owner"] = owner.astype(np.int16)
+        out[f"{tag}_class"] = cls.astype(np.int8)
+        out[f"{tag}_delta"] = np.array(delta)
+        out[f"{tag}_loss"], out[f"{tag}_acc"] = np.array(loss), np.array(acc)
+        out[f"{tag}_recall_txt"] = np.array([recall_txt[t] for t in (1, 5, 10)])
+        out[f"{tag}_recall_img"] = np.array([recall_img[t] for t in (1, 5, 10)])
+        out[f"{tag}_rank_txt_top10"] = np.array([[int(n[4:11]) for n in rank_txt[str(j)][:10]] for j in range(n_cap)], dtype=np.int16)
+        imgs = sorted(rank_img)
+        out[f"{tag}_rank_img_ids"] = np.array([int(n[4:11]) for n in imgs], dtype=np.int16)
+        out[f"{tag}_rank_img_top10"] = np.array([[int(v) for v in rank_img[n][:10]] for n in imgs], dtype=np.int16)
+    out["db"] = np.array(json.dumps(CONFIGS0))
+    out["model"] = np.array(json.dumps(CONFIGS0_MODEL))
+    np.savez_compressed(os.path.join(GOLD, "configs0_planted.npz"), **out)
+
+
 def options_case():
     """dvl/options.py: what the reference's own parser yields for an empty command line and for its shipped config
     JSONs (the config files' CONTENT is not stored - only the parsed namespaces, which is the surface to match)."""
@@ -281,6 +439,9 @@ def options_case():
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if "--configs0" in sys.argv:      # the full-size case alone (minutes)
+        configs0_case()
+        return
     for case in TOWER_CASES:
         tower_case(*case)
     loss_case()
@@ -289,6 +450,8 @@ def main():
     evalloop_case()
     options_case()
     collate_case()
+    dataset_case()
+    evalflow_case()
     print("golden fixtures written to", GOLD)
 
 

@@ -53,6 +53,26 @@ class NumpyIndexFlatIP:
         return out_s, out_i
 
 
+class _FlatLmdbEnv:
+    """Stand-in for lmdb.Environment over the flat record file lightningdot_b200/data.py writes when the `lmdb` wheel is
+    absent (records.ldkv): lets the reference's OWN DetectFeatLmdb / TxtLmdb classes read a database directory so that
+    the mirror's datasets can be pinned against the reference's (make_golden.dataset_case)."""
+
+    def __init__(self, path, **kw):
+        from lightningdot_b200.data import FlatKV
+        self._kv = FlatKV(path)
+
+    def begin(self, **kw):
+        return self
+
+    def get(self, key=None, default=None):
+        v = self._kv.get(bytes(key))
+        return default if v is None else v
+
+    def close(self):
+        self._kv.close()
+
+
 def _stub(name, **attrs):
     m = types.ModuleType(name)
     m.__dict__.update(attrs)
@@ -71,7 +91,7 @@ def install():
     norm = _stub("apex.normalization", fused_layer_norm=fln)
     _stub("apex", normalization=norm)
     _stub("faiss", IndexFlatIP=NumpyIndexFlatIP)
-    _stub("lmdb")
+    _stub("lmdb", open=lambda path, **kw: _FlatLmdbEnv(path, **kw))
     frame = _stub("lz4.frame", compress=lambda b: b, decompress=lambda b: b)
     _stub("lz4", frame=frame)
     _stub("msgpack_numpy", patch=lambda: None)
@@ -124,6 +144,20 @@ def install():
 
     BertModel.forward = forward
 
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's `dvl` and `uniter_model` are NAMESPACE packages (no top-level __init__.py); the repository ships
+    # regular packages of the same names (the drop-in boundary), and a regular package wins over a namespace portion
+    # wherever it sits on sys.path.  Bind the two names to the reference's directories explicitly.
+    import os
+    for name in ("dvl", "uniter_model"):
+        have = sys.modules.get(name)
+        if have is not None and not any(str(p).startswith(REFERENCE_ROOT) for p in getattr(have, "__path__", [])):
+            raise RuntimeError(f"'{name}' is already imported from {getattr(have, '__path__', '?')}: the reference must be "
+                               "imported in a process that has not imported the repository's namesake packages")
+        if have is None:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, name)]
+            sys.modules[name] = pkg
+    while REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
+    sys.path.insert(0, REFERENCE_ROOT)
     install._done = True

@@ -2,7 +2,7 @@
 long enough that both run at the sustained (power-capped) clock.  Not a bench line: a development probe that tells
 how far each of our tcgen05 kernels is from what the library reaches on the same shape under the same conditions.
 
-    python scripts/bench_linear.py [tokens] [seconds_per_case]
+    python scripts/bench_linear.py [tokens] [seconds_per_case] [case,case...]
 """
 import os
 import sys
@@ -14,6 +14,7 @@ from lightningdot_b200 import _lib  # noqa: E402
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 320000
 SECS = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+ONLY = set(sys.argv[3].split(",")) if len(sys.argv) > 3 else None   # case filter (ncu captures of one shape)
 lib = _lib.load()
 dt = torch.bfloat16
 fmt = 1
@@ -40,6 +41,8 @@ def timed(fn, flops):
 
 
 def case(name, N, K, act=0, ln=False, res=False):
+    if ONLY is not None and name not in ONLY:
+        return
     g = torch.Generator(device="cuda").manual_seed(N + K)
     a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(dt)
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.02).to(dt)
