@@ -18,6 +18,7 @@ import os
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from torch.utils.data import ConcatDataset, DataLoader
 
@@ -113,10 +114,45 @@ class _LastWins:
         return torch.as_tensor(list(self.row_of.values()), dtype=torch.int64, device=device)
 
 
+def _world():
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
 def _new_indexer(args, hnsw_index):
+    """dvl/trainer.py:93-98,160-161.  One process: DenseFlatIndexer.  Under a torch.distributed group (one process per GPU)
+    the index is row-sharded over the ranks (ShardedFlatIndexer: per-shard exact top-k, NCCL all-gather, merge) - the
+    8-GPU configuration of BASELINE configs[3], reached through the reference's own entry points."""
     if hnsw_index:
         return DenseHNSWFlatIndexer(args.vector_size)
+    if _world() > 1 and getattr(args, "shard_index", True):
+        from .sharded import ShardedFlatIndexer
+        return ShardedFlatIndexer(args.vector_size)
     return DenseFlatIndexer(args.vector_size)
+
+
+def _gather_interleaved(local, ids, world):
+    """Every rank encoded the samples ids[rank::world] of one sequential pass (TxtTokLmdb strides the caption ids over
+    the ranks, uniter_model/data/data.py:186-187).  -> (the [n_total, D] matrix, the id lists) in the order ONE process
+    would have seen them, identical on every rank: sample j of rank r is global sample j * world + r."""
+    dev = local.device
+    counts = [None] * world
+    dist.all_gather_object(counts, (local.shape[0], list(ids[0]), list(ids[1])))
+    m = max(c[0] for c in counts)
+    padded = local.new_zeros((m, local.shape[1]))
+    padded[:local.shape[0]] = local
+    parts = torch.empty((world, m, local.shape[1]), dtype=local.dtype, device=dev)
+    dist.all_gather_into_tensor(parts.view(world * m, -1), padded)
+    total = sum(c[0] for c in counts)
+    out = local.new_empty((total, local.shape[1]))
+    ids_a, ids_b = [None] * total, [None] * total
+    for r, (n, a, b) in enumerate(counts):
+        pos = torch.arange(n, device=dev) * world + r
+        if n and int(pos[-1]) >= total:
+            raise ValueError("ranks hold unevenly strided shares of the dataset: expected ids[rank::world]")
+        out[pos] = parts[r, :n]
+        ids_a[r::world] = a
+        ids_b[r::world] = b
+    return out, ids_a, ids_b
 
 
 def get_indexer(bi_encoder, eval_dataloader, args, hnsw_index, img_retrieval=True):
@@ -133,6 +169,14 @@ def get_indexer(bi_encoder, eval_dataloader, args, hnsw_index, img_retrieval=Tru
         n += vec.shape[0]
     if n:
         allv = torch.cat(chunks, 0)
+        world = _world()
+        if world > 1 and getattr(args, "shard_index", True) and not hnsw_index:
+            ids = [k for k, _ in sorted(seen.row_of.items(), key=lambda kv: kv[1])] if len(seen.row_of) == n else None
+            if ids is None:   # duplicates inside a rank's share: resolve them locally first
+                allv, ids = allv.index_select(0, seen.rows(allv.device)), seen.keys()
+            allv, ids, _ = _gather_interleaved(allv, (ids, ids), world)
+            seen = _LastWins()
+            seen.update(ids, 0)
         indexer.index_matrix(seen.keys(), allv.index_select(0, seen.rows(allv.device)))
     return indexer
 
@@ -170,11 +214,28 @@ def eval_model_on_dataloader(bi_encoder, eval_dataloader, args, img2txt=None, nu
 
     if batches == 0:
         raise ValueError("empty dataloader")
-    total_loss = float(total_loss.item()) / batches
-    correct_ratio = float(total_correct.item()) / float(total_samples)
     query_txt = torch.cat(txt_chunks, 0)
     query_img = torch.cat(img_chunks, 0)
     dev = query_txt.device
+    world = _world()
+    if world > 1 and getattr(args, "shard_index", True):
+        # every rank evaluated its stride of the captions: pool the embeddings (one all-gather per tower), rebuild the
+        # single-process sample order, and let every rank index / search the GLOBAL set through the row-sharded indexer.
+        # (The reference would report each rank's recall over its own subset; this is the one-process result.)
+        sums = torch.stack([total_loss, total_correct.double(),
+                            torch.tensor(float(batches), device=dev, dtype=torch.float64),
+                            torch.tensor(float(total_samples), device=dev, dtype=torch.float64)])
+        dist.all_reduce(sums)
+        total_loss, total_correct = sums[0], sums[1]
+        batches, total_samples = int(sums[2].item()), int(sums[3].item())
+        both, query_txt_id, query_img_id = _gather_interleaved(torch.cat([query_txt, query_img], 1),
+                                                               (query_txt_id, query_img_id), world)
+        query_txt, query_img = both[:, :query_txt.shape[1]].contiguous(), both[:, query_txt.shape[1]:].contiguous()
+        img_seen, txt_seen = _LastWins(), _LastWins()
+        img_seen.update(query_img_id, 0)
+        txt_seen.update(query_txt_id, 0)
+    total_loss = float(total_loss.item()) / batches
+    correct_ratio = float(total_correct.item()) / float(total_samples)
     indexer_img.index_matrix(img_seen.keys(), query_img.index_select(0, img_seen.rows(dev)))
     indexer_txt.index_matrix(txt_seen.keys(), query_txt.index_select(0, txt_seen.rows(dev)))
     if no_eval:

@@ -217,6 +217,60 @@ def test_sharded_search_protocol_two_ranks_gloo(tmp_path, n, nq, k):
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
 
 
+def _eval_loop_worker(rank, world, port, gold_path, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import lightningdot_b200.sharded as sh
+        gold = json.load(open(gold_path))
+        txt, img, _, img2txt = evalloop_inputs()
+        n_cap = len(txt)
+        txt_ids = [str(j) for j in range(n_cap)]
+        img_ids = [f"img_{j // 5:07d}.npz" for j in range(n_cap)]
+        mine = np.arange(rank, n_cap, world)          # TxtTokLmdb's ids[rank::world]
+        batches = [{"txts": {"input_ids": torch.zeros(len(rows), 4, dtype=torch.long)},
+                    "txt_index": [txt_ids[j] for j in rows], "img_fname": [img_ids[j] for j in rows], "_rows": rows}
+                   for rows in np.array_split(mine, 32)]
+
+        class StridedEncoder:
+            def eval(self):
+                return self
+
+            def __call__(self, batch):
+                return torch.from_numpy(txt[batch["_rows"]]), torch.from_numpy(img[batch["_rows"]]), None
+
+        trainer.BiEncoderNllLoss = OracleLoss
+        sh.ShardedFlatIndexer = _CpuSharded           # (trainer._new_indexer imports it from the module at call time)
+        args = types.SimpleNamespace(hnsw_index=False, vector_size=768, caption_score_weight=0.0)
+        out = trainer.eval_model_on_dataloader(StridedEncoder(), batches, args, img2txt, num_tops=100)
+        loss, acc, (ix_img, ix_txt), (recall_txt, recall_img), (rank_txt, rank_img) = out
+        assert isinstance(ix_img, _CpuSharded) and ix_img.index.ntotal == 100 and ix_txt.index.ntotal == 500
+        assert {str(k): v for k, v in recall_txt.items()} == gold["recall_txt"]
+        assert {str(k): v for k, v in recall_img.items()} == gold["recall_img"]
+        assert all(list(rank_txt[k][:10]) == v for k, v in gold["rank_txt_top10"].items())
+        assert all(list(rank_img[k][:10]) == v for k, v in gold["rank_img_top10"].items())
+        assert ix_img.index_id_to_db_id == [f"img_{i:07d}.npz" for i in range(200)] and ix_txt.index_id_to_db_id == txt_ids
+        assert np.isfinite(loss) and 0.0 <= acc <= 1.0
+        ix = trainer.get_indexer(StridedEncoder(), batches, args, hnsw_index=False, img_retrieval=True)
+        assert ix.index_id_to_db_id == [f"img_{i:07d}.npz" for i in range(200)] and ix.n_global == 200
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_eval_loop_two_ranks_gloo_equals_single_process_fixture(golden_dir, tmp_path):
+    """eval_model_on_dataloader under a process group: every rank evaluates the captions ids[rank::world], embeddings are
+    pooled into the single-process order, the indexes are row-sharded - recalls and rankings equal the fixture minted
+    from the reference's single-process loop, on every rank."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_eval_loop_worker, args=(2, port, os.path.join(golden_dir, "evalloop_small.json"), str(tmp_path)), nprocs=2,
+             join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
 def _loss_worker(rank, world, port, tmp):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
