@@ -84,24 +84,43 @@ def _grads(optimizer):
 
 @contextlib.contextmanager
 def scale_loss(loss, optimizer, **kwargs):
-    """Yields loss * scale; on exit the gradients are unscaled in place (so clip_grad_norm_ and the optimiser see true
-    gradients) and checked: a non-finite gradient makes the next optimizer.step() a no-op and halves the scale."""
+    """Yields loss * scale; on exit the gradients THIS backward produced are unscaled (so clip_grad_norm_ and the
+    optimiser see true gradients) and checked: a non-finite gradient makes the next optimizer.step() a no-op and halves
+    the scale.  Gradients accumulated by earlier micro-batches (gradient_accumulation_steps > 1: train_itm.py calls this
+    every micro-step and zero_grad only after step()) were unscaled when they were produced: they are set aside on entry
+    and added back after the unscale, as apex does with its stashed gradients."""
     sc = _scaler(optimizer)
     if not sc.enabled:
         yield loss
         return
+    stash = [(g, g.clone()) for g in _grads(optimizer)]
+    for g, _ in stash:
+        g.zero_()
     yield loss * sc.scale
     grads = _grads(optimizer)
     if not grads:
         return
     torch._foreach_mul_(grads, 1.0 / sc.scale)
     total = torch.stack([g.abs().max() for g in grads]).max()
-    overflow = not bool(torch.isfinite(total).item())      # (one host sync per step, as apex's dynamic scaler does)
+    overflow = ~torch.isfinite(total)
+    if getattr(optimizer, "distributed", False):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            flag = overflow.to(torch.int32)        # every rank must skip (or take) the step together: step() is collective
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            overflow = flag > 0
+    overflow = bool(overflow.item())               # (one host sync per step, as apex's dynamic scaler does)
     sc.update(overflow)
     if overflow:
         for g in grads:
             g.zero_()
         _skip_next_step(optimizer)
+        return
+    live = {g.data_ptr(): g for g in grads}
+    for g, saved in stash:
+        tgt = live.get(g.data_ptr())
+        if tgt is not None and tgt.shape == saved.shape:
+            tgt.add_(saved)
 
 
 def _skip_next_step(optimizer):

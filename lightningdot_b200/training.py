@@ -566,8 +566,11 @@ def zero_grads(module, set_to_none=True):
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    """torch.optim.AdamW semantics (what transformers.AdamW of bi_encoder.py:566-576 computes with
-    correct_bias=True) as ONE kernel launch per parameter group: parameters, gradients and both moments of a group
+    """torch.optim.AdamW semantics - decoupled weight decay applied to the parameter BEFORE the Adam update, eps added
+    after the bias-corrected sqrt(v), one step counter for all parameters - which is what bi_encoder.py:566-576's
+    transformers.AdamW(correct_bias=True) computes up to the placement of eps (HF adds it before the bias-2 correction) and
+    the order of the decay term (HF decays after the update); with the shipped eps = 1e-8 / weight_decay = 0 the two rules
+    differ by O(eps) per step.  ONE kernel launch per parameter group: parameters, gradients and both moments of a group
     live in flat fp32 buffers (the nn.Parameters become views of the flat master copy), `step()` is ldot_adamw over the
     flat buffers, optionally preceded by the global gradient-norm clip of train_itm.py:262-267 (`max_grad_norm` > 0:
     one extra reduction launch per group instead of a pass per tensor).
@@ -658,6 +661,7 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
+        self._unregister()    # (the old flat buffers must not stay listed in _lib.flat_buffers)
         self._flat = None     # re-laid out at the next step(), adopting the loaded moments and step count
         self._steps = 0
 

@@ -260,6 +260,41 @@ def test_eval_flow_on_database_directory_gpu(cuda_lib, golden_dir, tmp_path, fp1
 
 
 @pytest.mark.gpu
+def test_rerank_retrieval_loop_gpu(cuda_lib, tmp_path):
+    """rerank.py:149-214: index the validation database (no_eval=True), then 400-query batches of the test database
+    against both indexes; with the same database on both sides Recall@1/5/10 (text -> image) must equal what
+    eval_model_on_dataloader reports, rankings included, and the image -> text count follows the script's per-sample rule."""
+    from dvl.data.itm import itm_fast_collate
+    from dvl.trainer import build_dataloader, load_dataset
+    from lightningdot_b200.rerank import build_retrieval_indexes, retrieval_loop
+    from uniter_model.data import ImageLmdbGroup
+    ws = flow.make_workspace(str(tmp_path), n_img=90, caps_per_img=5, layers=2, batch_size=64)
+    out = flow.eval_flow(ws["config"], ws["checkpoint"], fp16=True)
+    args, model = out["args"], out["bi_encoder"]
+    dbs = ImageLmdbGroup(0.2, 100, 10, 36, False)
+
+    def loader(bs):
+        ds = load_dataset(dbs, args.val_txt_db, args.val_img_db, args, is_train=False)
+        ds.new_epoch()
+        return build_dataloader(ds, itm_fast_collate, False, args, batch_size=bs)
+
+    ix_img, ix_txt = build_retrieval_indexes(model, loader(64), args, ws["img2txt"])
+    res = retrieval_loop(model, ix_img, ix_txt, loader(400), ws["img2txt"])
+    assert res["total_len"] == 450 and set(res["recall_img"]) == {1, 5, 10, 20, 50, 100}
+    for t in (1, 5, 10):
+        assert res["recall_img"][t] == out["recall_txt"][t]          # text -> image: same quantity, same value
+    # (the same images are encoded in different batch compositions by the two passes: allow the odd near-tie swap)
+    same = np.mean([res["ranking_res_img"][q][:10] == out["rank_txt"][q][:10] for q in out["rank_txt"]])
+    assert same >= 0.98, same
+    per_sample = {t: np.mean([any(c in res["ranking_res_txt"][ws_img][:t] for c in ws["img2txt"][ws_img])
+                              for ws_img in [f"img_{j // 5:07d}.npz" for j in range(450)]]) for t in (1, 5, 10)}
+    assert all(abs(res["recall_txt"][t] - per_sample[t]) < 1e-12 for t in (1, 5, 10))
+    f = res["feats_dict"]
+    assert f["txts"]["7"]["input_ids"].dim() == 1 and f["imgs"]["img_0000001.npz"]["img_feat"].shape[1] == 2048
+    assert f["txts"]["7"]["img_feat"] is None and f["txts"]["7"]["position_ids"].dim() == 1
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fp16", [False, True], ids=["bf16", "fp16_amp"])
 def test_train_flow_on_database_directory_gpu(cuda_lib, tmp_path, fp16):
     """train_itm.py's flow on the real kernels: BiEncoder from config + checkpoint, FusedAdamW, linear schedule, shuffled

@@ -387,3 +387,48 @@ def test_fp16_training_with_amp_shim(cuda_lib):
     assert sc.skipped == 1 and sc.scale == amp.INIT_SCALE / 2 and torch.equal(w.detach(), before)
     one_step()
     assert not torch.equal(w.detach(), before) and torch.isfinite(w).all()
+
+
+def test_fp16_amp_shim_with_gradient_accumulation(cuda_lib):
+    """gradient_accumulation_steps > 1 (train_itm.py:246-248,280-283; the fp16 pre-training config uses 6): scale_loss is
+    entered once per micro-batch and zero_grad only follows step(), so gradients of earlier micro-batches - already
+    unscaled - must not be divided by the scale again.  Two half-weighted passes over the same batch must accumulate to the
+    gradient of one full pass, before and after the flat buffers exist."""
+    from lightningdot_b200 import amp
+    from lightningdot_b200.bi_encoder import setup_for_distributed_mode
+    args = types.SimpleNamespace(img_model_type='uniter-base', img_model_config=TowerConfig(num_hidden_layers=2),
+                                 img_checkpoint=None, txt_model_type='bert-base',
+                                 txt_model_config=TowerConfig(num_hidden_layers=2), txt_checkpoint=None)
+    torch.manual_seed(3)
+    model = BiEncoder(args, project_dim=768)
+    opt = get_optimizer(model, learning_rate=1e-6)
+    model, opt = setup_for_distributed_mode(model, opt, torch.device("cuda"), 1, -1, fp16=True)
+    model.eval()
+    B = 8
+    batch = {"txts": synth.text_batch(B, 24, seed=1, ragged=True), "imgs": synth.image_batch(B, 20, seed=2, ragged=True),
+             "caps": {"input_ids": None}, "sample_size": B, "pos_ctx_indices": list(range(B)), "neg_ctx_indices": []}
+    largs = types.SimpleNamespace(caption_score_weight=0.0)
+
+    def backward(weight):
+        t, i, _ = model(batch)
+        l1, _, _ = _calc_loss(largs, BiEncoderNllLoss(), i, t, None, batch["pos_ctx_indices"], None)
+        l2, _, _ = _calc_loss(largs, BiEncoderNllLoss(), t, i, None, batch["pos_ctx_indices"], None)
+        with amp.scale_loss((0.5 * l1 + 0.5 * l2) * weight, opt) as scaled_loss:
+            scaled_loss.backward()
+
+    def grads():
+        return {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+    for phase in ("before the flat layout", "after the flat layout"):
+        backward(1.0)
+        full = grads()
+        model.zero_grad()
+        backward(0.5)
+        backward(0.5)
+        acc = grads()
+        num = sum(float((acc[n] - full[n]).norm()) ** 2 for n in full)
+        den = sum(float(full[n].norm()) ** 2 for n in full)
+        assert den > 0 and (num / den) ** 0.5 < 2e-2, (phase, (num / den) ** 0.5)
+        opt.step()            # lays the flat buffers out (first pass) / steps on them (second pass)
+        model.zero_grad()
+    assert opt._amp_scaler.skipped == 0

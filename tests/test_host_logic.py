@@ -381,8 +381,17 @@ def test_hard_negative_sampling_logic(tmp_path, monkeypatch):
     args = types.SimpleNamespace(num_hard_negatives=2)
     t_all, i_all = hn.sampled_hard_negatives(None, args, None, object(), img2txt, txt2img, train_dataloaders=[[1], [2]])
     assert calls == [([1], 50), ([2], 50)] and set(t_all) == set(rank_img) and set(i_all) == set(rank_txt)
-    with pytest.raises(NotImplementedError):
-        hn.sampled_hard_negatives(None, args, None, object(), img2txt, txt2img)
+    # default path: the per-dataset loaders are built from the database folders as dvl/hn.py:48-52 does
+    from lightningdot_b200 import data as mdata
+    txt_dir, img_dir = synth.make_itm_db(str(tmp_path / "db"), 6, 2, seq_len=16, num_bb=12, seed=4)
+    built = []
+    monkeypatch.setattr(hn, "build_dataloader", lambda dset, collate, is_train, a, bs=None: built.append((dset, is_train, bs)) or [len(dset)])
+    args = types.SimpleNamespace(num_hard_negatives=2, train_txt_dbs=[txt_dir], train_img_dbs=[img_dir], max_txt_len=60,
+                                 img_meta=None, tokenizer=None, valid_batch_size=5)
+    calls.clear()
+    hn.sampled_hard_negatives(mdata.ImageLmdbGroup(0.2, 100, 10, 36, False), args, None, object(), img2txt, txt2img)
+    assert calls == [([12], 50)] and isinstance(built[0][0], mdata.ItmFastDataset) and built[0][1:] == (True, 5)
+    assert built[0][0].train_imgs is not None and built[0][0].neg_imgs == [None] * 12      # new_epoch() without negatives
     # mappings
     for name, part in (("d1", {"a.npz": ["0", "1"]}), ("d2", {"b.npz": ["2", "3"], "c.npz": ["4"]})):
         os.makedirs(tmp_path / name)
