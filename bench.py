@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=2048, help="queries of the cpu_baseline sample (~10 s of CPU work)")
     ap.add_argument("--ref-sample", type=int, default=256, help="queries per step of --impl reference (~1.5 s of CPU work per step)")
+    ap.add_argument("--parity-sample", type=int, default=1024,
+                    help="queries whose GPU top-k is compared with the oracle's exact CPU search over the full index")
+    ap.add_argument("--train-steps", type=int, default=4, help="timed steps of the train_step leg (BASELINE configs[4]); 0 = skip")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -380,6 +383,29 @@ def run_ours(args):
                                   "materialisation of faiss_indexers.py:85-87 (host-side, nq * k object references)",
                "timer": "host wall clock around the API calls (sync on both sides)"}
 
+    # ---- the same device-resident step with fp16 towers (what `fp16: true` of the reference's shipped eval config selects,
+    # config/flickr30k_eval_config.json:19); the headline above is bf16, the dtype north_star names
+    fp16_line = None
+    if not args.no_e2e:
+        txt_model.compute_dtype = torch.float16
+        for _ in range(2):
+            step_device()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            s16, i16 = step_device()
+        f1.record()
+        barrier()
+        ms16 = f0.elapsed_time(f1)
+        if world > 1:
+            t = torch.tensor([ms16], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms16 = float(t.item())
+        fp16_line = {"value": nq / (ms16 / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms16 / args.steps,
+                     "recall_planted": recall_at(i16, gt), "dtype": "fp16 towers (bf16 is the headline dtype)"}
+        txt_model.compute_dtype = torch.bfloat16
+
     # ---- certificate margins (diagnostic): error bound E of the coarse pass vs the score gap between rank k and k'
     cert = None
     if rank == 0:
@@ -475,6 +501,21 @@ def run_ours(args):
         del img_model, ib, img_emb
     barrier()
 
+    # ---- BASELINE configs[4]: the train_itm.py step at 512 pairs per GPU (global batch 512 x N, 4096 at N = 8), dropout on,
+    # symmetric in-batch NLL over the GLOBAL batch (embedding all-gather), gradient average, clip, AdamW
+    train_step = None
+    if args.train_steps > 0 and not args.no_e2e:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_train", os.path.join(ROOT, "scripts", "bench_train.py"))
+        bt = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bt)
+        x_host_keep = x.cpu() if (world == 1 and not args.no_cpu_baseline) else None   # (the CPU legs below need the rows)
+        del indexer, x
+        x = x_host_keep
+        torch.cuda.empty_cache()
+        train_step = bt.measure(bt.default_args(steps=args.train_steps, warmup=3), rank, world, local_rank, dev)
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -502,7 +543,13 @@ def run_ours(args):
     if os.path.exists(traffic_file):   # dram bytes per launch from the committed ncu --set full captures
         with open(traffic_file) as f:
             tr = json.load(f)
-        roof_lin["traffic"] = tr.get("linear_tcgen05")
+        shapes = tr.get("linear_tcgen05_shapes")
+        if shapes:   # per-shape captures at the bench's own M (scripts/ncu_shapes.sh): launch-weighted mean over a layer
+            per = [v["dram_bytes"] for v in shapes.values()]
+            roof_lin["traffic"] = sum(per) / len(per)
+            roof_lin["traffic_per_shape"] = shapes
+        else:
+            roof_lin["traffic"] = tr.get("linear_tcgen05")
         roof_search["traffic"] = tr.get("coarse_score_topk")
         if online:
             online["traffic"] = tr.get("coarse_score_topk_online")
@@ -519,6 +566,8 @@ def run_ours(args):
         "roofline_search": roof_search,
         "roofline_online": online,
         "index_build": index_build,
+        "fp16_towers": fp16_line,
+        "train_step": train_step,
         "kernel_shares": shares,
         "parity": {"recall_planted": recall, "scores_sorted": sorted_ok, "flagged_queries_last_step": int(flagged),
                    "certificate": cert},
@@ -540,7 +589,7 @@ def cpu_baseline(args, sd, ids_h, mask_h, pos_h, x_dev, emb_all, ids_gpu, scores
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     s, k = min(args.cpu_sample, ids_h.shape[0]), args.k
-    x_host = x_dev.cpu()
+    x_host = x_dev.cpu()   # (already on the host when the train_step leg released the device copy)
     # (a) the timed leg: the reference's CPU path on the sample
     t0 = time.perf_counter()
     emb_cpu = cpu_text_tower(sd, ids_h[:s], mask_h[:s], pos_h)
@@ -553,21 +602,28 @@ def cpu_baseline(args, sd, ids_h, mask_h, pos_h, x_dev, emb_all, ids_gpu, scores
                        f"text tower ({s / (t1 - t0):.1f} q/s) + fp32 sgemm/top-{k} flat-IP search over the full "
                        f"{x_host.shape[0]} x {D} index ({s / (t2 - t1):.1f} q/s)")}
     # (b) parity at the index boundary: the oracle's exact search on the GPU-produced embeddings (same inputs)
-    m = min(64, s)
+    m = min(args.parity_sample, ids_h.shape[0])
     q_np = emb_all[:m].cpu().numpy()
     x_np = x_host.numpy()
-    blocks = [flatip.scores_f64(q_np, x_np[r:r + 125000]) for r in range(0, x_np.shape[0], 125000)]
-    os_, oi = flatip.rank_topk(np.concatenate(blocks, axis=1), k)
+    os_, oi = flatip.search_blocked(q_np, x_np, k, row_block=125000)   # fp64-accumulated exact search, (score desc, id asc)
     gi = ids_gpu[:m].cpu().numpy()
     gs = scores_gpu[:m].cpu().numpy()
     rel = float(np.max(np.abs(gs - os_) / np.maximum(np.abs(os_), 1e-30)))
+    ms_ = min(m, s)
     tower_cos = float(torch.nn.functional.cosine_similarity(emb_all[:s].cpu(), emb_cpu, dim=1).min().item())
+    # ... and the end-to-end statement on the sample both sides encoded: CPU fp32 tower + fp32 sgemm search vs GPU towers +
+    # GPU search, Recall@1/5/10 of the planted rows
+    rec_e2e_cpu = {str(t): float((ci[:ms_, :t] == gt[:ms_, None].cpu()).any(dim=1).float().mean()) for t in (1, 5, 10)}
+    rec_e2e_gpu = {str(t): float(np.mean((ids_gpu[:ms_].cpu().numpy()[:, :t] == gt[:ms_].cpu().numpy()[:, None]).any(axis=1)))
+                   for t in (1, 5, 10)}
     gt_h = gt[:m].cpu().numpy()
     rec_cpu = {str(t): float(np.mean((oi[:, :t] == gt_h[:, None]).any(axis=1))) for t in (1, 5, 10)}
     rec_gpu = {str(t): float(np.mean((gi[:, :t] == gt_h[:, None]).any(axis=1))) for t in (1, 5, 10)}
     par = {"oracle_sample_queries": m, "ids_identical_to_oracle": bool(np.array_equal(gi, oi)),
            "max_rel_score_err_vs_oracle": rel, "recall_sample_oracle": rec_cpu, "recall_sample_gpu": rec_gpu,
-           "tower_embedding_min_cosine_vs_fp32_cpu": tower_cos}
+           "tower_embedding_min_cosine_vs_fp32_cpu": tower_cos,
+           "recall_end_to_end_cpu_reference_path": rec_e2e_cpu, "recall_end_to_end_gpu_path": rec_e2e_gpu,
+           "recall_end_to_end_sample_queries": ms_}
     return base, par
 
 

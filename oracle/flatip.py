@@ -71,6 +71,24 @@ def search(q, x, k, scorer=scores_f64, q_block=1024):
     return out_s, out_i
 
 
+def search_blocked(q, x, k, scorer=scores_f64, row_block=125000):
+    """search() for an index too large to hold a full [nq, n] score matrix: exact top-k per block of rows, then the
+    top-k of the per-block winners.  Candidates are concatenated in row order, so the (score desc, position asc) rule
+    of rank_topk is still (score desc, row id asc).  Same result as search()."""
+    q = np.ascontiguousarray(q, np.float32)
+    cs, ci = [], []
+    for r in range(0, len(x), row_block):
+        s, i = rank_topk(scorer(q, np.ascontiguousarray(x[r:r + row_block], np.float32)), k)
+        cs.append(s)
+        ci.append(np.where(i >= 0, i + r, -1))
+    cs, ci = np.concatenate(cs, axis=1), np.concatenate(ci, axis=1)
+    keep = ci >= 0
+    s2, pos = rank_topk(np.where(keep, cs, NEG), k)
+    ids = np.take_along_axis(ci, np.maximum(pos, 0), axis=1)
+    valid = (pos >= 0) & np.take_along_axis(keep, np.maximum(pos, 0), axis=1)
+    return np.where(valid, s2, NEG).astype(np.float32), np.where(valid, ids, -1)
+
+
 class FlatIndexer:
     """DenseFlatIndexer restated (dvl/indexer/faiss_indexers.py:63-87): id list + flat index + search_knn."""
 

@@ -31,27 +31,15 @@ from lightningdot_b200.bi_encoder import (BiEncoder, BiEncoderNllLoss, TowerConf
 from lightningdot_b200.utils import _calc_loss  # noqa: E402
 
 
-def main():
-    # stdout carries exactly one JSON line (NCCL prints its version banner there): everything else goes to stderr
-    sys.stdout.flush()
-    real_stdout = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--per-gpu-batch", type=int, default=512)
-    ap.add_argument("--seq-len", type=int, default=32)
-    ap.add_argument("--regions", type=int, default=36)
-    ap.add_argument("--layers", type=int, default=12)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--fp16", action="store_true")
-    ap.add_argument("--check", action="store_true")
-    a = ap.parse_args()
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+def default_args(**over):
+    a = types.SimpleNamespace(per_gpu_batch=512, seq_len=32, regions=36, layers=12, steps=5, warmup=3, fp16=False, check=False)
+    a.__dict__.update(over)
+    return a
+
+
+def measure(a, rank, world, local_rank, dev):
+    """One measurement of the training step inside an ALREADY initialised process group (bench.py's `train_step` key calls
+    this at every N).  -> the result dict on rank 0, None elsewhere."""
     b = a.per_gpu_batch
     B = b * world
 
@@ -189,6 +177,33 @@ def main():
             "loss_first_last": [losses[0].item(), losses[-1].item()],
             "peak_tflops": peak, "distributed_check": check,
         }
+        return line
+    return None
+
+
+def main():
+    # stdout carries exactly one JSON line (NCCL prints its version banner there): everything else goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--per-gpu-batch", type=int, default=512)
+    ap.add_argument("--seq-len", type=int, default=32)
+    ap.add_argument("--regions", type=int, default=36)
+    ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--fp16", action="store_true")
+    ap.add_argument("--check", action="store_true")
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = measure(a, rank, world, local_rank, dev)
+    if line is not None:
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     if world > 1:

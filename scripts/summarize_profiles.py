@@ -92,6 +92,24 @@ def ncu_report(tag, rep, name, traffic_key=None, kernel_index=0, traffic=None):
             traffic[traffic_key] = to_bytes(*r) + to_bytes(*w)
 
 
+SHAPES = {  # scripts/ncu_shapes.sh captures at M = 320 000 tokens: name -> (N, K, reads a residual)
+    "qkv": (2304, 768, False), "oproj_ln": (768, 768, True), "ffn1_gelu": (3072, 768, False), "ffn2_ln": (768, 3072, True)}
+
+
+def shape_traffic(tag, traffic, M=320000):
+    """Per-shape dram bytes of one launch at the bench's own size next to the algorithmic bytes (A + W + residual + out,
+    16-bit): profiles/traffic.json["linear_tcgen05_shapes"] - what bench.py's roofline.traffic is read from."""
+    out = {}
+    for name, (N, K, res) in SHAPES.items():
+        t = {}
+        ncu_report(tag, f"shape_{name}.ncu-rep", f"shape_{name}_m{M}", "x", 0, t)
+        if "x" in t:
+            alg = 2.0 * (M * K + N * K + M * N + (M * N if res else 0))
+            out[name] = {"M": M, "N": N, "K": K, "dram_bytes": t["x"], "algorithmic_bytes": alg, "ratio": t["x"] / alg}
+    if out:
+        traffic["linear_tcgen05_shapes"] = out
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
@@ -103,6 +121,11 @@ def main():
     for i, nm in enumerate(["linear_qkv", "linear_oproj", "linear_ffn1_gelu", "linear_ffn2", "linear_next"]):
         ncu_report(tag, "prof_linear.ncu-rep", nm, "linear_tcgen05" if nm == "linear_ffn1_gelu" else None, i, traffic)
     ncu_report(tag, "prof_attention.ncu-rep", "attention_fwd", None, 0, None)
+    shape_traffic(tag, traffic)
+    old = os.path.join(OUT, "traffic.json")
+    if os.path.exists(old):   # keep entries this run had no capture for
+        with open(old) as f:
+            traffic = {**json.load(f), **traffic}
     if traffic:
         with open(os.path.join(OUT, "traffic.json"), "w") as f:
             json.dump(traffic, f, indent=1)
