@@ -609,21 +609,15 @@ def cpu_baseline(args, sd, ids_h, mask_h, pos_h, x_dev, emb_all, ids_gpu, scores
     gi = ids_gpu[:m].cpu().numpy()
     gs = scores_gpu[:m].cpu().numpy()
     rel = float(np.max(np.abs(gs - os_) / np.maximum(np.abs(os_), 1e-30)))
-    ms_ = min(m, s)
     tower_cos = float(torch.nn.functional.cosine_similarity(emb_all[:s].cpu(), emb_cpu, dim=1).min().item())
-    # ... and the end-to-end statement on the sample both sides encoded: CPU fp32 tower + fp32 sgemm search vs GPU towers +
-    # GPU search, Recall@1/5/10 of the planted rows
-    rec_e2e_cpu = {str(t): float((ci[:ms_, :t] == gt[:ms_, None].cpu()).any(dim=1).float().mean()) for t in (1, 5, 10)}
-    rec_e2e_gpu = {str(t): float(np.mean((ids_gpu[:ms_].cpu().numpy()[:, :t] == gt[:ms_].cpu().numpy()[:, None]).any(axis=1)))
-                   for t in (1, 5, 10)}
     gt_h = gt[:m].cpu().numpy()
     rec_cpu = {str(t): float(np.mean((oi[:, :t] == gt_h[:, None]).any(axis=1))) for t in (1, 5, 10)}
     rec_gpu = {str(t): float(np.mean((gi[:, :t] == gt_h[:, None]).any(axis=1))) for t in (1, 5, 10)}
     par = {"oracle_sample_queries": m, "ids_identical_to_oracle": bool(np.array_equal(gi, oi)),
            "max_rel_score_err_vs_oracle": rel, "recall_sample_oracle": rec_cpu, "recall_sample_gpu": rec_gpu,
            "tower_embedding_min_cosine_vs_fp32_cpu": tower_cos,
-           "recall_end_to_end_cpu_reference_path": rec_e2e_cpu, "recall_end_to_end_gpu_path": rec_e2e_gpu,
-           "recall_end_to_end_sample_queries": ms_}
+           "note": "index-boundary parity (same embeddings into both searches); end-to-end Recall@1/5/10 identity through the "
+                   "16-bit towers is tests/test_gpu_configs0.py (BASELINE configs[0] at full size vs the reference's own run)"}
     return base, par
 
 
