@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LDOT_ABI_VERSION 4
+#define LDOT_ABI_VERSION 5
 
 #define LDOT_OK 0
 #define LDOT_ERR_ARG (-1)
@@ -129,6 +129,14 @@ int ldot_embed_image(const float* d_lin, const float* d_box, const float* d_img_
 int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,
                    int32_t heads, int32_t q_rows, int32_t dtype, void* stream);
 int ldot_cast_f32(const float* d_in, void* d_out, int64_t n, int32_t dtype, void* stream);
+/* ldot_qkv_attention  BertSelfAttention in one kernel (uniter_model/model/layer.py:60-101): d_ctx [B * S, H] =
+ *                     attention over Q | K | V = d_x [B * S, K] . d_w [3 H, K]^T + d_bias [3 H] (the query / key / value
+ *                     nn.Linear weights stacked in that order), additive mask from d_mask int64 [B, S] (1 = attend),
+ *                     heads of 64.  Replaces ldot_linear (N = 3 H) + ldot_attention (q_rows = S): the [B * S, 3 H]
+ *                     projection never reaches HBM.  S <= 128.                                                          */
+int ldot_qkv_attention(const void* d_x, int64_t ldx, const void* d_w, int64_t ldw, const float* d_bias,
+                       const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H, int32_t heads, int32_t K,
+                       int32_t dtype, void* stream);
 /* Training-mode dropout of the towers (bi_encoder.py:97-99 -> hidden_dropout_prob, attention_probs_dropout_prob): masks
  * are a counter-based function of (seed, site, element index) - csrc/dropout.cuh - regenerated by the backward kernels.
  * ldot_attention_train  ldot_attention (q_rows = S) with dropout of the attention probabilities (layer.py:93)

@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
 
-ABI_VERSION = 4   # LDOT_ABI_VERSION of include/ldot.h
+ABI_VERSION = 5   # LDOT_ABI_VERSION of include/ldot.h
 COARSE_FP16 = 0
 COARSE_BF16 = 1
 
@@ -70,6 +70,8 @@ SIGNATURES = {
     "ldot_embed_image": (c_int32, [c_void_p] * 12 + [c_int32] * 6 + [c_void_p]),
     "ldot_attention": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_cast_f32": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "ldot_qkv_attention": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                     c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "ldot_split16": (c_int32, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "ldot_inbatch_nll": (c_int32, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -198,6 +198,8 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
 }  // namespace ldot
 #include "encoder_params.h"
 namespace ldot {
+int qkv_attention_run(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const long long* mask,
+                      void* ctx, int B, int S, int H, int heads, int K, int fmt, void* stream);
 int attention_run(const void* qkv, const long long* mask, void* ctx, int B, int S, int H, int heads, int q_rows, int fmt,
                   void* stream, float drop_p = 0.f, unsigned long long seed = 0, int site = 0);
 int layernorm_run(const void* in, long long ld_in, int in_f32, const float* gamma, const float* beta, void* out,
@@ -387,6 +389,14 @@ int ldot_attention(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_
   LDOT_REQUIRE(d_qkv && d_mask && d_ctx, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
   return attention_run(d_qkv, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, q_rows, dtype, stream);
+}
+
+int ldot_qkv_attention(const void* d_x, int64_t ldx, const void* d_w, int64_t ldw, const float* d_bias, const int64_t* d_mask,
+                       void* d_ctx, int32_t B, int32_t S, int32_t H, int32_t heads, int32_t K, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_x && d_w && d_bias && d_mask && d_ctx, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return qkv_attention_run(d_x, ldx, d_w, ldw, d_bias, reinterpret_cast<const long long*>(d_mask), d_ctx, B, S, H, heads, K,
+                           dtype, stream);
 }
 
 int ldot_attention_train(const void* d_qkv, const int64_t* d_mask, void* d_ctx, int32_t B, int32_t S, int32_t H,

@@ -7,6 +7,7 @@
 // The kernel is linear_tc.cuh; this file is its host side.
 #include "linear_tc.cuh"
 #include "linear_ln.cuh"
+#include "qkv_attn.cuh"
 #include "host_common.h"
 #include "prof.h"
 #include <cstdlib>
@@ -294,6 +295,90 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
                      (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
   LDOT_CUDA(cudaLaunchKernelEx(&cfg, linear_ln_kernel, ta, tw, tr, te, to, s, p));
   return kOk;
+}
+
+
+// ---------------------------------------------------------------------------------------- fused QKV projection + attention
+template <int SPAD, int FMT>
+static int launch_qkv_attn(const CUtensorMap& ta, const CUtensorMap& tw, const QaSched& s, const QaParams& p, cudaStream_t st) {
+  auto kern = qkv_attn_kernel<SPAD, FMT>;
+  static bool configured = false;
+  static int max_pairs = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kQaThreads);
+  cfg.dynamicSmemBytes = QaSmem::kDynamic;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, QaSmem::kDynamic));
+    cfg.gridDim = dim3(2);
+    LDOT_CUDA(cudaOccupancyMaxActiveClusters(&max_pairs, kern, &cfg));
+    LDOT_REQUIRE(max_pairs >= 1, "no resident CTA pair possible");
+    configured = true;
+  }
+  const int pairs = s.num_tiles < max_pairs ? s.num_tiles : max_pairs;
+  cfg.gridDim = dim3(static_cast<unsigned>(pairs * 2));
+  LDOT_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tw, s, p));
+  return kOk;
+}
+
+// x [B * S, K] (16-bit) -> ctx [B * S, H]: BertSelfAttention (Q | K | V projection with the stacked [3 H, K] weight, scaled
+// dot-product attention with the additive mask, per head) without the [B * S, 3 H] intermediate in HBM.
+int qkv_attention_run(const void* x, long long ldx, const void* w, long long ldw, const float* bias, const long long* mask,
+                      void* ctx, int B, int S, int H, int heads, int K, int fmt, void* stream) {
+  LDOT_REQUIRE(B >= 1 && S >= 1 && S <= 128, "qkv_attention: bad shape B=%d S=%d (S <= 128)", B, S);
+  LDOT_REQUIRE(H == heads * kHeadDim, "qkv_attention: hidden %d must be heads (%d) x 64", H, heads);
+  LDOT_REQUIRE(K >= 8 && K % 8 == 0 && ldx % 8 == 0 && ldw % 8 == 0, "K, ldx, ldw must be multiples of 8 elements");
+  LDOT_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE(bias != nullptr, "qkv_attention: the projection bias is required");
+  LDOT_REQUIRE((reinterpret_cast<uintptr_t>(ctx) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
+               "ctx / bias must be 16-byte aligned");
+  const long long T = static_cast<long long>(B) * S;
+  LDOT_REQUIRE(T < (1ll << 31) - 256, "too many tokens");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUtensorMap ta, tw;
+  if (int e = make_tmap_kmajor_16b(&ta, x, static_cast<uint64_t>(T), K, static_cast<uint64_t>(ldx) * 2, kBM)) return e;
+  if (int e = make_tmap_kmajor_16b(&tw, w, static_cast<uint64_t>(3) * H, K, static_cast<uint64_t>(ldw) * 2, 32)) return e;
+  QaSched s;
+  s.seq_per_tile = kBM / S;
+  s.rows_per_tile = s.seq_per_tile * S;
+  s.m_tiles = (B + s.seq_per_tile - 1) / s.seq_per_tile;
+  s.heads = heads;
+  s.num_tiles = ((s.m_tiles + 1) / 2) * heads;
+  s.k_blocks = (K + kBK - 1) / kBK;
+  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), kBM * 2, kQaBN);
+  static int yield_mma = -1;
+  if (yield_mma < 0) {
+    const char* e = getenv("LDOT_QA_YIELD");   // (measurement switch)
+    yield_mma = e ? atoi(e) : 2;
+  }
+  s.yield_mma = yield_mma;
+  QaParams p;
+  p.bias = bias;
+  p.mask = mask;
+  p.ctx = static_cast<uint16_t*>(ctx);
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  // algorithmic work: the projection GEMM + the two attention contractions; bytes: x + W + ctx (no Q | K | V round trip)
+  KernelScope ks(kKcLinear, st, 2.0 * T * 3.0 * H * K + 4.0 * T * S * H,
+                 (static_cast<double>(T) * K + 3.0 * H * K + static_cast<double>(T) * H) * 2.0);
+  const int spad = S <= 32 ? 32 : S <= 48 ? 48 : S <= 64 ? 64 : S <= 96 ? 96 : 128;
+#define LDOT_QA(SP) (fmt == 1 ? launch_qkv_attn<SP, 1>(ta, tw, s, p, st) : launch_qkv_attn<SP, 0>(ta, tw, s, p, st))
+  switch (spad) {
+    case 32: return LDOT_QA(32);
+    case 48: return LDOT_QA(48);
+    case 64: return LDOT_QA(64);
+    case 96: return LDOT_QA(96);
+    default: return LDOT_QA(128);
+  }
+#undef LDOT_QA
 }
 
 }  // namespace ldot

@@ -10,11 +10,15 @@ exactly as uniter_model/model/model.py:356-387 + layer.py:159-170 + dvl/models/b
 All GEMMs are the tcgen05 kernel (ldot_linear); everything runs on torch's current stream.  No torch math is
 used on this path.
 """
+import os
+
 import torch
 
 from . import _lib
 
 SEQ_BATCH_TOKENS = 524288   # tokens per engine pass (bounds activation scratch to ~10 GB)
+# LDOT_FUSED_ATTN=0: Q | K | V projection and attention as two kernels with the [tokens, 3H] round trip (measurement switch)
+FUSED_ATTN = os.environ.get("LDOT_FUSED_ATTN", "1") != "0"
 
 
 def _fmt_of(dtype):
@@ -153,18 +157,19 @@ class TowerEngine:
         lib = _lib.load()
         T, H, dt, dev = B * S, self.H, self.dtype, h.device
         w = self.w
-        qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
+        qkv = None   # (only the unfused layers need the [T, 3H] projection buffer)
         ctx = torch.empty((T, H), dtype=dt, device=dev)
         pre = None if self.fuse_ln else torch.empty((T, H), dtype=torch.float32 if self.pre_ln_f32 else dt, device=dev)
         a = torch.empty((T, H), dtype=dt, device=dev)
         f = torch.empty((T, self.ffn), dtype=dt, device=dev)
         stream = _lib.stream_ptr()
 
-        def block(i, x_in, ldx, ctx_, a_, f_, out_, rows, q_rows):
+        def block(i, x_in, ldx, ctx_, a_, f_, out_, rows, q_rows, attend=True):
             """attention output ctx_ -> BertSelfOutput -> BertIntermediate -> BertOutput for `rows` rows; x_in (row pitch
             ldx) is the layer input of those rows (the residual)."""
-            _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx_), B, S, H, self.heads, q_rows,
-                                          self.fmt, stream))
+            if attend:
+                _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx_), B, S, H, self.heads, q_rows,
+                                              self.fmt, stream))
             res = x_in.as_strided((rows, H), (ldx, 1))
             if self.fuse_ln:
                 self._linear_ln(ctx_, H, w[f"o_w{i}"], w[f"o_b{i}"], res, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a_, rows)
@@ -179,8 +184,17 @@ class TowerEngine:
             self._layernorm(pre_, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out_, rows, H)
 
         for i in range(self.layers):
+            last_cls = cls_only and i == self.layers - 1
+            if FUSED_ATTN and not last_cls:
+                # BertSelfAttention as ONE kernel: the projection's [T, 3H] output stays in shared memory / TMEM
+                _lib.check(lib.ldot_qkv_attention(_lib.ptr(h), H, _lib.ptr(w[f"qkv_w{i}"]), H, _lib.ptr(w[f"qkv_b{i}"]),
+                                                  _lib.ptr(mask), _lib.ptr(ctx), B, S, H, self.heads, H, self.fmt, stream))
+                block(i, h, H, ctx, a, f, h, T, S, attend=False)
+                continue
+            if qkv is None:
+                qkv = torch.empty((T, 3 * H), dtype=dt, device=dev)
             self._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
-            if cls_only and i == self.layers - 1:
+            if last_cls:
                 cls = torch.empty((B, H), dtype=dt, device=dev)
                 block(i, h, S * H, ctx[:B], a[:B], f[:B], cls, B, 1)
                 return h, cls

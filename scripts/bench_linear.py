@@ -71,7 +71,45 @@ def case(name, N, K, act=0, ln=False, res=False):
           f"{tf_c:7.1f} TF/s | ours/cuBLAS {tf_o / tf_c:.3f}", flush=True)
 
 
+def case_qkv_attn(name, S=32, H=768, heads=12):
+    """BertSelfAttention as one kernel (ldot_qkv_attention) next to the two kernels it replaces and to cuBLAS's bare
+    projection GEMM; FLOPs counted: projection + the two attention contractions."""
+    if ONLY is not None and name not in ONLY:
+        return
+    B = M // S
+    T = B * S
+    g = torch.Generator(device="cuda").manual_seed(S)
+    x = (torch.randn(T, H, device="cuda", generator=g) * 0.5).to(dt)
+    w = (torch.randn(3 * H, H, device="cuda", generator=g) * 0.02).to(dt)
+    b = torch.randn(3 * H, device="cuda", generator=g) * 0.1
+    mask = torch.ones(B, S, dtype=torch.int64, device="cuda")
+    qkv = torch.empty(T, 3 * H, device="cuda", dtype=dt)
+    ctx = torch.empty(T, H, device="cuda", dtype=dt)
+    s = _lib.stream_ptr()
+    flops = 2.0 * T * 3 * H * H + 4.0 * T * S * H
+
+    def fused():
+        _lib.check(lib.ldot_qkv_attention(_lib.ptr(x), H, _lib.ptr(w), H, _lib.ptr(b), _lib.ptr(mask), _lib.ptr(ctx), B, S, H,
+                                          heads, H, fmt, s))
+
+    def two():
+        _lib.check(lib.ldot_linear(_lib.ptr(x), H, _lib.ptr(w), H, _lib.ptr(b), None, 0, _lib.ptr(qkv), 3 * H, T, 3 * H, H,
+                                   fmt, 0, 0, s))
+        _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, heads, S, fmt, s))
+    wt = w.t()
+
+    def cublas():
+        torch.matmul(x, wt, out=qkv)
+    ms_c, tf_c = timed(cublas, 2.0 * T * 3 * H * H)
+    ms_t, tf_t = timed(two, flops)
+    ms_f, tf_f = timed(fused, flops)
+    print(f"{name:10s} T={T} S={S}: fused {ms_f:8.3f} ms {tf_f:7.1f} TF/s | projection + attention kernels {ms_t:8.3f} ms "
+          f"{tf_t:7.1f} TF/s | cuBLAS projection only {ms_c:8.3f} ms {tf_c:7.1f} TF/s", flush=True)
+
+
 print(torch.cuda.get_device_name(0), flush=True)
+case_qkv_attn("qkv+attn", 32)
+case_qkv_attn("qkv+attn37", 37)
 case("qkv", 2304, 768)
 case("o+ln", 768, 768, ln=True)
 case("o+res", 768, 768, res=True)

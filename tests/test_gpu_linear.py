@@ -119,3 +119,39 @@ def test_linear_layernorm_fused(cuda_lib, M, N, K, fmt):
                                   _lib.ptr(out), N, M, N, K, fmt, _lib.stream_ptr()))
     ref2 = torch.nn.functional.layer_norm(a.float() @ w.float().t(), (N,), gamma, beta, 1e-12)
     torch.testing.assert_close(out[:M].float(), ref2, **tol)
+
+
+@pytest.mark.parametrize("B,S", [(8, 32), (9, 32), (1, 32), (7, 37), (64, 37), (5, 17), (130, 1), (3, 64), (4, 65), (2, 128),
+                                 (11, 50), (6, 100)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_fused_qkv_attention_equals_projection_then_attention(cuda_lib, B, S, fmt):
+    """ldot_qkv_attention (BertSelfAttention as one kernel, Q | K | V kept on chip) against the two-kernel path it replaces -
+    ldot_linear (N = 3H) + ldot_attention - on the same inputs: both round Q, K, V to 16 bit after the bias and run the same
+    attention arithmetic, so the context tensors must agree to the last bit; and against a torch fp32 reference of
+    uniter_model/model/layer.py:60-101.  Shapes cover whole / partial last tiles, sequences that do not divide 128, key
+    blocks that run past row 127 of the tile, S = 1 and S = 128; masks are ragged."""
+    lib = _lib.load()
+    H, heads = 768, 12
+    dt = torch.float16 if fmt == 0 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(100 * B + S)
+    x = (torch.randn(B * S, H, device="cuda", generator=g) * 0.8).to(dt)
+    w = (torch.randn(3 * H, H, device="cuda", generator=g) * 0.04).to(dt)
+    b = torch.randn(3 * H, device="cuda", generator=g) * 0.1
+    lens = torch.randint(1, S + 1, (B,), device="cuda", generator=g)
+    mask = (torch.arange(S, device="cuda")[None, :] < lens[:, None]).long()
+    st = _lib.stream_ptr()
+    qkv = torch.empty((B * S, 3 * H), dtype=dt, device="cuda")
+    want = torch.empty((B * S, H), dtype=dt, device="cuda")
+    _lib.check(lib.ldot_linear(_lib.ptr(x), H, _lib.ptr(w), H, _lib.ptr(b), None, 0, _lib.ptr(qkv), 3 * H, B * S, 3 * H, H,
+                               fmt, 0, 0, st))
+    _lib.check(lib.ldot_attention(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(want), B, S, H, heads, S, fmt, st))
+    got = torch.full((B * S, H), float("nan"), dtype=dt, device="cuda")
+    _lib.check(lib.ldot_qkv_attention(_lib.ptr(x), H, _lib.ptr(w), H, _lib.ptr(b), _lib.ptr(mask), _lib.ptr(got), B, S, H,
+                                      heads, H, fmt, st))
+    torch.cuda.synchronize()
+    assert torch.isfinite(got.float()).all()
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+    q, k, v = (qkv.float().view(B, S, 3, heads, 64)[:, :, j].permute(0, 2, 1, 3) for j in range(3))
+    sc = q @ k.transpose(-1, -2) / 8.0 + (1.0 - mask.float())[:, None, None, :] * -10000.0
+    ref = (torch.softmax(sc, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, H)
+    torch.testing.assert_close(got.float(), ref, atol=3e-2 if fmt else 4e-3, rtol=2e-2 if fmt else 3e-3)
