@@ -80,11 +80,13 @@ int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n,
                       int64_t id_offset, float* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes,
                       void* stream);
 
-/* Merge the exact top-k lists of `world` index shards (after the NCCL all-gather):
+/* Merge the exact top-k lists of `world` index shards (after the NCCL exchange):
  * d_scores [world, nq, k], d_idx [world, nq, k] (global ids; every list ranked as ldot_flatip_search returns it:
- * (score desc, id asc), label -1 entries last) -> d_out_* [nq, k], same ranking rule.                            */
+ * (score desc, id asc), label -1 entries last) -> d_out_* [nq, k], same ranking rule.  shard_stride_* = elements between
+ * the lists of consecutive shards (0 = dense, nq * k): lets scores and ids of a shard travel in one packed buffer.     */
 int ldot_topk_merge(const float* d_scores, const int64_t* d_idx, int32_t world, int64_t nq, int32_t k,
-                    float* d_out_scores, int64_t* d_out_idx, void* stream);
+                    int64_t shard_stride_scores, int64_t shard_stride_idx, float* d_out_scores, int64_t* d_out_idx,
+                    void* stream);
 
 /* ---- encoder Linear: replaces nn.Linear (+ fused GELU / residual) on the tower path ---------------------------
  * (uniter_model/model/layer.py:76-78,107,133,148; model.py:252; dvl/models/bi_encoder.py:83-88,138-143)

@@ -332,9 +332,11 @@ int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n,
 }
 
 int ldot_topk_merge(const float* d_scores, const int64_t* d_idx, int32_t world, int64_t nq, int32_t k,
-                    float* d_out_scores, int64_t* d_out_idx, void* stream) {
+                    int64_t shard_stride_scores, int64_t shard_stride_idx, float* d_out_scores, int64_t* d_out_idx,
+                    void* stream) {
   LDOT_REQUIRE(d_scores && d_idx && d_out_scores && d_out_idx, "null pointer argument");
-  return merge_run(d_scores, reinterpret_cast<const long long*>(d_idx), world, nq, k, d_out_scores,
+  return merge_run(d_scores, reinterpret_cast<const long long*>(d_idx), world, nq, k, shard_stride_scores,
+                   shard_stride_idx, d_out_scores,
                    reinterpret_cast<long long*>(d_out_idx), stream);
 }
 

@@ -702,17 +702,19 @@ __global__ void __launch_bounds__(1024) exact_merge_kernel(const unsigned long l
 // Every shard list arrives RANKED ((score desc, id asc); label -1 entries at the end), and keys are unique (global ids),
 // so the global rank of entry r of list w is r + sum over the other lists of how many of their entries beat it:
 // W - 1 binary searches per entry in shared memory and one synchronisation, instead of a bitonic sort of all W k keys.
+// ws_s / ws_i: elements between the lists of consecutive shards (nq * k when the two arrays are dense [W, nq, k]; larger when
+// every shard's scores and ids arrive in ONE packed buffer, sharded.py).
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ scores, const long long* __restrict__ idx,
-                                                    int W, int nq, int k, float* __restrict__ out_scores,
-                                                    long long* __restrict__ out_idx) {
+                                                    int W, int nq, int k, long long ws_s, long long ws_i,
+                                                    float* __restrict__ out_scores, long long* __restrict__ out_idx) {
   extern __shared__ unsigned long long mg_keys[];  // [W * k]
   const int q = blockIdx.x;
   const int total = W * k;
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
     const int w = i / k, r = i - w * k;
-    const size_t o = (static_cast<size_t>(w) * nq + q) * k + r;
-    const long long id = idx[o];
-    mg_keys[i] = id >= 0 ? rank_key(scores[o], static_cast<uint32_t>(id)) : 0ull;
+    const size_t o = static_cast<size_t>(q) * k + r;
+    const long long id = idx[static_cast<size_t>(w) * ws_i + o];
+    mg_keys[i] = id >= 0 ? rank_key(scores[static_cast<size_t>(w) * ws_s + o], static_cast<uint32_t>(id)) : 0ull;
   }
   for (int r = threadIdx.x; r < k; r += blockDim.x) {   // (fewer than k valid entries in total: the tail stays empty)
     out_scores[static_cast<size_t>(q) * k + r] = -FLT_MAX;
@@ -1218,8 +1220,10 @@ int exact_run(const float* q, long long nf, const float* x, long long n, int d, 
   return kOk;
 }
 
-int merge_run(const float* scores, const long long* idx, int W, long long nq, int k, float* out_scores,
-              long long* out_idx, void* stream) {
+int merge_run(const float* scores, const long long* idx, int W, long long nq, int k, long long ws_s, long long ws_i,
+              float* out_scores, long long* out_idx, void* stream) {
+  if (ws_s <= 0) ws_s = nq * k;
+  if (ws_i <= 0) ws_i = nq * k;
   LDOT_REQUIRE(W >= 1 && W <= 64 && nq >= 0 && k >= 1 && k <= 1024, "bad merge shape W=%d nq=%lld k=%d", W, nq, k);
   if (nq == 0) return kOk;
   const size_t smem = static_cast<size_t>(W) * k * sizeof(unsigned long long);
@@ -1228,7 +1232,7 @@ int merge_run(const float* scores, const long long* idx, int W, long long nq, in
   {
     KernelScope ks(kKcMerge, static_cast<cudaStream_t>(stream), 0.0, static_cast<double>(nq) * k * 12.0 * (W + 1));
     merge_kernel<<<static_cast<int>(nq), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-        scores, idx, W, static_cast<int>(nq), k, out_scores, out_idx);
+        scores, idx, W, static_cast<int>(nq), k, ws_s, ws_i, out_scores, out_idx);
   }
   LDOT_CHECK_LAUNCH();
   return kOk;

@@ -55,7 +55,8 @@ int index_prepare_run(const float* x, long long n, int d, int coarse_dtype, int 
 size_t exact_workspace_bytes(long long n);
 int exact_run(const float* q, long long nf, const float* x, long long n, int d, int k, long long id_offset,
               float* out_scores, long long* out_idx, void* ws, size_t ws_bytes, void* stream);
-int merge_run(const float* scores, const long long* idx, int W, long long nq, int k, float* out_scores,
+int merge_run(const float* scores, const long long* idx, int W, long long nq, int k, long long ws_s, long long ws_i,
+              float* out_scores,
               long long* out_idx, void* stream);
 
 }  // namespace ldot

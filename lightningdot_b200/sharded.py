@@ -6,8 +6,13 @@ split by ROWS over the ranks of a torch.distributed group (one process per GPU):
 global.  A search is
 
     every rank:  exact top-k of ALL queries against ITS rows      (fused score + top-k kernel, exact rescoring)
-    exchange:    all-gather of the per-shard (score fp32, id int64) [nq, k] lists  (NCCL over NVLink; 12 B * nq * k per rank)
-    every rank:  k best of the W * k candidates per query, ranked (score desc, id asc)   (ldot_topk_merge)
+    exchange 1:  all-to-all: rank j receives every shard's (score fp32, id int64) lists for ITS slice of nq / W queries,
+                 scores and ids of a shard packed in one buffer (ONE collective, 12 B * nq * k / W per pair)
+    every rank:  k best of the W * k candidates of its nq / W queries, ranked (score desc, id asc)   (ldot_topk_merge)
+    exchange 2:  all-gather of the merged slices -> the full [nq, k] result on every rank
+  (Gathering all W * nq lists on every rank and merging all nq queries W times over - the first version - moved W times
+  the bytes and did W times the merge work.)  Nothing synchronises with the host in between: the per-shard "certificate
+  failed" counts are combined with one 4-byte all-reduce and looked at after the merge has been queued.
 
 The union of the shard top-k lists contains the global top-k, and every shard list is exact, so the merged result
 equals the single-index result bit for bit.  `index_id_to_db_id` is replicated on every rank (host memory).
@@ -114,33 +119,97 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         dist.all_gather(parts, t, group=self.group)
         return [int(p.item()) for p in parts]
 
-    def search_device(self, queries, k):
+    def search_device(self, queries, k, lazy_flags=False):
         """queries: the full [nq, d] matrix (same on every rank), on this rank's device -> merged (scores [nq, k]
-        fp32, global row ids [nq, k] int64), identical on every rank."""
-        ls, li = self._local_search(queries, k)
+        fp32, global row ids [nq, k] int64), identical on every rank.
+
+        lazy_flags=True queues everything without a host synchronisation and leaves the (rare) uncertified-query check to
+        the caller: `self.pending_flags()` -> number of queries, over all shards, whose result must be recomputed with
+        `search_device(queries, k)`."""
         if self.world == 1:
-            return ls, li
-        nq = queries.shape[0]
+            return self._local_search(queries, k)
+        ls, li, n_flag = self._local_search(queries, k, defer=True)
+        self._pending = n_flag
+        nq, W = queries.shape[0], self.world
+        m = (nq + W - 1) // W              # queries merged by one rank
+        if (m * k) % 2:                    # (the packed layout needs the id block 8-byte aligned)
+            m += 1
+        dev, nb = ls.device, 12 * m * k    # bytes of one (rank, slice) block: scores fp32 | ids int64
+        send = torch.empty((W, nb), dtype=torch.uint8, device=dev)
+        s_view = send[:, :4 * m * k].view(torch.float32).view(W, m, k)      # [destination rank, query in its slice, k]
+        i_view = send[:, 4 * m * k:].view(torch.int64).view(W, m, k)
+        whole, rest = divmod(nq, m)
+        if whole:
+            s_view[:whole].copy_(ls[:whole * m].view(whole, m, k))
+            i_view[:whole].copy_(li[:whole * m].view(whole, m, k))
+        if whole < W:                      # the last slices are short or empty: padding entries rank below everything
+            s_view[whole:].fill_(torch.finfo(torch.float32).min)
+            i_view[whole:].fill_(-1)
+            if rest:
+                s_view[whole, :rest].copy_(ls[whole * m:])
+                i_view[whole, :rest].copy_(li[whole * m:])
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
+        mine = torch.empty((nb,), dtype=torch.uint8, device=dev)      # merged slice, same packed layout
+        self._merge_packed(recv, W, m, k, mine)
+        full = torch.empty((W, nb), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(full.view(-1), mine, group=self.group)
+        out_s = full[:, :4 * m * k].view(torch.float32).view(W, m, k).reshape(W * m, k)[:nq]
+        out_i = full[:, 4 * m * k:].view(torch.int64).view(W, m, k).reshape(W * m, k)[:nq]
+        if n_flag is not None:
+            dist.all_reduce(n_flag, op=dist.ReduceOp.MAX, group=self.group)
+        if not lazy_flags and self.pending_flags():
+            # some shard could not certify a query with the default candidate-list width: redo the search with the
+            # per-shard fallbacks (wider list, exhaustive scan) resolved before the exchange - every rank takes this branch
+            ls, li = self._local_search(queries, k)
+            return self._exchange_dense(ls, li, k)
+        return out_s, out_i
+
+    def pending_flags(self):
+        """Uncertified queries (max over the shards) of the last lazy search; synchronises with the device."""
+        n = getattr(self, "_pending", None)
+        self._pending = None
+        return 0 if n is None else int(n.item())
+
+    def _exchange_dense(self, ls, li, k):
+        """The simple protocol (all-gather of every shard's full lists, merge of all queries on every rank): the fallback."""
+        nq = ls.shape[0]
         gs = torch.empty((self.world, nq, k), dtype=torch.float32, device=ls.device)
         gi = torch.empty((self.world, nq, k), dtype=torch.int64, device=ls.device)
-        # one collective each, straight into the [W, nq, k] buffers (gloo in the CPU tests accepts the same calls)
         dist.all_gather_into_tensor(gs.view(self.world * nq, k), ls.contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi.view(self.world * nq, k), li.contiguous(), group=self.group)
         return self._merge(gs, gi, k)
 
-    def _local_search(self, queries, k):
+    def _local_search(self, queries, k, defer=False):
+        """This shard's exact top-k.  defer=True: no host synchronisation; -> (scores, ids, flagged-count tensor [1] on the
+        device or None) - queries whose certificate failed keep their coarse-list result until the caller resolves them."""
         if self.index.ntotal == 0:  # more ranks than rows: an empty shard contributes nothing
             nq = queries.shape[0]
-            return (torch.full((nq, k), -3.4028235e38, dtype=torch.float32, device=queries.device),
-                    torch.full((nq, k), -1, dtype=torch.int64, device=queries.device))
-        return self.index.search_device(queries, k)
+            out = (torch.full((nq, k), -3.4028235e38, dtype=torch.float32, device=queries.device),
+                   torch.full((nq, k), -1, dtype=torch.int64, device=queries.device))
+            return out + (torch.zeros(1, dtype=torch.int32, device=queries.device),) if defer else out
+        if not defer:
+            return self.index.search_device(queries, k)
+        s, i, flags, _ = self.index.search_device(queries, k, resolve_flags=False, return_flags=True)
+        return s, i, flags.sum(dtype=torch.int32).reshape(1)
+
+    def _merge_packed(self, recv, W, m, k, out):
+        """recv [W, 12 m k] bytes: shard w's (scores fp32 [m, k] | ids int64 [m, k]) for this rank's query slice -> `out`
+        [12 m k] bytes in the same layout."""
+        lib = _lib.load()
+        nb = 12 * m * k
+        o_s = out[:4 * m * k].view(torch.float32)
+        o_i = out[4 * m * k:].view(torch.int64)
+        base = recv.data_ptr()
+        _lib.check(lib.ldot_topk_merge(_lib.c_void_p(base), _lib.c_void_p(base + 4 * m * k), W, m, k, nb // 4, nb // 8,
+                                       _lib.ptr(o_s), _lib.ptr(o_i), _lib.stream_ptr()))
 
     def _merge(self, gs, gi, k):
         lib = _lib.load()
         world, nq, _ = gs.shape
         out_s = torch.empty((nq, k), dtype=torch.float32, device=gs.device)
         out_i = torch.empty((nq, k), dtype=torch.int64, device=gs.device)
-        _lib.check(lib.ldot_topk_merge(_lib.ptr(gs), _lib.ptr(gi), world, nq, k, _lib.ptr(out_s), _lib.ptr(out_i),
+        _lib.check(lib.ldot_topk_merge(_lib.ptr(gs), _lib.ptr(gi), world, nq, k, 0, 0, _lib.ptr(out_s), _lib.ptr(out_i),
                                        _lib.stream_ptr()))
         return out_s, out_i
 
@@ -152,15 +221,20 @@ class ShardedFlatIndexer(DenseFlatIndexer):
     def _device(self):
         return self.index._device()
 
-    def search(self, query_vectors, k: int):
+    def search(self, query_vectors, k: int, host_rank=None):
         """faiss-level call (IndexFlatIP.search, faiss_indexers.py:83) over the sharded index:
-        -> (scores float32 [nq, k], global row labels int64 [nq, k]) numpy arrays."""
+        -> (scores float32 [nq, k], global row labels int64 [nq, k]) numpy arrays.  host_rank=r: only rank r pays for the
+        device -> host copy and gets the arrays (the others return None) - one consumer, as in a served deployment."""
         scores, idx = self.search_device(self._queries_on_device(query_vectors), k)
+        if host_rank is not None and host_rank != self.rank:
+            return None
         return self._to_host(scores, idx)
 
     def _to_host(self, scores, idx):
         return self.index.to_host(scores, idx)
 
-    def search_knn(self, query_vectors, top_docs: int):
+    def search_knn(self, query_vectors, top_docs: int, host_rank=None):
         scores, idx = self.search_device(self._queries_on_device(query_vectors), top_docs)
+        if host_rank is not None and host_rank != self.rank:
+            return None
         return self._format_result(*self._to_host(scores, idx))

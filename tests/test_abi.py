@@ -30,9 +30,9 @@ def test_binding_covers_header():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 5
     # argument validation happens before any CUDA call, so it is testable without a GPU
-    rc = lib.ldot_topk_merge(None, None, 2, 4, 10, None, None, None)
+    rc = lib.ldot_topk_merge(None, None, 2, 4, 10, 0, 0, None, None, None)
     assert rc == -1
     assert b"null pointer" in lib.ldot_last_error()
     assert lib.ldot_flatip_search_workspace_bytes(10, 1000, 770, 10, 0) == 0   # d not a multiple of 8

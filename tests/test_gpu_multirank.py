@@ -61,6 +61,13 @@ def _search_worker(rank, world, port, tmp):
         one.index_matrix(ids, torch.from_numpy(x).cuda())
         s_1, i_1 = one.index.search_device(qd, k)
         assert torch.equal(i_sh, i_1) and torch.equal(s_sh, s_1)
+        for nq2, k2 in ((5, 7), (1, 1), (64, 33)):     # odd slice sizes (padding of the packed exchange), fewer queries than ranks
+            a_s, a_i = sh.search_device(qd[:nq2].contiguous(), k2)
+            b_s, b_i = one.index.search_device(qd[:nq2].contiguous(), k2)
+            assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s), (nq2, k2)
+        l_s, l_i = sh.search_device(qd, k, lazy_flags=True)
+        assert sh.pending_flags() == 0 and torch.equal(l_i, i_1) and torch.equal(l_s, s_1)
+        assert (sh.search(q[:9], 10, host_rank=0) is None) == (rank != 0)
         res = sh.search_knn(q[:7], 10)
         ref = one.search_knn(q[:7], 10)
         assert [r[0] for r in res] == [r[0] for r in ref]

@@ -146,7 +146,7 @@ def test_topk_merge_kernel_vs_oracle(cuda_lib, world, nq, k):
     ds, di = torch.from_numpy(gs).cuda(), torch.from_numpy(gi).cuda()
     out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
-    _lib.check(lib.ldot_topk_merge(_lib.ptr(ds), _lib.ptr(di), world, nq, k, _lib.ptr(out_s), _lib.ptr(out_i),
+    _lib.check(lib.ldot_topk_merge(_lib.ptr(ds), _lib.ptr(di), world, nq, k, 0, 0, _lib.ptr(out_s), _lib.ptr(out_i),
                                    _lib.stream_ptr()))
     os_, oi = flatip.search(q, x, k)
     assert np.array_equal(out_i.cpu().numpy(), oi) and np.array_equal(out_s.cpu().numpy(), os_)

@@ -153,6 +153,19 @@ class _CpuSharded(sharded.ShardedFlatIndexer):
     def _make_local_index(self, row_offset):
         return _OracleLocalIndex(self.vector_sz, row_offset=row_offset)
 
+    def _local_search(self, queries, k, defer=False):
+        s, i = self.index.search_device(queries, k) if self.index.ntotal else \
+            (torch.full((queries.shape[0], k), -3.4028235e38), torch.full((queries.shape[0], k), -1, dtype=torch.int64))
+        return (s, i, torch.zeros(1, dtype=torch.int32)) if defer else (s, i)
+
+    def _merge_packed(self, recv, W, m, k, out):
+        # the packed exchange layout of sharded.py: per shard (scores fp32 [m, k] | ids int64 [m, k]) as bytes
+        gs = recv[:, :4 * m * k].contiguous().view(torch.float32).view(W, m, k)
+        gi = recv[:, 4 * m * k:].contiguous().view(torch.int64).view(W, m, k)
+        s, i = self._merge(gs, gi, k)
+        out[:4 * m * k].view(torch.float32).copy_(s.reshape(-1))
+        out[4 * m * k:].view(torch.int64).copy_(i.reshape(-1))
+
     def _merge(self, gs, gi, k):
         # (score desc, id asc) over the W * k gathered candidates of every query - what ldot_topk_merge does
         world, nq, _ = gs.shape
