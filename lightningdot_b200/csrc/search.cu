@@ -451,7 +451,7 @@ struct RescoreParams {
   int d, k, kprime, kp_pad;
 };
 
-__global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
+__global__ void __launch_bounds__(1024) rescore_kernel(const RescoreParams p) {
   extern __shared__ unsigned long long rs_smem[];
   unsigned long long* keys = rs_smem;                              // [kp_pad]
   float4* qs = reinterpret_cast<float4*>(rs_smem + p.kp_pad);      // [d / 4]
@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(256) rescore_kernel(const RescoreParams p) {
   for (int i = p.kprime + threadIdx.x; i < p.kp_pad; i += blockDim.x) keys[i] = 0ull;
   __syncthreads();
   const int* cand = p.sel_idx + static_cast<size_t>(q) * p.kprime;
-  for (int j = warp; j < p.kprime; j += 8) {
+  const int nwarps = blockDim.x >> 5;
+  for (int j = warp; j < p.kprime; j += nwarps) {
     const int id = cand[j];
     if (id < 0) {
       if (lane == 0) keys[j] = 0ull;
@@ -776,7 +777,18 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   // Units = m_tiles x chunks, dealt round-robin to one persistent CTA per SM.  Pick the chunk count that fills the
   // last wave best; prefer long chunks (>= 4096 index rows: fewer candidate lists, fewer list compactions) and, on
   // ties, fewer chunks.
-  const int min_tpu = 4096 / pl->bn;
+  int min_tpu = 4096 / pl->bn;
+  // ... unless the index (shard) is so small that long chunks would leave SMs without a unit: 125 k rows in 4096-row
+  // chunks are 28 units on 148 SMs (81 us for the 128-query pass, measured); down to 512-row chunks when units are scarce
+  {
+    const long long units_long = static_cast<long long>(pl->m_tiles) * (pl->n_tiles / min_tpu > 0 ? pl->n_tiles / min_tpu : 1);
+    if (units_long < sms) {
+      int t = static_cast<int>((static_cast<long long>(pl->m_tiles) * pl->n_tiles + sms - 1) / sms);
+      const int floor_tpu = 512 / pl->bn > 0 ? 512 / pl->bn : 1;
+      if (t < floor_tpu) t = floor_tpu;
+      if (t < min_tpu) min_tpu = t;
+    }
+  }
   int max_chunks = pl->n_tiles / min_tpu;
   if (max_chunks < 1) max_chunks = 1;
   if (max_chunks > 2048) max_chunks = 2048;
@@ -821,6 +833,8 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   {
     int stride = kp / 2;
     if (stride > pl->n_tiles / 64) stride = pl->n_tiles / 64;  // at least 64 sample tiles (4096 rows)
+    // (skipping the pre-pass for small shards was measured: 125 k rows x 128 queries 59 -> 782 us - without an initial
+    // threshold every list is compacted several times per unit)
     if (stride >= 2 && stride * 10 >= kp) {
       pl->sample = 1;
       pl->s_stride = stride;
@@ -1126,7 +1140,9 @@ int search_run(const SearchArgs& a) {
   const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
   {
     KernelScope ks(kKcRescore, st, 2.0 * nq * pl.kprime * a.d, static_cast<double>(nq) * pl.kprime * a.d * 4.0);
-    rescore_kernel<<<nq, 256, rs_smem, st>>>(rp);
+    // one block per query; each warp gathers its candidates' fp32 rows one after the other, so a small batch (online
+    // regime: fewer blocks than the machine has room for) gets 32 warps per block - 5 dependent row gathers instead of 20
+    rescore_kernel<<<nq, nq <= 4 * sms ? 1024 : 256, rs_smem, st>>>(rp);
   }
   LDOT_CHECK_LAUNCH();
   if (a.out_flag_count)

@@ -94,6 +94,18 @@ def random_tower_state(kind, seed=42, perturb=False, **shape_kw):
     return out
 
 
+def conditioned_tower_state(kind, seed=42, head_scale=0.1, **shape_kw):
+    """random_tower_state(perturb=True) with the last projection (encode_proj.3) scaled by `head_scale`.  Random-init
+    embeddings have norm ~22, so in-batch scores differ by several units and the softmax of the loss turns 16-bit score
+    noise (0.2 units in bf16) into ~15 % gradient changes - a property of the random model, not of the kernels.  Scaling
+    the head by 0.1 divides the scores by 100: the loss keeps every term of its arithmetic but is well conditioned, so a
+    whole training step can be compared with the reference at the precision of the backward kernels themselves."""
+    sd = random_tower_state(kind, seed=seed, perturb=True, **shape_kw)
+    sd["encode_proj.3.weight"] = sd["encode_proj.3.weight"] * head_scale
+    sd["encode_proj.3.bias"] = sd["encode_proj.3.bias"] * head_scale
+    return sd
+
+
 def text_batch(batch, seq_len=32, seed=0, ragged=False, min_len=8, vocab=VOCAB):
     """'txts' sub-batch of itm_fast_collate (dvl/data/itm.py:230-246): [CLS]=101 ... [SEP]=102, zero padded."""
     g = torch.Generator().manual_seed(seed)

@@ -97,13 +97,17 @@ def loss_case():
                         loss1=l1.numpy(), correct1=np.array(int(c1)), scores0=s0.numpy(), scores1=s1.numpy())
 
 
-def train_case(name, layers, seed, batch):
+def train_case(name, layers, seed, batch, head_scale=None):
     """One train_itm.py step (train_itm.py:191-222,252-258) by the reference modules: forward of both towers, the two
     _calc_loss calls, 0.5 / 0.5 mix, loss.backward().  eval() mode: dropout off, so the step is deterministic."""
     from dvl.models.bi_encoder import BiEncoderNllLoss
     from dvl.utils import _calc_loss
-    sd_t = synth.random_tower_state("txt", seed=seed, perturb=True, layers=layers)
-    sd_i = synth.random_tower_state("img", seed=seed + 1, perturb=True, layers=layers)
+    if head_scale is None:
+        sd_t = synth.random_tower_state("txt", seed=seed, perturb=True, layers=layers)
+        sd_i = synth.random_tower_state("img", seed=seed + 1, perturb=True, layers=layers)
+    else:   # well-conditioned in-batch loss (synth.conditioned_tower_state): pins the whole step at kernel precision
+        sd_t = synth.conditioned_tower_state("txt", seed=seed, head_scale=head_scale, layers=layers)
+        sd_i = synth.conditioned_tower_state("img", seed=seed + 1, head_scale=head_scale, layers=layers)
     mt, mi = build_reference_tower("txt", layers, sd_t), build_reference_tower("img", layers, sd_i)
     tb = synth.text_batch(batch, 32, seed=seed, ragged=True)
     ib = synth.image_batch(batch, 36, seed=seed, ragged=True)
@@ -143,6 +147,7 @@ def train_case(name, layers, seed, batch):
     print(f"[train {name}] reference loss {loss.item():.6f}; oracle gradients match the reference's "
           f"(worst relative L2 error {worst:.2e}) over {len(out['txt_names'])} + {len(out['img_names'])} tensors")
     out["meta"] = np.array([layers, seed, batch])
+    out["head_scale"] = np.array(0.0 if head_scale is None else head_scale)
     np.savez_compressed(os.path.join(GOLD, f"train_step_{name}.npz"), **out)
 
 
@@ -446,6 +451,7 @@ def main():
         tower_case(*case)
     loss_case()
     train_case("l2", 2, 201, 6)
+    train_case("l4c", 4, 401, 64, head_scale=0.1)
     indexer_case()
     evalloop_case()
     options_case()
