@@ -75,6 +75,22 @@ int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const voi
                        int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, void* stream);
 
 /* Exhaustive fp64-accumulated scan (no tensor cores): the fallback for flagged queries; same outputs/ranking. */
+/* Row-SHARDED search in two phases over the same workspace (lightningdot_b200/sharded.py): every shard runs phase 1,
+ * the shards take the MINIMUM of their d_bound vectors (one all-reduce of nq floats), every shard runs phase 2.
+ *   phase 1  query prepare .. candidate selection; d_bound[q] = a score that at least bound_m rows of THIS shard reach
+ *            (bound_m-th best coarse score + q.mu - error bound; -inf if the shard holds fewer rows).  With
+ *            world * bound_m >= k the minimum over the shards is a lower bound tau[q] of the global k-th best score.
+ *   phase 2  exact rescoring of the candidates that can reach d_tau[q], ranking, certificate (a query is certified when
+ *            the usual local condition holds OR no row outside the candidate list can reach tau); fewer than k rows may
+ *            survive: the tail of the list is (-FLT_MAX, -1), which ldot_topk_merge skips.
+ *   phase 0  the whole search in one call (== ldot_flatip_search; d_bound / d_tau unused).
+ * Arguments as ldot_flatip_search; the workspace must not be touched between the phases.                            */
+int ldot_flatip_search_phase(const float* d_q, int64_t nq, const float* d_x, const void* d_x16, const float* d_mu,
+                             const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,
+                             int32_t coarse_dtype, int64_t id_offset, float* d_out_scores, int64_t* d_out_idx,
+                             int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, int32_t phase,
+                             int32_t bound_m, float* d_bound, const float* d_tau, void* stream);
+
 size_t ldot_flatip_exact_workspace_bytes(int64_t n);
 int ldot_flatip_exact(const float* d_q, int64_t nq, const float* d_x, int64_t n, int32_t d, int32_t k,
                       int64_t id_offset, float* d_out_scores, int64_t* d_out_idx, void* d_ws, size_t ws_bytes,

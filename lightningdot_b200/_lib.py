@@ -55,6 +55,9 @@ SIGNATURES = {
     "ldot_flatip_search": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                      c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_size_t, c_void_p]),
+    "ldot_flatip_search_phase": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
+                                           c_int32, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_size_t, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "ldot_flatip_exact_workspace_bytes": (c_size_t, [c_int64]),
     "ldot_flatip_exact": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_int32, c_int32, c_int64, c_void_p,
                                     c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -295,8 +295,18 @@ int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const voi
                        const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,
                        int32_t coarse_dtype, int64_t id_offset, float* d_out_scores, int64_t* d_out_idx,
                        int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, void* stream) {
+  return ldot_flatip_search_phase(d_q, nq, d_x, d_x16, d_mu, d_xstats, n, d, k, coarse_k, coarse_dtype, id_offset, d_out_scores,
+                                  d_out_idx, d_out_flags, d_out_flag_count, d_ws, ws_bytes, 0, 0, nullptr, nullptr, stream);
+}
+
+int ldot_flatip_search_phase(const float* d_q, int64_t nq, const float* d_x, const void* d_x16, const float* d_mu,
+                             const float* d_xstats, int64_t n, int32_t d, int32_t k, int32_t coarse_k,
+                             int32_t coarse_dtype, int64_t id_offset, float* d_out_scores, int64_t* d_out_idx,
+                             int32_t* d_out_flags, int32_t* d_out_flag_count, void* d_ws, size_t ws_bytes, int32_t phase,
+                             int32_t bound_m, float* d_bound, const float* d_tau, void* stream) {
   LDOT_REQUIRE(d_q && d_x && d_x16 && d_mu && d_xstats && d_out_scores && d_out_idx && d_out_flags && d_ws,
                "null pointer argument");
+  LDOT_REQUIRE(phase >= 0 && phase <= 2, "phase must be 0 (whole search), 1 (through select + bound) or 2 (rescore)");
   static_assert(sizeof(long long) == sizeof(int64_t), "int64 layout");
   SearchArgs a;
   a.q = d_q;
@@ -318,6 +328,10 @@ int ldot_flatip_search(const float* d_q, int64_t nq, const float* d_x, const voi
   a.ws = d_ws;
   a.ws_bytes = ws_bytes;
   a.stream = stream;
+  a.phase = phase;
+  a.bound_m = bound_m;
+  a.bound_out = d_bound;
+  a.tau = d_tau;
   return search_run(a);
 }
 

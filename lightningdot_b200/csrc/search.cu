@@ -275,7 +275,8 @@ struct SelLists {
 __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const unsigned int* __restrict__ gtau, int kprime,
                                                      int final, unsigned long long* __restrict__ out_ent,
                                                      int* __restrict__ out_cnt, int* __restrict__ sel_idx,
-                                                     float* __restrict__ sel_cmin, unsigned int* __restrict__ tau_out) {
+                                                     float* __restrict__ sel_cmin, unsigned int* __restrict__ tau_out,
+                                                     unsigned int* __restrict__ sel_key) {
   extern __shared__ unsigned long long sel_smem[];
   unsigned long long* stage = sel_smem;  // [kSelStage]
   __shared__ int cnts[kSelGroup];
@@ -297,9 +298,14 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
   auto list_of = [&](int c) { return in.ent + (c0 + c) * in.ent_sc + q * in.ent_sq; };
   unsigned long long* oent = final ? nullptr : out_ent + (static_cast<size_t>(q) * groups + g) * kprime;
   int* oidx = final ? sel_idx + static_cast<size_t>(q) * kprime : nullptr;
+  unsigned int* okey = (final && sel_key) ? sel_key + static_cast<size_t>(q) * kprime : nullptr;   // coarse keys, same order
   auto emit = [&](int pos, unsigned long long e) {
-    if (final) oidx[pos] = static_cast<int>(e & 0xFFFFFFFFu);
-    else oent[pos] = e;
+    if (final) {
+      oidx[pos] = static_cast<int>(e & 0xFFFFFFFFu);
+      if (okey) okey[pos] = entry_key(e);
+    } else {
+      oent[pos] = e;
+    }
   };
 
   if (L < kprime) {
@@ -312,7 +318,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
     }
     if (final) {
       __syncthreads();
-      for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
+      for (int i = L + threadIdx.x; i < kprime; i += blockDim.x) {
+        oidx[i] = -1;
+        if (okey) okey[i] = 0u;
+      }
       if (threadIdx.x == 0) {
         const uint32_t g = gtau[q];
         sel_cmin[q] = g > kKeyNegInf ? fkey_inv(g) : -INFINITY;
@@ -354,7 +363,10 @@ __global__ void __launch_bounds__(256) select_kernel(const SelLists in, const un
     // only possible in a non-final group that does not hold the list that set gtau: nothing >= gtau was dropped
     if (!final && threadIdx.x == 0) out_cnt[q * groups + g] = ns;
     if (final) {  // cannot happen (the union holds the list that set gtau); keep the output well-formed anyway
-      for (int i = ns + threadIdx.x; i < kprime; i += blockDim.x) oidx[i] = -1;
+      for (int i = ns + threadIdx.x; i < kprime; i += blockDim.x) {
+        oidx[i] = -1;
+        if (okey) okey[i] = 0u;
+      }
       if (threadIdx.x == 0) {
         sel_cmin[q] = fkey_inv(floor_key);
         if (tau_out) tau_out[q] = 0u;
@@ -440,6 +452,8 @@ struct RescoreParams {
   const float* x;        // [n, d] fp32 master index
   const int* sel_idx;    // [nq, kprime] candidate rows (-1 = none)
   const float* sel_cmin; // [nq]
+  const unsigned int* sel_key;  // [nq, kprime] coarse keys of the candidates (same order as sel_idx)
+  const float* tau;      // [nq] or null: a lower bound of the GLOBAL k-th best exact score (sharded search, phase 2)
   const float* qstats;   // [nq, 2]: |q16|, |q - q16|
   const double* qmu;     // [nq]: q . mu
   const float* xstats;   // [2]: max_j |x'_j - x16_j|, max_j |x16_j|
@@ -450,6 +464,49 @@ struct RescoreParams {
   long long id_offset;   // added to every returned row id (shard offset)
   int d, k, kprime, kp_pad;
 };
+
+// |exact centred score - coarse score| <= E: rounding of x, rounding of q (+ cross term), tensor-core fp32 accumulation
+// (d additions, each within 2^-22 of the running sum of |products| <= |q16| |x16|: twice the bound of a truncating adder)
+__device__ __forceinline__ double coarse_error_bound(const float* qstats, const float* xstats, int q, int d) {
+  const double nq16 = qstats[2 * q], rq = qstats[2 * q + 1];
+  const double rmax = xstats[0], xmax = xstats[1];
+  return nq16 * rmax + rq * (xmax + rmax) + d * 2.384185791015625e-07 * nq16 * xmax;
+}
+
+// Sharded search, phase 1 -> phase 2 hand-off.  bound[q] = a value that at least m rows of THIS shard reach in exact
+// score: (m-th best coarse score of the candidate list) + q.mu - E.  Over W shards with W m >= k, the minimum of the
+// bounds is a lower bound of the global k-th best exact score (k rows reach it), so a shard only has to rescore - and
+// only has to have kept - rows whose exact score can reach that minimum.  -inf when the list holds fewer than m rows.
+__global__ void __launch_bounds__(256) shard_bound_kernel(const unsigned int* __restrict__ sel_key, const float* __restrict__ qstats,
+                                                          const double* __restrict__ qmu, const float* __restrict__ xstats,
+                                                          int kprime, int m, int d, float* __restrict__ bound) {
+  extern __shared__ unsigned int sb_keys[];
+  __shared__ unsigned int found;
+  const int q = blockIdx.x;
+  for (int i = threadIdx.x; i < kprime; i += blockDim.x) sb_keys[i] = sel_key[static_cast<size_t>(q) * kprime + i];
+  if (threadIdx.x == 0) found = 0u;
+  __syncthreads();
+  // rank by counting: the entry with exactly m - 1 entries ahead of it (ties broken by position) is the m-th best
+  for (int i = threadIdx.x; i < kprime; i += blockDim.x) {
+    const unsigned int key = sb_keys[i];
+    if (key == 0u) continue;
+    int ahead = 0;
+    for (int j = 0; j < kprime; ++j) ahead += (sb_keys[j] > key) || (sb_keys[j] == key && j < i);
+    if (ahead == m - 1) found = key;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float b = -INFINITY;
+    if (found > kKeyNegInf) {
+      const double c = static_cast<double>(fkey_inv(found));
+      const double E = coarse_error_bound(qstats, xstats, q, d);
+      const double v = c + qmu[q] - E * 1.0001;
+      b = static_cast<float>(v - 1.1920928955078125e-07 * (fabs(v) + 1e-30) - 1e-30);   // round towards -inf
+      if (static_cast<double>(b) > v) b = nextafterf(b, -INFINITY);
+    }
+    bound[q] = b;
+  }
+}
 
 __global__ void __launch_bounds__(1024) rescore_kernel(const RescoreParams p) {
   extern __shared__ unsigned long long rs_smem[];
@@ -464,9 +521,18 @@ __global__ void __launch_bounds__(1024) rescore_kernel(const RescoreParams p) {
   __syncthreads();
   const int* cand = p.sel_idx + static_cast<size_t>(q) * p.kprime;
   const int nwarps = blockDim.x >> 5;
+  // sharded search: a candidate whose exact score cannot reach the global lower bound tau is not rescored
+  const bool pruned = p.tau != nullptr && p.tau[q] > -INFINITY;
+  const double reach = pruned ? coarse_error_bound(p.qstats, p.xstats, q, p.d) * 1.0001 + p.qmu[q] : 0.0;
+  const double tau = pruned ? static_cast<double>(p.tau[q]) : 0.0;
   for (int j = warp; j < p.kprime; j += nwarps) {
     const int id = cand[j];
-    if (id < 0) {
+    bool skip = id < 0;
+    if (!skip && pruned) {
+      const double up = static_cast<double>(fkey_inv(p.sel_key[static_cast<size_t>(q) * p.kprime + j])) + reach;
+      skip = up + 1.1920928955078125e-07 * fabs(up) < tau;
+    }
+    if (skip) {
       if (lane == 0) keys[j] = 0ull;
       continue;
     }
@@ -489,17 +555,15 @@ __global__ void __launch_bounds__(1024) rescore_kernel(const RescoreParams p) {
     bool certified;
     if (cmin == -INFINITY) {
       certified = true;  // no row was dropped anywhere
+    } else if (pruned && static_cast<double>(cmin) + reach + 1.1920928955078125e-07 * fabs(static_cast<double>(cmin) + reach) < tau) {
+      certified = true;  // no row outside the list can reach the global k-th best score: this shard's list is complete
     } else {
       const unsigned long long kk = keys[p.k - 1];
       if (kk == 0ull) {
         certified = false;
       } else {
         const double sk = static_cast<double>(rank_key_score(kk));
-        const double nq16 = p.qstats[2 * q], rq = p.qstats[2 * q + 1];
-        const double rmax = p.xstats[0], xmax = p.xstats[1];
-        // rounding of x, rounding of q (+ cross term), tensor-core fp32 accumulation: d additions, each within
-        // 2^-22 of the running sum of |products| <= |q16| |x16| (twice the bound of a truncating fp32 adder)
-        const double E = nq16 * rmax + rq * (xmax + rmax) + p.d * 2.384185791015625e-07 * nq16 * xmax;
+        const double E = coarse_error_bound(p.qstats, p.xstats, q, p.d);
         const double slack = 1.1920928955078125e-07 * (fabs(sk) + fabs(p.qmu[q])) + 1e-30;
         certified = (sk - p.qmu[q] - slack) > (static_cast<double>(cmin) + E * 1.0001);
       }
@@ -861,6 +925,7 @@ int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, in
   pl->off_cnt = take(static_cast<size_t>(pl->num_units) * kBM * sizeof(int));
   pl->off_sel_idx = take(static_cast<size_t>(nq) * kp * sizeof(int));
   pl->off_sel_cmin = take(static_cast<size_t>(nq) * sizeof(float));
+  pl->off_sel_key = take(static_cast<size_t>(nq) * kp * sizeof(unsigned int));
   pl->off_l2_ent = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * kp * sizeof(unsigned long long) : 0);
   pl->off_l2_cnt = take(pl->groups > 1 ? static_cast<size_t>(nq) * pl->groups * sizeof(int) : 0);
   pl->off_cand = take(static_cast<size_t>(pl->num_units) * kBM * pl->cap * sizeof(unsigned long long));
@@ -968,10 +1033,46 @@ int search_run(const SearchArgs& a) {
   int* cnt = reinterpret_cast<int*>(ws + pl.off_cnt);
   int* sel_idx = reinterpret_cast<int*>(ws + pl.off_sel_idx);
   float* sel_cmin = reinterpret_cast<float*>(ws + pl.off_sel_cmin);
+  unsigned int* sel_key = reinterpret_cast<unsigned int*>(ws + pl.off_sel_key);
   unsigned long long* l2_ent = reinterpret_cast<unsigned long long*>(ws + pl.off_l2_ent);
   int* l2_cnt = reinterpret_cast<int*>(ws + pl.off_l2_cnt);
   unsigned long long* cand = reinterpret_cast<unsigned long long*>(ws + pl.off_cand);
   const int nq = static_cast<int>(a.nq);
+
+  // exact rescoring of the selected candidates + ranking + certificate (phase 2 of a sharded search starts here)
+  auto rescore_stage = [&]() -> int {
+  RescoreParams rp;
+    rp.q = a.q;
+    rp.x = a.x;
+    rp.sel_idx = sel_idx;
+    rp.sel_cmin = sel_cmin;
+    rp.sel_key = sel_key;
+    rp.tau = a.tau;
+    rp.qstats = qstats;
+    rp.qmu = qmu;
+    rp.xstats = a.xstats;
+    rp.out_scores = a.out_scores;
+    rp.out_idx = a.out_idx;
+    rp.flags = a.out_flags;
+    rp.flag_count = flagcnt;
+    rp.id_offset = a.id_offset;
+    rp.d = a.d;
+    rp.k = a.k;
+    rp.kprime = pl.kprime;
+    rp.kp_pad = pl.kp_pad;
+    const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
+    {
+      KernelScope ks(kKcRescore, st, 2.0 * nq * pl.kprime * a.d, static_cast<double>(nq) * pl.kprime * a.d * 4.0);
+      // one block per query; each warp gathers its candidates' fp32 rows one after the other, so a small batch (online
+      // regime: fewer blocks than the machine has room for) gets 32 warps per block - 5 dependent row gathers instead of 20
+      rescore_kernel<<<nq, nq <= 4 * sms ? 1024 : 256, rs_smem, st>>>(rp);
+    }
+    LDOT_CHECK_LAUNCH();
+    if (a.out_flag_count)
+      LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDefault, st));  // device or pinned host
+    return kOk;
+  };
+  if (a.phase == 2) return rescore_stage();
 
   // gtau and the flag counter are adjacent in the plan: one memset clears both
   float* tmax = reinterpret_cast<float*>(ws + pl.off_tmax);
@@ -1096,13 +1197,14 @@ int search_run(const SearchArgs& a) {
   const SelLists l1 = lists_of(pl.chunks, pl.cap);
   if (pl.groups == 1) {
     KernelScope ks(kKcSelect, st);
-    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr);
+    select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr,
+                                                      sel_key);
     LDOT_CHECK_LAUNCH();
   } else {
     {
       KernelScope ks(kKcSelect, st);
       select_kernel<<<dim3(nq, pl.groups), 256, sel_smem, st>>>(l1, gtau, pl.kprime, 0, l2_ent, l2_cnt, nullptr, nullptr,
-                                                                nullptr);
+                                                                nullptr, nullptr);
     }
     LDOT_CHECK_LAUNCH();
     SelLists l2;
@@ -1115,39 +1217,21 @@ int search_run(const SearchArgs& a) {
     l2.num_lists = pl.groups;
     {
       KernelScope ks(kKcSelect, st);
-      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr);
+      select_kernel<<<dim3(nq, 1), 256, sel_smem, st>>>(l2, gtau, pl.kprime, 1, nullptr, nullptr, sel_idx, sel_cmin, nullptr,
+                                                        sel_key);
     }
     LDOT_CHECK_LAUNCH();
   }
 
-  RescoreParams rp;
-  rp.q = a.q;
-  rp.x = a.x;
-  rp.sel_idx = sel_idx;
-  rp.sel_cmin = sel_cmin;
-  rp.qstats = qstats;
-  rp.qmu = qmu;
-  rp.xstats = a.xstats;
-  rp.out_scores = a.out_scores;
-  rp.out_idx = a.out_idx;
-  rp.flags = a.out_flags;
-  rp.flag_count = flagcnt;
-  rp.id_offset = a.id_offset;
-  rp.d = a.d;
-  rp.k = a.k;
-  rp.kprime = pl.kprime;
-  rp.kp_pad = pl.kp_pad;
-  const size_t rs_smem = pl.kp_pad * sizeof(unsigned long long) + static_cast<size_t>(a.d) * sizeof(float);
-  {
-    KernelScope ks(kKcRescore, st, 2.0 * nq * pl.kprime * a.d, static_cast<double>(nq) * pl.kprime * a.d * 4.0);
-    // one block per query; each warp gathers its candidates' fp32 rows one after the other, so a small batch (online
-    // regime: fewer blocks than the machine has room for) gets 32 warps per block - 5 dependent row gathers instead of 20
-    rescore_kernel<<<nq, nq <= 4 * sms ? 1024 : 256, rs_smem, st>>>(rp);
+  if (a.phase == 1) {   // sharded search: stop here and report what this shard can guarantee (see shard_bound_kernel)
+    LDOT_REQUIRE(a.bound_out != nullptr && a.bound_m >= 1 && a.bound_m <= pl.kprime, "phase 1 needs bound_out and 1 <= m <= k'");
+    KernelScope ks(kKcSelect, st);
+    shard_bound_kernel<<<nq, 256, pl.kprime * sizeof(unsigned int), st>>>(sel_key, qstats, qmu, a.xstats, pl.kprime, a.bound_m,
+                                                                          a.d, a.bound_out);
+    LDOT_CHECK_LAUNCH();
+    return kOk;
   }
-  LDOT_CHECK_LAUNCH();
-  if (a.out_flag_count)
-    LDOT_CUDA(cudaMemcpyAsync(a.out_flag_count, flagcnt, sizeof(int), cudaMemcpyDefault, st));  // device or pinned host
-  return kOk;
+  return rescore_stage();
 }
 
 size_t index_prepare_workspace_bytes(int d) { return align_up(static_cast<size_t>(d) * sizeof(double), 256); }

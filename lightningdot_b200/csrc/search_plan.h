@@ -23,7 +23,7 @@ struct SearchPlan {
   int s_tiles, s_tiles_per_unit, s_chunks, s_units;
   int s_kprime;        // the s_kprime-th best sample score of a query seeds its threshold
   size_t off_tmax;     // tile maxima of the pre-pass [m_tiles * 128][s_tiles] fp32
-  size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_l2_ent,
+  size_t off_q16, off_qstats, off_qmu, off_gtau, off_flagcnt, off_cnt, off_sel_idx, off_sel_cmin, off_sel_key, off_l2_ent,
       off_l2_cnt, off_cand;
   size_t total_bytes;
 };
@@ -45,6 +45,13 @@ struct SearchArgs {
   void* ws;
   size_t ws_bytes;
   void* stream;
+  // sharded search in two phases over the SAME workspace (0 = the whole search in one call):
+  //   1  query prepare .. select, then bound_out[q] = what bound_m rows of this shard are guaranteed to reach
+  //   2  rescore + rank + certificate, pruned by tau[q] (a lower bound of the global k-th best score; may be null)
+  int phase = 0;
+  int bound_m = 0;
+  float* bound_out = nullptr;
+  const float* tau = nullptr;
 };
 
 int search_make_plan(SearchPlan* pl, long long nq, long long n, int d, int k, int coarse_k, int sms);

@@ -205,6 +205,43 @@ class FlatIPIndex:
                 _lib.ptr(ws), need, stream))
         return counts
 
+    # -- two-phase form for a row-sharded index (sharded.py): phase 1 up to the candidate lists + a per-query bound the
+    # shards min-reduce, phase 2 rescoring pruned by that bound (include/ldot.h: ldot_flatip_search_phase)
+    def search_phase1(self, qd, k, bound_m):
+        """-> state for search_phase2; state['bound'] is the fp32 [nq] tensor the shards combine with a MIN all-reduce.
+        One C-ABI call: nq <= MAX_QUERY_BATCH."""
+        lib = _lib.load()
+        self._finalize()
+        nq, dev = qd.shape[0], qd.device
+        if not (1 <= nq <= MAX_QUERY_BATCH):
+            raise ValueError(f"search_phase1 takes 1 .. {MAX_QUERY_BATCH} queries, got {nq}")
+        st = dict(q=qd, k=k, scores=torch.empty((nq, k), dtype=torch.float32, device=dev),
+                  idx=torch.empty((nq, k), dtype=torch.int64, device=dev),
+                  flags=torch.empty((nq,), dtype=torch.int32, device=dev),
+                  count=torch.zeros((1,), dtype=torch.int32, device=dev),
+                  bound=torch.empty((nq,), dtype=torch.float32, device=dev))
+        need = lib.ldot_flatip_search_workspace_bytes(nq, self._n, self.d, k, self.coarse_k)
+        if need == 0:
+            raise _lib.LdotError(f"invalid search shape: {lib.ldot_last_error().decode()}")
+        st["ws"], st["need"] = self._ws.get(need, dev), need
+        self._phase_call(st, 1, bound_m, None)
+        return st
+
+    def search_phase2(self, st, tau):
+        """tau: fp32 [nq] lower bounds of the global k-th best score (or None: no pruning) -> (scores, idx, flags,
+        flagged-count tensor [1]) on the device; no host synchronisation."""
+        self._phase_call(st, 2, 0, tau)
+        return st["scores"], st["idx"], st["flags"], st["count"]
+
+    def _phase_call(self, st, phase, bound_m, tau):
+        lib = _lib.load()
+        qd, k = st["q"], st["k"]
+        _lib.check(lib.ldot_flatip_search_phase(
+            _lib.ptr(qd), qd.shape[0], _lib.ptr(self._x), _lib.ptr(self._x16), _lib.ptr(self._mu), _lib.ptr(self._xstats),
+            self._n, self.d, k, self.coarse_k, self.coarse_dtype, self.row_offset, _lib.ptr(st["scores"]),
+            _lib.ptr(st["idx"]), _lib.ptr(st["flags"]), _lib.ptr(st["count"]), _lib.ptr(st["ws"]), st["need"], phase, bound_m,
+            _lib.ptr(st["bound"]), _lib.ptr(tau), _lib.stream_ptr()))
+
     def exact_search_device(self, qd, k):
         """Exhaustive fp64-accumulated scan (no tensor cores) - the fallback path, also usable on its own."""
         lib = _lib.load()

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .indexer import MAX_QUERY_BATCH as MAX_PHASED_QUERIES
 from .indexer import DenseFlatIndexer, FlatIPIndex
 
 
@@ -128,7 +129,7 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         `search_device(queries, k)`."""
         if self.world == 1:
             return self._local_search(queries, k)
-        ls, li, n_flag = self._local_search(queries, k, defer=True)
+        ls, li, n_flag = self._local_search_pruned(queries, k)
         self._pending = n_flag
         nq, W = queries.shape[0], self.world
         m = (nq + W - 1) // W              # queries merged by one rank
@@ -192,6 +193,25 @@ class ShardedFlatIndexer(DenseFlatIndexer):
             return self.index.search_device(queries, k)
         s, i, flags, _ = self.index.search_device(queries, k, resolve_flags=False, return_flags=True)
         return s, i, flags.sum(dtype=torch.int32).reshape(1)
+
+    def _local_search_pruned(self, queries, k):
+        """This shard's contribution to the global top-k, with the rescoring sharded too: phase 1 (coarse pass + candidate
+        selection) yields, per query, a score that ceil(k / W) rows of this shard are guaranteed to reach; the MINIMUM over
+        the shards (one all-reduce of nq floats) is a lower bound of the global k-th best score, and phase 2 rescores only
+        the candidates that can reach it - about k / W + slack rows per query and shard instead of k' = 1.6 k.  Lists come
+        back ranked, shorter than k where fewer rows survive (tail = -FLT_MAX / -1).  Exactness does not depend on the
+        data: a query whose candidate list might be incomplete w.r.t. the bound is flagged as before."""
+        ix = self.index
+        if not hasattr(ix, "search_phase1") or not (1 <= queries.shape[0] <= MAX_PHASED_QUERIES):
+            return self._local_search(queries, k, defer=True)
+        if ix.ntotal == 0:   # an empty shard guarantees nothing: its bound is -inf (every rank joins the reduction)
+            none = torch.full((queries.shape[0],), float("-inf"), dtype=torch.float32, device=queries.device)
+            dist.all_reduce(none, op=dist.ReduceOp.MIN, group=self.group)
+            return self._local_search(queries, k, defer=True)
+        st = ix.search_phase1(queries, k, (k + self.world - 1) // self.world)
+        dist.all_reduce(st["bound"], op=dist.ReduceOp.MIN, group=self.group)
+        s, i, flags, count = ix.search_phase2(st, st["bound"])
+        return s, i, count
 
     def _merge_packed(self, recv, W, m, k, out):
         """recv [W, 12 m k] bytes: shard w's (scores fp32 [m, k] | ids int64 [m, k]) for this rank's query slice -> `out`

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from lightningdot_b200 import synth
+from lightningdot_b200 import _lib, synth
 from lightningdot_b200.indexer import DenseFlatIndexer, FlatIPIndex
 from oracle import flatip
 
@@ -146,3 +146,57 @@ def test_full_size_properties(cuda_lib):
     assert torch.equal(s2, s[:256])
     # scores are continuous random numbers: no exact ties, so ids map one-to-one through the permutation
     assert torch.equal(perm[i2], i[:256])
+
+
+@pytest.mark.parametrize("W,n,nq,k,kind", [(2, 40001, 257, 100, "gauss"), (8, 100003, 130, 100, "gauss"), (4, 30000, 64, 10, "collinear"),
+                                           (3, 5000, 33, 100, "ties"), (8, 900, 17, 100, "gauss")])
+def test_two_phase_sharded_search_equals_single_index(cuda_lib, W, n, nq, k, kind):
+    """The row-sharded search with sharded rescoring (ldot_flatip_search_phase), emulated on one GPU: W shard indexes with
+    their row offsets run phase 1, the per-query bounds are min-reduced, phase 2 rescores only what can reach the bound, and
+    ldot_topk_merge combines the (possibly short) lists.  Ids and scores must equal the single-index search and the
+    oracle bit for bit - gaussian rows, collinear rows (random-init-tower-like), exact duplicates, and shards smaller than k;
+    and the shards must really have pruned (far fewer than k exact rescorings survive per shard)."""
+    from lightningdot_b200.indexer import FlatIPIndex
+    from lightningdot_b200.sharded import shard_bounds
+    from oracle import flatip
+    d = 768
+    if kind == "collinear":
+        x = synth.collinear_index(n, d, seed=5)
+    else:
+        x = synth.gaussian_index(n, d, seed=5)
+    if kind == "ties":
+        x[100:140] = x[4000:4040]           # exact duplicates living in different shards
+        x[7] = x[4999]
+    q, _ = synth.planted_queries(x, nq, sigma=2.0, seed=6)
+    xd, qd = torch.from_numpy(x).cuda(), torch.from_numpy(q).cuda()
+    bounds = shard_bounds(n, W)
+    shards = []
+    for r in range(W):
+        ix = FlatIPIndex(d, row_offset=bounds[r])
+        ix.add(xd[bounds[r]:bounds[r + 1]])
+        shards.append(ix)
+    m = (k + W - 1) // W
+    states = [ix.search_phase1(qd, k, m) for ix in shards]
+    tau = torch.stack([st["bound"] for st in states]).min(dim=0).values
+    gs = torch.empty((W, nq, k), dtype=torch.float32, device="cuda")
+    gi = torch.empty((W, nq, k), dtype=torch.int64, device="cuda")
+    flagged = 0
+    for r, (ix, st) in enumerate(zip(shards, states)):
+        s, i, flags, count = ix.search_phase2(st, tau)
+        gs[r], gi[r] = s, i
+        flagged += int(count.item())
+    assert flagged == 0
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    out_i = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    _lib.check(cuda_lib.ldot_topk_merge(_lib.ptr(gs), _lib.ptr(gi), W, nq, k, 0, 0, _lib.ptr(out_s), _lib.ptr(out_i),
+                                        _lib.stream_ptr()))
+    one = FlatIPIndex(d)
+    one.add(xd)
+    ref_s, ref_i = one.search_device(qd, k)
+    assert torch.equal(out_i, ref_i) and torch.equal(out_s, ref_s)
+    os_, oi = flatip.search(q, x, k)
+    assert np.array_equal(out_i.cpu().numpy(), oi) and np.array_equal(out_s.cpu().numpy(), os_)
+    survivors = float((gi >= 0).sum()) / (W * nq)
+    print(f"W={W} n={n} k={k} {kind}: {survivors:.1f} rescored rows per (query, shard) instead of k' >= {k + max(k // 2, 32)}")
+    if n >= 8 * k * W:       # (big enough shards: the bound must bite - about k / W rows plus the error-bound slack)
+        assert survivors <= k / W + 0.2 * k, survivors
