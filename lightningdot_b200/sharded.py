@@ -130,7 +130,6 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         if self.world == 1:
             return self._local_search(queries, k)
         ls, li, n_flag = self._local_search_pruned(queries, k)
-        self._pending = n_flag
         nq, W = queries.shape[0], self.world
         m = (nq + W - 1) // W              # queries merged by one rank
         if (m * k) % 2:                    # (the packed layout needs the id block 8-byte aligned)
@@ -151,14 +150,19 @@ class ShardedFlatIndexer(DenseFlatIndexer):
                 i_view[whole, :rest].copy_(li[whole * m:])
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv.view(-1), send.view(-1), group=self.group)
-        mine = torch.empty((nb,), dtype=torch.uint8, device=dev)      # merged slice, same packed layout
+        # merged slice in the same packed layout + 16 trailing bytes that carry this shard's uncertified-query count, so the
+        # second exchange also tells every rank whether ANY shard has to fall back (no extra collective, no host sync)
+        mine = torch.empty((nb + 16,), dtype=torch.uint8, device=dev)
         self._merge_packed(recv, W, m, k, mine)
-        full = torch.empty((W, nb), dtype=torch.uint8, device=dev)
+        tail = mine[nb:].view(torch.int32)
+        tail.zero_()
+        if n_flag is not None:
+            tail[:1].copy_(n_flag)
+        full = torch.empty((W, nb + 16), dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(full.view(-1), mine, group=self.group)
         out_s = full[:, :4 * m * k].view(torch.float32).view(W, m, k).reshape(W * m, k)[:nq]
-        out_i = full[:, 4 * m * k:].view(torch.int64).view(W, m, k).reshape(W * m, k)[:nq]
-        if n_flag is not None:
-            dist.all_reduce(n_flag, op=dist.ReduceOp.MAX, group=self.group)
+        out_i = full[:, 4 * m * k:nb].view(torch.int64).view(W, m, k).reshape(W * m, k)[:nq]
+        self._pending = full[:, nb:nb + 4].view(torch.int32).sum()
         if not lazy_flags and self.pending_flags():
             # some shard could not certify a query with the default candidate-list width: redo the search with the
             # per-shard fallbacks (wider list, exhaustive scan) resolved before the exchange - every rank takes this branch
@@ -219,7 +223,7 @@ class ShardedFlatIndexer(DenseFlatIndexer):
         lib = _lib.load()
         nb = 12 * m * k
         o_s = out[:4 * m * k].view(torch.float32)
-        o_i = out[4 * m * k:].view(torch.int64)
+        o_i = out[4 * m * k:nb].view(torch.int64)
         base = recv.data_ptr()
         _lib.check(lib.ldot_topk_merge(_lib.c_void_p(base), _lib.c_void_p(base + 4 * m * k), W, m, k, nb // 4, nb // 8,
                                        _lib.ptr(o_s), _lib.ptr(o_i), _lib.stream_ptr()))

@@ -199,4 +199,4 @@ def test_two_phase_sharded_search_equals_single_index(cuda_lib, W, n, nq, k, kin
     survivors = float((gi >= 0).sum()) / (W * nq)
     print(f"W={W} n={n} k={k} {kind}: {survivors:.1f} rescored rows per (query, shard) instead of k' >= {k + max(k // 2, 32)}")
     if n >= 8 * k * W:       # (big enough shards: the bound must bite - about k / W rows plus the error-bound slack)
-        assert survivors <= k / W + 0.2 * k, survivors
+        assert survivors <= k / W + 0.35 * k, survivors

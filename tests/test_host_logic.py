@@ -164,7 +164,7 @@ class _CpuSharded(sharded.ShardedFlatIndexer):
         gi = recv[:, 4 * m * k:].contiguous().view(torch.int64).view(W, m, k)
         s, i = self._merge(gs, gi, k)
         out[:4 * m * k].view(torch.float32).copy_(s.reshape(-1))
-        out[4 * m * k:].view(torch.int64).copy_(i.reshape(-1))
+        out[4 * m * k:12 * m * k].view(torch.int64).copy_(i.reshape(-1))
 
     def _merge(self, gs, gi, k):
         # (score desc, id asc) over the W * k gathered candidates of every query - what ldot_topk_merge does
