@@ -7,6 +7,7 @@
 // The kernel is linear_tc.cuh; this file is its host side.
 #include "linear_tc.cuh"
 #include "linear_ln.cuh"
+#include "linear_ln2.cuh"
 #include "qkv_attn.cuh"
 #include "host_common.h"
 #include "prof.h"
@@ -220,6 +221,60 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
 }
 
 // out = LayerNorm(A . W^T + bias + residual) * gamma + beta, 16-bit output; a cluster of ceil(N / 256) CTAs per row block
+// CTA-pair form (linear_ln2.cuh): N == 768 with a residual and enough rows to fill the machine.  LDOT_LN_PAIR=0 disables it.
+static int linear_ln_pair_run(const void* a, long long lda, const void* w, long long ldw, const float* bias,
+                              const void* residual, long long ldr, const float* gamma, const float* beta, void* out,
+                              long long ldo, long long M, int N, int K, int fmt, cudaStream_t st) {
+  CUtensorMap ta, tw, to, tr, te;
+  const uint16_t* eye = nullptr;
+  if (int e = eye_pointer(fmt, st, &eye)) return e;
+  if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
+  if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN / 2)) return e;
+  if (int e = make_tmap_store(&to, out, 2, M, N, static_cast<uint64_t>(ldo) * 2, 32, 32)) return e;
+  if (int e = make_tmap_kmajor_16b(&tr, residual, M, N, static_cast<uint64_t>(ldr) * 2, kBM)) return e;
+  if (int e = make_tmap_kmajor_16b(&te, eye, kLinBN, kLinBN, kLinBN * 2, kBK / 2)) return e;   // 32-row halves of I_64
+  static bool configured = false;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 6;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kLinThreads);
+  cfg.dynamicSmemBytes = Ln2Smem::kDynamic;
+  cfg.stream = st;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (!configured) {
+    LDOT_CUDA(cudaFuncSetAttribute(linear_ln2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Ln2Smem::kDynamic));
+    cfg.gridDim = dim3(6);
+    LDOT_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, linear_ln2_kernel, &cfg));
+    LDOT_REQUIRE(max_clusters >= 1, "no resident cluster of 6 CTAs possible");
+    configured = true;
+  }
+  LnSched s;
+  s.m_tiles = static_cast<int>((M + 2 * kBM - 1) / (2 * kBM));   // 256-row blocks, one per cluster pass
+  s.k_blocks = (K + kBK - 1) / kBK;
+  s.cluster = 3;
+  s.res_blocks = kLinBN / kBK;
+  s.num_clusters = s.m_tiles < max_clusters ? s.m_tiles : max_clusters;
+  s.idesc = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), 2 * kBM, kLinBN);
+  s.idesc_res = ptx::make_idesc_f16(static_cast<uint32_t>(fmt), 2 * kBM, kBK);
+  LnParams p;
+  p.bias = bias;
+  p.gamma = gamma;
+  p.beta = beta;
+  p.M = M;
+  p.N = N;
+  p.fmt = fmt;
+  cfg.gridDim = dim3(static_cast<unsigned>(s.num_clusters * 6));
+  KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
+                 (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * 4.0);
+  LDOT_CUDA(cudaLaunchKernelEx(&cfg, linear_ln2_kernel, ta, tw, tr, te, to, s, p));
+  return kOk;
+}
+
 int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
                   long long ldr, const float* gamma, const float* beta, void* out, long long ldo, long long M, int N,
                   int K, int fmt, void* stream) {
@@ -237,6 +292,15 @@ int linear_ln_run(const void* a, long long lda, const void* w, long long ldw, co
   LDOT_REQUIRE(M < (1ll << 31) - 128, "M too large");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int C = (N + kLinBN - 1) / kLinBN;
+  {
+    static int pair = -1;
+    if (pair < 0) {
+      const char* e = getenv("LDOT_LN_PAIR");
+      pair = e ? atoi(e) : 1;
+    }
+    if (pair && N == 3 * kLinBN && residual != nullptr && M >= 64 * 2 * kBM)
+      return linear_ln_pair_run(a, lda, w, ldw, bias, residual, ldr, gamma, beta, out, ldo, M, N, K, fmt, st);
+  }
   CUtensorMap ta, tw, to;
   if (int e = make_tmap_kmajor_16b(&ta, a, M, K, static_cast<uint64_t>(lda) * 2, kBM)) return e;
   if (int e = make_tmap_kmajor_16b(&tw, w, N, K, static_cast<uint64_t>(ldw) * 2, kLinBN)) return e;
