@@ -542,7 +542,9 @@ def run_ours(args):
                 "us_per_launch": 1e3 * v["ms"] / max(1, v["timed"]), "peak_source": peaks["source"] + " (sustained bf16)"}
 
     dominant = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
-    roof_lin = tensor_roof(lin, "linear_tcgen05 (linear_tc_kernel + linear_ln_kernel)")
+    roof_lin = tensor_roof(lin, "linear_tcgen05 (linear_tc_kernel + linear_ln2_kernel: O-proj+LN, FFN-up+GELU, FFN-down+LN, head)")
+    roof_qa = tensor_roof(prof["qkv_attention"], "qkv_attention (qkv_attn_kernel: Q|K|V projection + attention, one kernel)") \
+        if prof.get("qkv_attention", {}).get("launches") else None
     roof_search = tensor_roof(coarse, "coarse_score_topk (coarse_ts_kernel<EpiTopK>)")
     roof_search["queries_per_pass"] = nq
     roofline = roof_lin if dominant == "linear_tcgen05" else roof_search
@@ -570,6 +572,7 @@ def run_ours(args):
         "gpu_launches": int(sum(v["launches"] for v in prof.values())),
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_qkv_attention": roof_qa,
         "roofline_search": roof_search,
         "roofline_online": online,
         "index_build": index_build,

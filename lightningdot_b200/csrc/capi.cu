@@ -115,7 +115,7 @@ ProfState& prof_state() {
 const char* kernel_class_name(int c) {
   static const char* names[kKcCount] = {"coarse_score_topk", "select", "rescore", "query_prepare", "index_prepare",
                                         "exact_scan", "merge", "linear_tcgen05", "attention", "layernorm", "embed",
-                                        "cast", "nll", "optim"};
+                                        "cast", "nll", "optim", "qkv_attention"};
   return c >= 0 && c < kKcCount ? names[c] : "?";
 }
 

@@ -431,7 +431,7 @@ int qkv_attention_run(const void* x, long long ldx, const void* w, long long ldw
   p.S = S;
   p.H = H;
   // algorithmic work: the projection GEMM + the two attention contractions; bytes: x + W + ctx (no Q | K | V round trip)
-  KernelScope ks(kKcLinear, st, 2.0 * T * 3.0 * H * K + 4.0 * T * S * H,
+  KernelScope ks(kKcQkvAttn, st, 2.0 * T * 3.0 * H * K + 4.0 * T * S * H,
                  (static_cast<double>(T) * K + 3.0 * H * K + static_cast<double>(T) * H) * 2.0);
   const int spad = S <= 32 ? 32 : S <= 48 ? 48 : S <= 64 ? 64 : S <= 96 ? 96 : 128;
 #define LDOT_QA(SP) (fmt == 1 ? launch_qkv_attn<SP, 1>(ta, tw, s, p, st) : launch_qkv_attn<SP, 0>(ta, tw, s, p, st))

@@ -22,6 +22,7 @@ enum KernelClass : int {
   kKcCast,           // casts / hi-lo splits
   kKcNll,
   kKcOptim,          // AdamW / gradient norm
+  kKcQkvAttn,        // fused Q|K|V projection + attention (tcgen05 main loop, mma.sync attention in the epilogue)
   kKcCount
 };
 

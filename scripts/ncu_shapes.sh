@@ -9,6 +9,7 @@ cap() {  # name, kernel regex, case
     -o "gpurun_out/shape_$1" python scripts/bench_linear.py "$M" 0.01 "$3" > "gpurun_out/shape_$1.out" 2>&1; echo "ncu $1 rc=$?"
 }
 cap qkv 'linear_tc_kernel' qkv
+cap qkv_attn 'qkv_attn_kernel' qkv+attn
 cap oproj_ln 'linear_ln' o+ln
 cap ffn1_gelu 'linear_tc_kernel' ffn1+gelu
 cap ffn2_ln 'linear_ln' ffn2+ln

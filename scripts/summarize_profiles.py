@@ -93,7 +93,8 @@ def ncu_report(tag, rep, name, traffic_key=None, kernel_index=0, traffic=None):
 
 
 SHAPES = {  # scripts/ncu_shapes.sh captures at M = 320 000 tokens: name -> (N, K, reads a residual)
-    "qkv": (2304, 768, False), "oproj_ln": (768, 768, True), "ffn1_gelu": (3072, 768, False), "ffn2_ln": (768, 3072, True)}
+    "qkv": (2304, 768, False), "oproj_ln": (768, 768, True), "ffn1_gelu": (3072, 768, False), "ffn2_ln": (768, 3072, True),
+    "qkv_attn": (768, 768, False)}   # (fused projection + attention: reads x + the stacked weight, writes ctx only)
 
 
 def shape_traffic(tag, traffic, M=320000):
@@ -104,7 +105,7 @@ def shape_traffic(tag, traffic, M=320000):
         t = {}
         ncu_report(tag, f"shape_{name}.ncu-rep", f"shape_{name}_m{M}", "x", 0, t)
         if "x" in t:
-            alg = 2.0 * (M * K + N * K + M * N + (M * N if res else 0))
+            alg = 2.0 * (M * K + N * K + M * N + (M * N if res else 0)) + (2.0 * 2 * N * K if name == "qkv_attn" else 0.0)
             out[name] = {"M": M, "N": N, "K": K, "dram_bytes": t["x"], "algorithmic_bytes": alg, "ratio": t["x"] / alg}
     if out:
         traffic["linear_tcgen05_shapes"] = out

@@ -90,8 +90,10 @@ def test_gelu_epilogue_is_the_erf_form(cuda_lib):
     assert (tanh_form - ref).abs().max().item() > 1e-4   # (what the bar excludes)
 
 
+# (M >= 16 384 with N = 768 and a residual runs the CTA-pair form - 2 x 3 clusters, linear_ln2.cuh; 16 384 + 131 rows leave a
+# partial 256-row block and a partial 128-row half; the no-residual second call of the test stays on the single-CTA form)
 @pytest.mark.parametrize("M,N,K", [(128, 768, 768), (300, 768, 3072), (4097, 768, 768), (77, 256, 64), (1000, 512, 128),
-                                   (130, 96, 72)])
+                                   (130, 96, 72), (16384 + 131, 768, 768), (16384 + 257, 768, 3072), (45 * 256, 768, 768)])
 @pytest.mark.parametrize("fmt", [0, 1])
 def test_linear_layernorm_fused(cuda_lib, M, N, K, fmt):
     """ldot_linear_ln = LayerNorm(A W^T + bias + residual) * gamma + beta against fp32 torch.  The statistics are exact
