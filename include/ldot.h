@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LDOT_ABI_VERSION 5
+#define LDOT_ABI_VERSION 6
 
 #define LDOT_OK 0
 #define LDOT_ERR_ARG (-1)
@@ -237,6 +237,38 @@ int ldot_sumsq(const float* d_g, int64_t n, float* d_out, void* stream);
 int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16, int64_t n, float lr, float beta1,
                float beta2, float eps, float weight_decay, int32_t step, const float* d_sumsq, float max_norm,
                int32_t dtype, void* stream);
+
+/* ---- fused forms of the training step and CUDA-graph support (ABI 6) ---------------------------------------------
+ * ldot_linear_dropout   BertSelfOutput / BertOutput in training mode up to the LayerNorm (layer.py:111-115,152-156):
+ *                       d_out = dropout(d_a . d_w^T + d_bias) (+ d_residual), the mask of ldot_dropout(site) applied in
+ *                       the GEMM epilogue (element index row * N + col); 16-bit output, N % 8 == 0
+ * ldot_linear_gelu_pre  BertIntermediate in training mode (layer.py:133-136): d_out = GELU(z) and d_pre = z =
+ *                       d_a . d_w^T + d_bias, both 16-bit, written by one kernel (backward needs z, the next GEMM GELU(z))
+ * ldot_layernorm_bwd_dropout   ldot_layernorm_bwd (16-bit dy / x / dx) for a LayerNorm whose input was
+ *                       dropout(dense) + residual: d_dx gets the residual-branch gradient, d_dx_masked = mask * dx / keep
+ *                       the dense-branch gradient (row pitch ld_dx), and d_dxsum sums the MASKED values (the dense bias
+ *                       gradient) - LayerNorm backward + ldot_dropout + ldot_colsum16 in one pass
+ * ldot_dropout_epoch    registers a DEVICE word that every later dropout-bearing launch mixes into its mask key when the
+ *                       kernel RUNS (NULL: none).  A captured CUDA graph replays launch arguments of capture time; bumping
+ *                       the word between replays gives every replay fresh masks while forward and backward of one replay
+ *                       agree.  Process-wide setting; returns the previous pointer through the return value's absence:
+ *                       call with NULL to clear.
+ * ldot_adamw_dev        ldot_adamw whose step-dependent scalars come from device memory, d_hyper = { lr, 1 - beta1^t,
+ *                       sqrt(1 - beta2^t) } (fp32), so that a captured step follows the learning-rate schedule         */
+int ldot_linear_dropout(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
+                        const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
+                        int32_t dtype, float drop_p, uint64_t seed, int32_t site, void* stream);
+int ldot_linear_gelu_pre(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_pre,
+                         int64_t ld_pre, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype,
+                         void* stream);
+int ldot_layernorm_bwd_dropout(const void* d_dy, int64_t ld_dy, const void* d_x, int64_t ld_x, const float* d_gamma,
+                               void* d_dx, void* d_dx_masked, int64_t ld_dx, float* d_dgamma, float* d_dbeta,
+                               float* d_dxsum, int64_t rows, int32_t H, float drop_p, uint64_t seed, int32_t site,
+                               int32_t dtype, void* stream);
+int ldot_dropout_epoch(const uint32_t* d_epoch);
+int ldot_adamw_dev(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16, int64_t n, const float* d_hyper,
+                   float beta1, float beta2, float eps, float weight_decay, const float* d_sumsq, float max_norm,
+                   int32_t dtype, void* stream);
 
 #ifdef __cplusplus
 }

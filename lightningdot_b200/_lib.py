@@ -11,7 +11,7 @@ from ctypes import c_char_p, c_float, c_int32, c_int64, c_size_t, c_void_p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libldot_sm100a.so")
 
-ABI_VERSION = 5   # LDOT_ABI_VERSION of include/ldot.h
+ABI_VERSION = 6   # LDOT_ABI_VERSION of include/ldot.h
 COARSE_FP16 = 0
 COARSE_BF16 = 1
 
@@ -104,6 +104,17 @@ SIGNATURES = {
     "ldot_sumsq": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p]),
     "ldot_adamw": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                              c_float, c_int32, c_void_p, c_float, c_int32, c_void_p]),
+    # fused training forms + CUDA-graph support (ABI 6)
+    "ldot_linear_dropout": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                      c_int64, c_int32, c_int32, c_int32, c_float, ctypes.c_uint64, c_int32, c_void_p]),
+    "ldot_linear_gelu_pre": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                       c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_layernorm_bwd_dropout": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
+                                             c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, ctypes.c_uint64,
+                                             c_int32, c_int32, c_void_p]),
+    "ldot_dropout_epoch": (c_int32, [c_void_p]),
+    "ldot_adamw_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_float,
+                                 c_float, c_float, c_void_p, c_float, c_int32, c_void_p]),
 }
 
 

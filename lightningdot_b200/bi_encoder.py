@@ -479,11 +479,21 @@ class BiEncoderNllLoss(object):
             raise ValueError("reduction must be 'mean' or 'sum'")
         # (hard_negatice_idx_per_question is accepted and unused, exactly as in the reference)
         dev = q_vectors.device
-        pos = torch.as_tensor(positive_idx_per_question, dtype=torch.int64, device=dev).contiguous()
+        if torch.is_tensor(positive_idx_per_question):
+            # (a device tensor, e.g. the static index buffer of a captured step: range-checked unless a CUDA graph is
+            # being captured, where a host read of device data is impossible)
+            pos = positive_idx_per_question.to(device=dev, dtype=torch.int64).contiguous()
+            if not (pos.is_cuda and torch.cuda.is_current_stream_capturing()) and pos.numel():
+                if int(pos.min()) < 0 or int(pos.max()) >= ctx_vectors.shape[0]:
+                    raise IndexError("positive index out of range")
+        else:
+            # the reference passes a Python list (dvl/utils.py:160-169): checked on the host, no device round trip
+            idx = [int(v) for v in positive_idx_per_question]
+            if idx and (min(idx) < 0 or max(idx) >= ctx_vectors.shape[0]):
+                raise IndexError("positive index out of range")
+            pos = torch.as_tensor(idx, dtype=torch.int64, device=dev).contiguous()
         if pos.numel() != q_vectors.shape[0]:
             raise ValueError("one positive index per question expected")
-        if int(pos.min()) < 0 or int(pos.max()) >= ctx_vectors.shape[0]:
-            raise IndexError("positive index out of range")
         w = float(caption_score_weight) if caption_vectors is not None else 0.0
         # one autograd node: scores + NLL forward, tensor-core backward to the embeddings (training.py: NllFunction)
         loss, correct, scores, scores_img = NllFunction.apply(q_vectors, ctx_vectors, caption_vectors if w != 0 else None,

@@ -185,10 +185,11 @@ int device_sm_count(int* out) {
 
 }  // namespace ldot
 
+#include "dropout.cuh"
 namespace ldot {
 int linear_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
                long long ldr, void* out, long long ldo, long long M, int N, int K, int fmt, int act, int out_f32,
-               void* stream);
+               void* stream, const DropKey* drop = nullptr, void* pre = nullptr, long long ld_pre = 0);
 }
 
 namespace ldot {
@@ -467,7 +468,7 @@ int ldot_layernorm_bwd(const void* d_dy, int64_t ld_dy, int32_t dy_f32, const vo
   LnBwdParams p;
   p.dy = d_dy; p.ld_dy = ld_dy; p.dy_f32 = dy_f32; p.x = d_x; p.ld_x = ld_x; p.x_f32 = x_f32; p.gamma = d_gamma;
   p.dx = d_dx; p.ld_dx = ld_dx; p.dx_f32 = dx_f32; p.dgamma = d_dgamma; p.dbeta = d_dbeta; p.dxsum = d_dxsum;
-  p.rows = rows; p.fmt = dtype;
+  p.rows = rows; p.fmt = dtype; p.dx_masked = nullptr; p.drop = make_drop_key(0.f, 0, 0);
   return ln_bwd_run(p, H, stream);
 }
 
@@ -551,7 +552,56 @@ int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
   a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
-  a.sumsq = d_sumsq; a.max_norm = max_norm; a.fmt = dtype;
+  a.sumsq = d_sumsq; a.max_norm = max_norm; a.fmt = dtype; a.hyper = nullptr;
+  return adamw_run(a, stream);
+}
+
+// ---- fused training forms + CUDA-graph support (ABI 6) -----------------------------------------------------------
+int ldot_linear_dropout(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
+                        const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
+                        int32_t dtype, float drop_p, uint64_t seed, int32_t site, void* stream) {
+  LDOT_REQUIRE(d_a && d_w && d_out, "null pointer argument");
+  LDOT_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "linear_dropout: probability %f out of [0, 1)", drop_p);
+  const DropKey drop = make_drop_key(drop_p, seed, site);
+  return linear_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_out, ldo, M, N, K, dtype, 0, 0, stream, &drop);
+}
+
+int ldot_linear_gelu_pre(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_pre,
+                         int64_t ld_pre, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype,
+                         void* stream) {
+  LDOT_REQUIRE(d_a && d_w && d_out && d_pre, "null pointer argument");
+  return linear_run(d_a, lda, d_w, ldw, d_bias, nullptr, 0, d_out, ldo, M, N, K, dtype, 1, 0, stream, nullptr, d_pre, ld_pre);
+}
+
+int ldot_layernorm_bwd_dropout(const void* d_dy, int64_t ld_dy, const void* d_x, int64_t ld_x, const float* d_gamma,
+                               void* d_dx, void* d_dx_masked, int64_t ld_dx, float* d_dgamma, float* d_dbeta,
+                               float* d_dxsum, int64_t rows, int32_t H, float drop_p, uint64_t seed, int32_t site,
+                               int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_dy && d_x && d_gamma && d_dx && d_dx_masked && d_dgamma && d_dbeta, "null pointer argument");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  LDOT_REQUIRE(drop_p > 0.f && drop_p < 1.f, "layernorm_bwd_dropout: probability %f out of (0, 1)", drop_p);
+  LDOT_REQUIRE(H <= 1024, "layernorm_bwd_dropout: hidden size %d > 1024", H);
+  LnBwdParams p;
+  p.dy = d_dy; p.ld_dy = ld_dy; p.dy_f32 = 0; p.x = d_x; p.ld_x = ld_x; p.x_f32 = 0; p.gamma = d_gamma;
+  p.dx = d_dx; p.ld_dx = ld_dx; p.dx_f32 = 0; p.dgamma = d_dgamma; p.dbeta = d_dbeta; p.dxsum = d_dxsum;
+  p.rows = rows; p.fmt = dtype; p.dx_masked = d_dx_masked; p.drop = make_drop_key(drop_p, seed, site);
+  return ln_bwd_run(p, H, stream);
+}
+
+int ldot_dropout_epoch(const uint32_t* d_epoch) {
+  drop_epoch_slot() = d_epoch;
+  return kOk;
+}
+
+int ldot_adamw_dev(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16, int64_t n, const float* d_hyper,
+                   float beta1, float beta2, float eps, float weight_decay, const float* d_sumsq, float max_norm,
+                   int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_hyper, "adamw_dev: null d_hyper");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  AdamParams a;
+  a.p = d_p; a.g = d_g; a.m = d_m; a.v = d_v; a.p16 = static_cast<uint16_t*>(d_p16); a.n = n;
+  a.lr = 0.f; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay; a.bc1 = 1.f; a.bc2_sqrt = 1.f;
+  a.sumsq = d_sumsq; a.max_norm = max_norm; a.fmt = dtype; a.hyper = d_hyper;
   return adamw_run(a, stream);
 }
 

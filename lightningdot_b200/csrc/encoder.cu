@@ -297,7 +297,8 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gme
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
                                                               uint16_t* __restrict__ ctx, int B, int S, int H, int heads,
-                                                              int q_rows, const DropKey drop, int bufs) {
+                                                              int q_rows, const DropKey drop_in, int bufs) {
+  const DropKey drop = drop_resolve(drop_in);
   extern __shared__ __align__(16) uint16_t att_smem_all[];
   constexpr int kBuf = 3 * SPAD * kRowPad + SPAD * 4;   // 16-bit elements per buffer: Q | K | V | int64 mask row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -43,10 +43,10 @@ static int eye_pointer(int fmt, cudaStream_t st, const uint16_t** out) {
   return kOk;
 }
 
-template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
+template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0, int TRAIN = 0>
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
-  auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS, AMN, BMN, RED>;
+  auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS, AMN, BMN, RED, TRAIN>;
   using SM = LinSmemT<CTAS, lin_epi_warps(ACT)>;
   static bool configured = false;  // (one device per process)
   static int max_groups = 0;       // resident CTAs (CTAS = 1) or CTA pairs (CTAS = 2)
@@ -94,7 +94,7 @@ static int linear_ctas(long long M, int N, int sms) {
 
 int linear_run(const void* a, long long lda, const void* w, long long ldw, const float* bias, const void* residual,
                long long ldr, void* out, long long ldo, long long M, int N, int K, int fmt, int act, int out_f32,
-               void* stream) {
+               void* stream, const DropKey* drop = nullptr, void* pre = nullptr, long long ld_pre = 0) {
   LDOT_REQUIRE(M >= 1 && N >= 1 && K >= 8, "bad GEMM shape M=%lld N=%d K=%d", M, N, K);
   LDOT_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "K, lda, ldw must be multiples of 8 elements");
   LDOT_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (fp16) or 1 (bf16)");
@@ -105,6 +105,9 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
                    (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
                "out / residual / bias must be 16-byte aligned");
   LDOT_REQUIRE(M < (1ll << 31) - 256, "M too large");
+  LDOT_REQUIRE(!drop || drop->thr == 0 || (act == 0 && N % 8 == 0), "the dropout epilogue needs act 0 and N % 8 == 0");
+  LDOT_REQUIRE(!pre || (act == 1 && ld_pre % 8 == 0 && (reinterpret_cast<uintptr_t>(pre) & 15) == 0),
+               "the pre-activation output needs act 1, ld_pre % 8 == 0 and a 16-byte aligned base");
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   const int ctas = linear_ctas(M, N, sms);
@@ -128,11 +131,20 @@ int linear_run(const void* a, long long lda, const void* w, long long ldw, const
   p.M = M;
   p.N = N;
   p.fmt = fmt;
+  p.drop = drop ? *drop : make_drop_key(0.f, 0, 0);
+  p.pre = pre;
+  p.ld_pre = ld_pre;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
                  (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * elt +
-                     (residual ? static_cast<double>(M) * N * 2.0 : 0.0));
+                     (residual ? static_cast<double>(M) * N * 2.0 : 0.0) + (pre ? static_cast<double>(M) * N * 2.0 : 0.0));
 #define LDOT_LIN(ACT, F32) (ctas == 2 ? launch_linear<ACT, F32, 2>(ta, tw, to, s, p, sms, st) : launch_linear<ACT, F32, 1>(ta, tw, to, s, p, sms, st))
+#define LDOT_LIN_TRAIN(ACT) (ctas == 2 ? launch_linear<ACT, 0, 2, 0, 0, 0, 1>(ta, tw, to, s, p, sms, st) : launch_linear<ACT, 0, 1, 0, 0, 0, 1>(ta, tw, to, s, p, sms, st))
+  if (p.drop.thr != 0 || pre != nullptr) {
+    LDOT_REQUIRE(!out_f32, "the training-forward epilogues write 16-bit output");
+    return act == 1 ? LDOT_LIN_TRAIN(1) : LDOT_LIN_TRAIN(0);
+  }
+#undef LDOT_LIN_TRAIN
   if (act == 1) return out_f32 ? LDOT_LIN(1, 1) : LDOT_LIN(1, 0);
   return out_f32 ? LDOT_LIN(0, 1) : LDOT_LIN(0, 0);
 #undef LDOT_LIN
@@ -207,6 +219,9 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
   p.M = M;
   p.N = N;
   p.fmt = fmt;
+  p.drop = make_drop_key(0.f, 0, 0);
+  p.pre = nullptr;
+  p.ld_pre = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KernelScope ks(kKcLinear, st, 2.0 * M * static_cast<double>(N) * K,
                  (static_cast<double>(M) * K + static_cast<double>(N) * K) * 2.0 + static_cast<double>(M) * N * elt +

@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 #include "gemm_tc.cuh"
 #include "gelu.cuh"
+#include "dropout.cuh"
 
 namespace ldot {
 
@@ -57,6 +58,12 @@ struct LinParams {
   long long M;
   int N;
   int fmt;                // 0 = fp16, 1 = bf16 (A, W, residual, 16-bit output)
+  // training forward (ACT 0): out = dropout(acc + bias) (+ residual), mask element index row * N + col (drop.thr 0: off)
+  DropKey drop;
+  // training forward (ACT 1): the pre-activation acc + bias is ALSO written, 16-bit [M, ld_pre] (null: not written) -
+  // backward needs GELU's input and the next GEMM its output
+  void* pre;
+  long long ld_pre;
 };
 
 template <int CTAS, int EW = kLinEpiWarps>
@@ -102,7 +109,10 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
 //   ACT = 2         out = acc * gelu'(aux[m, n]) with aux = p.residual (the saved FFN-up pre-activation)
 //   RED = 1         fp32 output boxes are ADDED to global memory (cp.reduce.async.bulk.tensor .add): gradient
 //                   accumulation, and what makes split-K (sched.k_splits > 1) a pure scheduling decision.
-template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0>
+//   TRAIN = 1       the training-forward epilogues: dropout of the dense output (ACT 0, p.drop) / the pre-activation
+//                   written next to GELU's output (ACT 1, p.pre).  A template flag so that the inference
+//                   instantiations keep their register budget (the 16-warp GELU form has 96 per thread).
+template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0, int TRAIN = 0>
 __global__ void __launch_bounds__(lin_threads(ACT), 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
@@ -274,6 +284,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     uint32_t nstore = 0;
+    const DropKey drop = TRAIN ? drop_resolve(p.drop) : p.drop;
     // tempty of the LEADER collects the arrivals of both CTAs' epilogue warps
     const uint32_t tempty_addr[2] = {CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[0]), 0) : ptx::smem_u32(&tempty[0]),
                                      CTAS == 2 ? ptx::mapa(ptx::smem_u32(&tempty[1]), 0) : ptx::smem_u32(&tempty[1])};
@@ -357,7 +368,48 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (col + j < p.N) f[j] += __ldg(bias + col + j);
                 }
               }
+              if (TRAIN && ACT == 0 && drop.thr != 0) {
+                // hidden-state dropout of the dense output (layer.py:113,154); 8 consecutive indices share a high word
+                const unsigned long long idx = static_cast<unsigned long long>(grow) * p.N + col;
+#pragma unroll
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  const uint32_t inner = drop_inner(drop, idx + 8 * g8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    f[g8 * 8 + j] = drop_keep(drop, inner, static_cast<uint32_t>(idx) + g8 * 8 + j) ? f[g8 * 8 + j] * drop.inv_keep : 0.f;
+                }
+              }
               if (ACT == 1) {
+                if (TRAIN && p.pre != nullptr && row_ok) {
+                  uint16_t* pre = static_cast<uint16_t*>(p.pre) + grow * p.ld_pre + col;
+                  if (full_slice) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                      uint4 w;
+                      w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
+                      w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
+                      w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
+                      w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
+                      reinterpret_cast<uint4*>(pre)[j] = w;
+                      // GELU sees the ROUNDED pre-activation, as in the reference (the 16-bit tensor is what amp hands to
+                      // F.gelu) and as backward's GELU'(pre) assumes
+                      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                      for (int q = 0; q < 4; ++q) {
+                        const float2 x = unpack2(ww[q], p.fmt);
+                        f[8 * j + 2 * q] = x.x;
+                        f[8 * j + 2 * q + 1] = x.y;
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const uint32_t h = pack2(f[j], 0.f, p.fmt);
+                      f[j] = unpack2(h, p.fmt).x;
+                      if (col + j < p.N) pre[j] = static_cast<uint16_t>(h & 0xFFFFu);
+                    }
+                  }
+                }
 #pragma unroll
                 for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
               }

@@ -131,6 +131,142 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
   }
 }
 
+// The hot form (x and dy 16-bit: every encoder-layer LayerNorm of the step): the row stays in registers as the RAW 16-byte
+// vectors (re-converted per pass), two of the three column partials live in registers and the third (sum of dx) in the
+// warp's own shared-memory plane, so that the kernel fits 128 registers and two blocks (16 rows in flight) per SM - the
+// general kernel above needs 226 registers, one block per SM, and ran at a quarter of the HBM rate.
+// Hidden-state dropout fused in (p.dx_masked != null): the Linear that fed this LayerNorm was followed by dropout
+// (layer.py:111-115: LN(dropout(dense(x)) + residual)), so the residual branch gets dx and the dense branch gets
+// mask * dx / keep - written as a second output here, and p.dxsum (the dense bias gradient) sums the MASKED values;
+// one kernel instead of LayerNorm backward + dropout + column sums.
+template <int NV, int FMT>
+__global__ void __launch_bounds__(256, 2) ln_bwd16_kernel(const LnBwdParams p) {
+  constexpr int H = NV * 256;
+  extern __shared__ float ln_red[];   // [8 warps][3][H]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ag[NV][8], ab[NV][8];
+#pragma unroll
+  for (int v = 0; v < NV; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ag[v][j] = ab[v][j] = 0.f;
+  float* mine = ln_red + warp * 3 * H;
+  float* axs = mine + 2 * H;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    *reinterpret_cast<float4*>(axs + col) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(axs + col + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const DropKey drop = drop_resolve(p.drop);
+  const bool masked = p.dx_masked != nullptr && drop.thr != 0;
+  const uint16_t* xg = static_cast<const uint16_t*>(p.x);
+  const uint16_t* dyg = static_cast<const uint16_t*>(p.dy);
+  constexpr float kInvH = 1.f / static_cast<float>(H);
+
+  auto unpack = [](const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = cvt2<FMT>(w[t]);
+      f[2 * t] = x.x;
+      f[2 * t + 1] = x.y;
+    }
+  };
+
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < p.rows;
+       row += static_cast<long long>(gridDim.x) * 8) {
+    uint4 xr[NV], dr[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      xr[v] = __ldg(reinterpret_cast<const uint4*>(xg + row * p.ld_x + col));
+      dr[v] = __ldg(reinterpret_cast<const uint4*>(dyg + row * p.ld_dy + col));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float x[8];
+      unpack(xr[v], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += x[j];
+    }
+    const float mean = warp_sum(s) * kInvH;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float x[8];
+      unpack(xr[v], x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * kInvH + kLnEps);
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float x[8], dy[8], gam[8];
+      unpack(xr[v], x);
+      unpack(dr[v], dy);
+      load8_f32(p.gamma + (v * 32 + lane) * 8, gam);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float g = dy[j] * gam[j];
+        c1 += g;
+        c2 = fmaf(g, (x[j] - mean) * rstd, c2);
+      }
+    }
+    c1 = warp_sum(c1) * kInvH;
+    c2 = warp_sum(c2) * kInvH;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int col = (v * 32 + lane) * 8;
+      float x[8], dy[8], gam[8], dx[8];
+      unpack(xr[v], x);
+      unpack(dr[v], dy);
+      load8_f32(p.gamma + col, gam);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mean) * rstd;
+        dx[j] = rstd * (dy[j] * gam[j] - c1 - xh * c2);
+        ag[v][j] = fmaf(dy[j], xh, ag[v][j]);
+        ab[v][j] += dy[j];
+      }
+      st8(p.dx, row * p.ld_dx + col, p.dx_f32, FMT, dx);
+      if (masked) {
+        const unsigned long long idx = static_cast<unsigned long long>(row) * H + col;
+        const uint32_t inner = drop_inner(drop, idx);   // (H % 8 == 0: the 8 indices share their high word)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dx[j] = drop_keep(drop, inner, static_cast<uint32_t>(idx) + j) ? dx[j] * drop.inv_keep : 0.f;
+        store8_16<FMT>(static_cast<uint16_t*>(p.dx_masked) + row * p.ld_dx + col, dx);
+      }
+      float4 a0 = *reinterpret_cast<float4*>(axs + col), a1 = *reinterpret_cast<float4*>(axs + col + 4);
+      a0.x += dx[0]; a0.y += dx[1]; a0.z += dx[2]; a0.w += dx[3];
+      a1.x += dx[4]; a1.y += dx[5]; a1.z += dx[6]; a1.w += dx[7];
+      *reinterpret_cast<float4*>(axs + col) = a0;
+      *reinterpret_cast<float4*>(axs + col + 4) = a1;
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    *reinterpret_cast<float4*>(mine + col) = make_float4(ag[v][0], ag[v][1], ag[v][2], ag[v][3]);
+    *reinterpret_cast<float4*>(mine + col + 4) = make_float4(ag[v][4], ag[v][5], ag[v][6], ag[v][7]);
+    *reinterpret_cast<float4*>(mine + H + col) = make_float4(ab[v][0], ab[v][1], ab[v][2], ab[v][3]);
+    *reinterpret_cast<float4*>(mine + H + col + 4) = make_float4(ab[v][4], ab[v][5], ab[v][6], ab[v][7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * H; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ln_red[w * 3 * H + i];
+    if (i < H) atomicAdd(p.dgamma + i, t);
+    else if (i < 2 * H) atomicAdd(p.dbeta + i - H, t);
+    else if (p.dxsum) atomicAdd(p.dxsum + i - 2 * H, t);
+  }
+}
+
 #define LDOT_NV_DISPATCH(H, CALL)                                   \
   switch ((H) / 256) {                                              \
     case 1: { constexpr int NV = 1; CALL; break; }                  \
@@ -141,26 +277,33 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdParams p) {
     default: return set_error(kErrArg, "hidden size %d not supported (256 x {1,2,3,4,6})", (H)); \
   }
 
-static unsigned row_grid(long long rows) {
+static unsigned row_grid(long long rows, int blocks_per_sm) {
   long long b = (rows + 7) / 8;
-  // three resident blocks per SM (72 KB of partial tables each at H = 768); every block ends with 3 H global atomics
-  const long long cap = 148 * 3;
+  // resident blocks only (72 KB of partial tables each at H = 768); every block ends with 3 H global atomics
+  const long long cap = 148 * blocks_per_sm;
   return static_cast<unsigned>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
 int ln_bwd_run(const LnBwdParams& p, int H, void* stream) {
   LDOT_REQUIRE(p.rows >= 1 && H % 256 == 0, "layernorm_bwd: bad shape rows=%lld H=%d", p.rows, H);
   LDOT_REQUIRE(p.ld_dy % 8 == 0 && p.ld_x % 8 == 0 && p.ld_dx % 8 == 0, "layernorm_bwd: row pitches must be multiples of 8");
+  const bool all16 = !p.x_f32 && !p.dy_f32;
+  LDOT_REQUIRE(p.dx_masked == nullptr || (all16 && !p.dx_f32), "layernorm_bwd: the dropout form takes 16-bit dy, x and dx");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  KernelScope ks(kKcLayerNorm, st, 0.0, static_cast<double>(p.rows) * H * 6.0);
+  KernelScope ks(kKcLayerNorm, st, 0.0, static_cast<double>(p.rows) * H * (p.dx_masked ? 8.0 : 6.0));
   const size_t smem = static_cast<size_t>(8) * 3 * H * sizeof(float);
   LDOT_REQUIRE(smem <= 200 * 1024, "layernorm_bwd: hidden size %d too large", H);
-#define LDOT_LNB(NVV) \
+#define LDOT_LNB_K(KERN, BPS) \
   { static bool cfgd = false; \
-    if (!cfgd) { LDOT_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfgd = true; } \
-    ln_bwd_kernel<NVV><<<row_grid(p.rows), 256, smem, st>>>(p); }
-  LDOT_NV_DISPATCH(H, LDOT_LNB(NV))
-#undef LDOT_LNB
+    if (!cfgd) { LDOT_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); cfgd = true; } \
+    KERN<<<row_grid(p.rows, BPS), 256, smem, st>>>(p); }
+  if (all16 && H <= 1024) {
+    if (p.fmt == 1) { LDOT_NV_DISPATCH(H, LDOT_LNB_K((ln_bwd16_kernel<NV, 1>), 2)) }
+    else { LDOT_NV_DISPATCH(H, LDOT_LNB_K((ln_bwd16_kernel<NV, 0>), 2)) }
+  } else {
+    LDOT_NV_DISPATCH(H, LDOT_LNB_K(ln_bwd_kernel<NV>, 1))
+  }
+#undef LDOT_LNB_K
   LDOT_CHECK_LAUNCH();
   return kOk;
 }
@@ -190,7 +333,8 @@ __device__ __forceinline__ uint16_t f2h(float f, int fmt) {
 template <int SPAD, int FMT>
 __global__ void __launch_bounds__(SPAD * 2) attention_bwd_kernel(const uint16_t* __restrict__ qkv, const long long* __restrict__ mask,
                                                                   const uint16_t* __restrict__ dctx, uint16_t* __restrict__ dqkv,
-                                                                  int S, int H, const DropKey drop) {
+                                                                  int S, int H, const DropKey drop_in) {
+  const DropKey drop = drop_resolve(drop_in);
   constexpr int PP = SPAD + 8;          // pitch of the P / dS tiles (odd multiple of 16 B: conflict-free ldmatrix)
   constexpr int NT = SPAD / 8;
   extern __shared__ __align__(16) uint16_t ab_smem[];
@@ -473,7 +617,8 @@ static unsigned flat_grid(long long n_vec) {
 // [rows, cols] matrix (row pitch ld, cols % 8 == 0); the same call masks the gradient in backward (res = null).
 __global__ void __launch_bounds__(256) dropout_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ res,
                                                       uint16_t* __restrict__ out, long long rows, int cols, long long ld,
-                                                      int fmt, const DropKey drop) {
+                                                      int fmt, const DropKey drop_in) {
+  const DropKey drop = drop_resolve(drop_in);
   const int c8 = cols / 8;
   const long long n8 = rows * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
@@ -880,14 +1025,20 @@ __global__ void __launch_bounds__(256) adamw_kernel(const AdamParams a) {
     const float norm = sqrtf(__ldg(a.sumsq));
     clip = fminf(1.f, a.max_norm / (norm + 1e-6f));
   }
-  const float step = a.lr / a.bc1;
+  float lr = a.lr, bc1 = a.bc1, bc2_sqrt = a.bc2_sqrt;
+  if (a.hyper != nullptr) {
+    lr = __ldg(a.hyper);
+    bc1 = __ldg(a.hyper + 1);
+    bc2_sqrt = __ldg(a.hyper + 2);
+  }
+  const float step = lr / bc1;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float g = a.g[i] * clip;
-    float p = a.p[i] * (1.f - a.lr * a.wd);
+    float p = a.p[i] * (1.f - lr * a.wd);
     const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
     const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
-    p -= step * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+    p -= step * m / (sqrtf(v) / bc2_sqrt + a.eps);
     a.p[i] = p;
     a.m[i] = m;
     a.v[i] = v;

@@ -1,6 +1,7 @@
 // Parameter blocks and host entry points of the training kernels (train.cu), shared with the C-ABI layer (capi.cu).
 #pragma once
 #include <cstdint>
+#include "dropout.cuh"
 
 namespace ldot {
 
@@ -12,6 +13,10 @@ struct LnBwdParams {
   float* dgamma; float* dbeta; float* dxsum;     // fp32 [H], accumulated (+=); dxsum may be null
   long long rows;
   int fmt;
+  // hidden-state dropout of the Linear that fed this LayerNorm, fused (16-bit dy / x / dx only): when dx_masked is
+  // given, dx_masked = mask * dx / keep (row pitch ld_dx) is written next to dx and dxsum sums the masked values
+  void* dx_masked;
+  DropKey drop;
 };
 
 struct EmbedImagePreParams {
@@ -30,6 +35,7 @@ struct AdamParams {
   float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt;   // bc1 = 1 - b1^t, bc2_sqrt = sqrt(1 - b2^t)
   const float* sumsq; float max_norm;
   int fmt;
+  const float* hyper;   // device { lr, bc1, bc2_sqrt } overriding the by-value fields (null: by value)
 };
 
 int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, const float* bias,

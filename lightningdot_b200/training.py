@@ -128,6 +128,28 @@ class TowerTrainer(object):
     def _gelu(self, x, out):
         _lib.check(_lib.load().ldot_gelu(_lib.ptr(x), _lib.ptr(out), x.numel(), self.e.fmt, _lib.stream_ptr()))
 
+    def _linear_dropout(self, a, wt, bias, residual, out, M, site):
+        """out = dropout(a . wt^T + bias) + residual in ONE kernel (the mask of _dropout(site) in the GEMM epilogue)."""
+        N, K = wt.shape
+        _lib.check(_lib.load().ldot_linear_dropout(
+            _lib.ptr(a), a.stride(0), _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(residual), residual.stride(0),
+            _lib.ptr(out), out.stride(0), M, N, K, self.e.fmt, self.p_hidden, self.seed, site, _lib.stream_ptr()))
+
+    def _linear_gelu_pre(self, a, wt, bias, pre, out, M):
+        """pre = a . wt^T + bias and out = GELU(pre) from one kernel."""
+        N, K = wt.shape
+        _lib.check(_lib.load().ldot_linear_gelu_pre(
+            _lib.ptr(a), a.stride(0), _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(pre), pre.stride(0), _lib.ptr(out),
+            out.stride(0), M, N, K, self.e.fmt, _lib.stream_ptr()))
+
+    def _ln_bwd_dropout(self, dy, x, gamma, dx, dx_masked, dgamma, dbeta, dxsum, rows, H, site):
+        """LayerNorm backward whose input was dropout(dense) + residual: dx (residual branch), dx_masked (dense branch)
+        and the dense bias gradient (column sums of dx_masked) in one pass."""
+        _lib.check(_lib.load().ldot_layernorm_bwd_dropout(
+            _lib.ptr(dy), dy.stride(0), _lib.ptr(x), x.stride(0), _lib.ptr(gamma), _lib.ptr(dx), _lib.ptr(dx_masked),
+            dx.stride(0), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dxsum), rows, H, self.p_hidden, self.seed, site,
+            self.e.fmt, _lib.stream_ptr()))
+
     # ------------------------------------------------------------------------------------------------ forward
     def _forward_layers(self, h, mask, B, S, tape):
         e, lib = self.e, _lib.load()
@@ -150,17 +172,14 @@ class TowerTrainer(object):
             e._linear(h, H, w[f"qkv_w{i}"], w[f"qkv_b{i}"], qkv, T)
             _lib.check(lib.ldot_attention_train(_lib.ptr(qkv), _lib.ptr(mask), _lib.ptr(ctx), B, S, H, e.heads, self.p_attn,
                                                 self.seed, 4 * i, e.fmt, stream))
-            if ph:   # dense -> dropout -> + residual (layer.py:111-115)
-                e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T)
-                self._dropout(pre1, pre1, 4 * i + 1, T, H, res=h)
+            if ph:   # dense -> dropout -> + residual (layer.py:111-115), one kernel
+                self._linear_dropout(ctx, w[f"o_w{i}"], w[f"o_b{i}"], h, pre1, T, 4 * i + 1)
             else:
                 e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T, residual=h)
             e._layernorm(pre1, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
-            e._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, T)
-            self._gelu(fpre, f)
+            self._linear_gelu_pre(a, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, f, T)
             if ph:
-                e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T)
-                self._dropout(pre2, pre2, 4 * i + 2, T, H, res=a)
+                self._linear_dropout(f, w[f"f2_w{i}"], w[f"f2_b{i}"], a, pre2, T, 4 * i + 2)
             else:
                 e._linear(f, F, w[f"f2_w{i}"], w[f"f2_b{i}"], pre2, T, residual=a)
             e._layernorm(pre2, w[f"ln2_g{i}"], w[f"ln2_b{i}"], out, T, H)
@@ -212,7 +231,8 @@ class TowerTrainer(object):
             raise ValueError(f"sequence length {S} > 128 is not supported by the attention kernel")
         if mask.shape[1] != S:
             raise ValueError(f"attention_mask has {mask.shape[1]} positions, expected {S}")
-        if gather_index is not None:
+        if gather_index is not None and not torch.cuda.is_current_stream_capturing():
+            # (a captured step was run eagerly on the same static batch first: checked there)
             gi = gather_index.to(dev)
             if not torch.equal(gi, torch.arange(S, device=dev)[None, :].expand(B, S)):
                 raise NotImplementedError("only the identity gather_index of dvl/data/itm.py is supported")
@@ -288,15 +308,16 @@ class TowerTrainer(object):
             g.z(p + "output.LayerNorm.weight", H)
             g.z(p + "output.LayerNorm.bias", H)
             g.z(p + "output.dense.bias", H)
-            # (with hidden dropout the dense output's gradient is the MASKED d_pre2 - its bias gradient cannot come from
-            # the LayerNorm kernel's column sums; the residual branch keeps the unmasked one)
-            self._ln_bwd(d_h, pre2, w[f"ln2_g{i}"], d_pre2, g[p + "output.LayerNorm.weight"],
-                         g[p + "output.LayerNorm.bias"], None if ph else g[p + "output.dense.bias"], T, H)
-            d_o2 = d_pre2
+            # (with hidden dropout the dense output's gradient is the MASKED d_pre2 and its bias gradient the column sums
+            # of that; the residual branch keeps the unmasked one - the fused kernel writes both)
             if ph:
                 d_o2 = buf(T, H)
-                self._dropout(d_pre2, d_o2, 4 * i + 2, T, H)
-                self._colsum(d_o2, g[p + "output.dense.bias"], T)
+                self._ln_bwd_dropout(d_h, pre2, w[f"ln2_g{i}"], d_pre2, d_o2, g[p + "output.LayerNorm.weight"],
+                                     g[p + "output.LayerNorm.bias"], g[p + "output.dense.bias"], T, H, 4 * i + 2)
+            else:
+                self._ln_bwd(d_h, pre2, w[f"ln2_g{i}"], d_pre2, g[p + "output.LayerNorm.weight"],
+                             g[p + "output.LayerNorm.bias"], g[p + "output.dense.bias"], T, H)
+                d_o2 = d_pre2
             g.z(p + "output.dense.weight", H, F)
             self._wgrad(d_o2, f, g[p + "output.dense.weight"], T)
             d_fpre = buf(T, F)
@@ -315,14 +336,15 @@ class TowerTrainer(object):
             g.z(p + "attention.output.LayerNorm.weight", H)
             g.z(p + "attention.output.LayerNorm.bias", H)
             g.z(p + "attention.output.dense.bias", H)
-            self._ln_bwd(d_a, pre1, w[f"ln1_g{i}"], d_pre1, g[p + "attention.output.LayerNorm.weight"],
-                         g[p + "attention.output.LayerNorm.bias"], None if ph else g[p + "attention.output.dense.bias"],
-                         T, H)
-            d_o1 = d_pre1
             if ph:
                 d_o1 = buf(T, H)
-                self._dropout(d_pre1, d_o1, 4 * i + 1, T, H)
-                self._colsum(d_o1, g[p + "attention.output.dense.bias"], T)
+                self._ln_bwd_dropout(d_a, pre1, w[f"ln1_g{i}"], d_pre1, d_o1, g[p + "attention.output.LayerNorm.weight"],
+                                     g[p + "attention.output.LayerNorm.bias"], g[p + "attention.output.dense.bias"], T, H,
+                                     4 * i + 1)
+            else:
+                self._ln_bwd(d_a, pre1, w[f"ln1_g{i}"], d_pre1, g[p + "attention.output.LayerNorm.weight"],
+                             g[p + "attention.output.LayerNorm.bias"], g[p + "attention.output.dense.bias"], T, H)
+                d_o1 = d_pre1
             g.z(p + "attention.output.dense.weight", H, H)
             self._wgrad(d_o1, ctx, g[p + "attention.output.dense.weight"], T)
             d_ctx = buf(T, H)
@@ -592,6 +614,9 @@ class FusedAdamW(torch.optim.Optimizer):
         self._synced = False
         self._flat = None
         self._steps = 0
+        # {group index: fp32 [3] device tensor} once device_hyper(True) was called: lr and the bias corrections are then
+        # read by the kernel from device memory (ldot_adamw_dev), which is what lets step() be captured in a CUDA graph
+        self._hyper = None
 
     PAD = 64   # parameters start on 64-element boundaries (TMA operands need 16-byte aligned bases)
 
@@ -717,11 +742,33 @@ class FusedAdamW(torch.optim.Optimizer):
         sync_gradients([f["g"] for f in self._collect()], group)
         self._synced = True
 
+    def device_hyper(self, on=True):
+        """Route lr / bias corrections through device memory (GraphedTrainStep); off restores by-value arguments."""
+        self._hyper = {} if on else None
+
+    def begin_step(self):
+        """Host half of a step: count it and (device_hyper mode) upload this step's lr and bias corrections.  step() calls
+        it; a replayed CUDA graph calls it itself before every replay, since step() only ran at capture time."""
+        self._steps += 1
+        if self._hyper is None:
+            return
+        for gi, (group, f) in enumerate(zip(self.param_groups, self._flat or [])):
+            if f is None:
+                continue
+            b1, b2 = group["betas"]
+            host = torch.tensor([float(group["lr"]), 1.0 - b1 ** self._steps, (1.0 - b2 ** self._steps) ** 0.5],
+                                dtype=torch.float32).pin_memory()
+            if gi not in self._hyper:
+                self._hyper[gi] = torch.empty(3, dtype=torch.float32, device=f["p"].device)
+            self._hyper[gi].copy_(host, non_blocking=True)
+
     @torch.no_grad()
     def step(self, closure=None):
         lib = _lib.load()
         live = self._collect()
-        self._steps += 1
+        capturing = bool(live) and live[0]["p"].is_cuda and torch.cuda.is_current_stream_capturing()
+        if not capturing:   # (a capture records launches without running them: nothing is stepped)
+            self.begin_step()
         stream = _lib.stream_ptr()
         if not live:
             return None
@@ -738,9 +785,120 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             b1, b2 = group["betas"]
             fmt = _lib.COARSE_FP16 if (f["p16"] is not None and f["p16"].dtype == torch.float16) else _lib.COARSE_BF16
+            if self._hyper is not None:
+                gi = self.param_groups.index(group)
+                if gi not in self._hyper:
+                    if capturing:
+                        raise _lib.LdotError("FusedAdamW: run one eager step() in device_hyper mode before capturing")
+                    self._steps -= 1
+                    self.begin_step()
+                _lib.check(lib.ldot_adamw_dev(_lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["m"]), _lib.ptr(f["v"]),
+                                              _lib.ptr(f["p16"]), f["p"].numel(), _lib.ptr(self._hyper[gi]), float(b1),
+                                              float(b2), float(group["eps"]), float(group["weight_decay"]), _lib.ptr(ss),
+                                              self.max_grad_norm, fmt, stream))
+                continue
             _lib.check(lib.ldot_adamw(_lib.ptr(f["p"]), _lib.ptr(f["g"]), _lib.ptr(f["m"]), _lib.ptr(f["v"]),
                                       _lib.ptr(f["p16"]), f["p"].numel(), float(group["lr"]), float(b1), float(b2),
                                       float(group["eps"]), float(group["weight_decay"]), self._steps, _lib.ptr(ss),
                                       self.max_grad_norm, fmt, stream))
         _lib.param_generation[0] += 1   # towers that hold converted COPIES of the weights (not aliases) are stale now
         return None
+
+
+# ------------------------------------------------------------------------------------------------------- CUDA graph
+def _map_leaves(obj, fn):
+    if torch.is_tensor(obj):
+        return fn(obj)
+    if isinstance(obj, dict):
+        return {k: _map_leaves(v, fn) for k, v in obj.items()}
+    return obj
+
+
+def _copy_leaves(dst, src, path="batch"):
+    if torch.is_tensor(dst):
+        if not torch.is_tensor(src):
+            src = torch.as_tensor(src)
+        if tuple(src.shape) != tuple(dst.shape):
+            raise ValueError(f"{path}: shape {tuple(src.shape)} differs from the captured {tuple(dst.shape)} "
+                             "(a captured step replays fixed shapes: pad or re-capture)")
+        dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, dict):
+        for k, v in dst.items():
+            _copy_leaves(v, src[k], f"{path}[{k!r}]")
+
+
+class GraphedTrainStep(object):
+    """The training step of train_itm.py:191-289 as ONE CUDA graph: both towers forward, the symmetric in-batch NLL (with its
+    embedding all-gather under a process group), backward, gradient average, clip, AdamW, zero_grad - ~550 kernel launches
+    and their Python dispatch replayed with one cudaGraphLaunch.  The eager step is launch-bound for a fifth of its time
+    (measured: kernels cover 0.78-0.82 of the step); the replay is not.
+
+        step = GraphedTrainStep(fwd_bwd, optimizer, batch, scheduler=sched)   # fwd_bwd(batch) -> loss, ends in loss.backward()
+        for batch in loader: loss = step(batch)                                # same shapes as the captured batch
+
+    What makes the captured launches follow the training state: dropout masks mix in a device word the graph bumps at
+    the end of every replay (ldot_dropout_epoch), lr and the Adam bias corrections are read from device memory
+    (FusedAdamW.device_hyper), inputs are copied into the static batch the graph reads.  `pos_ctx_indices` (a Python list
+    in the reference's batches) is kept as a device tensor.  `warmup` eager steps run first (they are real steps): they
+    lay out the optimiser's flat buffers and validate the batch (the checks a capture cannot perform).
+    Do not keep losses of EARLIER eager steps alive with their grad_fn (store loss.detach()): autograd caches a
+    parameter's AccumulateGrad node, with the stream it was created on, for as long as any graph references it, and ends
+    every backward by joining those streams - inside a capture that is a dependency on uncaptured work."""
+
+    def __init__(self, fwd_bwd, optimizer, batch, scheduler=None, warmup=2):
+        if not isinstance(optimizer, FusedAdamW):
+            raise TypeError("GraphedTrainStep drives FusedAdamW (get_optimizer returns it)")
+        lib = _lib.load()
+        self.fwd_bwd, self.optimizer, self.scheduler = fwd_bwd, optimizer, scheduler
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def static_of(t):
+            return t.to(dev).clone() if t.is_cuda else t.to(dev, non_blocking=False)
+        self.static = _map_leaves(dict(batch), static_of)
+        if isinstance(self.static.get("pos_ctx_indices"), (list, tuple)):
+            self.static["pos_ctx_indices"] = torch.tensor([int(v) for v in self.static["pos_ctx_indices"]],
+                                                          dtype=torch.int64, device=dev)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        optimizer.device_hyper(True)
+        self.steps_taken = 0
+        self.loss = None
+        self.warmup_losses = []   # losses of the eager warm-up steps (device tensors)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(max(1, int(warmup))):
+                self.warmup_losses.append(self._eager().detach().clone())
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        _lib.check(lib.ldot_dropout_epoch(_lib.ptr(self.epoch)))
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self.fwd_bwd(self.static)
+                self.optimizer.step()
+                self.optimizer.zero_grad()
+                self.epoch.add_(1)
+        finally:
+            _lib.check(lib.ldot_dropout_epoch(None))
+
+    def _eager(self):
+        loss = self.fwd_bwd(self.static)
+        self.optimizer.step()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        self.optimizer.zero_grad()
+        self.steps_taken += 1
+        return loss
+
+    def __call__(self, batch=None):
+        """One replayed step on `batch` (None: the batch already in the static buffers).  -> the loss (a static device
+        tensor, overwritten by the next replay)."""
+        if batch is not None:
+            _copy_leaves(self.static, batch)
+        self.optimizer.begin_step()
+        self.graph.replay()
+        if self.scheduler is not None:
+            self.scheduler.step()
+        self.steps_taken += 1
+        return self.loss

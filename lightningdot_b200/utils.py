@@ -135,7 +135,10 @@ def _calc_loss(args, loss_function, local_q_vector, local_ctx_vectors, local_cap
         q = local_q_vector
         ctx = gather_embeddings(local_ctx_vectors)
         cap = gather_embeddings(local_caption_vectors) if local_caption_vectors is not None else None
-        positives = [p + rank * n_ctx for p in local_positive_idxs]
+        if torch.is_tensor(local_positive_idxs):
+            positives = local_positive_idxs + rank * n_ctx
+        else:
+            positives = [p + rank * n_ctx for p in local_positive_idxs]
         hard = None if local_hard_negatives_idxs is None else \
             [[v + rank * n_ctx for v in row] for row in local_hard_negatives_idxs]
     else:

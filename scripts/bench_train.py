@@ -32,7 +32,7 @@ from lightningdot_b200.utils import _calc_loss  # noqa: E402
 
 
 def default_args(**over):
-    a = types.SimpleNamespace(per_gpu_batch=512, seq_len=32, regions=36, layers=12, steps=5, warmup=3, fp16=False, check=False)
+    a = types.SimpleNamespace(per_gpu_batch=512, seq_len=32, regions=36, layers=12, steps=5, warmup=3, fp16=False, check=False, graph=True)
     a.__dict__.update(over)
     return a
 
@@ -83,12 +83,17 @@ def measure(a, rank, world, local_rank, dev):
             out[key] = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in bt[key].items()}
         return out
 
-    def step(m, o, s, bt, la, on_device=False):
-        t, i, _ = m(bt if on_device else to_dev(bt))
+    def fwd_bwd(m, bt, la):
+        """train_itm.py:191-258 for one batch on the device: both towers, the symmetric in-batch NLL, loss.backward()"""
+        t, i, _ = m(bt)
         l1, c1, _ = _calc_loss(la, BiEncoderNllLoss(), i, t, None, bt["pos_ctx_indices"], None)
         l2, c2, _ = _calc_loss(la, BiEncoderNllLoss(), t, i, None, bt["pos_ctx_indices"], None)
         loss = 0.5 * l1 + 0.5 * l2
         loss.backward()
+        return loss
+
+    def step(m, o, s, bt, la, on_device=False):
+        loss = fwd_bwd(m, bt if on_device else to_dev(bt), la)
         if o is not None:
             o.step()
             s.step()
@@ -143,7 +148,7 @@ def measure(a, rank, world, local_rank, dev):
     e0.record()
     losses = []
     for bt in loader:
-        losses.append(step(model, opt, sched, bt, largs, on_device=True))
+        losses.append(step(model, opt, sched, bt, largs, on_device=True).detach())   # (no autograd graph kept alive)
     e1.record()
     barrier()
     _lib.prof_enable(False)
@@ -154,6 +159,45 @@ def measure(a, rank, world, local_rank, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_step = ms / a.steps
+    eager_ms_step = ms_step
+    # the same step captured as ONE CUDA graph (training.GraphedTrainStep) and replayed: the launch-bound fifth of the
+    # eager step goes away.  Batches still arrive through PrefetchLoader (H2D on the side stream) and are copied into the
+    # graph's static inputs; lr schedule, Adam bias corrections and dropout masks advance per replay.
+    graph_info = None
+    if getattr(a, "graph", True):
+        from lightningdot_b200.training import GraphedTrainStep
+        ok = 1
+        try:
+            dev_batch = next(iter(PrefetchLoader([batch], dev)))
+            gstep = GraphedTrainStep(lambda bt: fwd_bwd(model, bt, largs), opt, dev_batch, scheduler=sched, warmup=1)
+            for bt in PrefetchLoader([batch] * a.warmup, dev):
+                gstep(bt)
+        except Exception as exc:   # noqa: BLE001 - reported in the line, the eager figure stands
+            ok = 0
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            graph_info = {"captured": False, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        if world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if ok:
+            loader = PrefetchLoader([batch] * a.steps, dev)
+            barrier()
+            e0.record()
+            glosses = []
+            for bt in loader:
+                glosses.append(gstep(bt).clone())
+            e1.record()
+            barrier()
+            gms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([gms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                gms = float(t.item())
+            ms_step = gms / a.steps
+            graph_info = {"captured": True, "ms_per_step": ms_step, "eager_ms_per_step": eager_ms_step,
+                          "loss_first_last": [glosses[0].item(), glosses[-1].item()]}
     peak_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peak_file)).get("bf16_tflops_sustained", 1400.0) if os.path.exists(peak_file) else 1400.0
     if rank == 0:
@@ -171,8 +215,10 @@ def measure(a, rank, world, local_rank, dev):
             "linear_tcgen05": {"ms_per_step": lin["ms"] / a.steps, "tflops": lin["flops"] / (lin["ms"] * 1e-3) / 1e12 if lin["ms"] else 0.0,
                                "frac_of_peak": (lin["flops"] / (lin["ms"] * 1e-3) / 1e12 / peak) if lin["ms"] else 0.0,
                                "launches_per_step": lin["launches"] / a.steps},
+            "cuda_graph": graph_info,
             "kernel_ms_per_step": {k: round(v["ms"] / a.steps, 3) for k, v in prof.items() if v["launches"]},
             "kernel_time_share_of_step": tot / a.steps / ms_step,
+            "kernel_times_from": "the eager run of the same step (per-launch CUDA events cannot bracket graph nodes)",
             "gpu_launches_per_step": sum(v["launches"] for v in prof.values()) / a.steps,
             "loss_first_last": [losses[0].item(), losses[-1].item()],
             "peak_tflops": peak, "distributed_check": check,
@@ -195,6 +241,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--fp16", action="store_true")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time the eager step only")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

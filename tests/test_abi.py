@@ -30,7 +30,7 @@ def test_binding_covers_header():
 
 def test_abi_version_and_error_string():
     lib = _lib.load()
-    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.ldot_abi_version() == _lib.ABI_VERSION == 6
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = lib.ldot_topk_merge(None, None, 2, 4, 10, 0, 0, None, None, None)
     assert rc == -1

@@ -212,6 +212,144 @@ def test_attention_dropout_fwd_bwd(cuda_lib, B, S, fmt):
     torch.testing.assert_close(dqkv.double(), x.grad, **tol)
 
 
+# ------------------------------------------------------------------------------------------- fused training forms
+@pytest.mark.parametrize("M,N,K", [(37, 768, 768), (1000, 768, 3072), (20000, 768, 768), (300, 264, 72)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_linear_dropout_equals_linear_then_dropout(cuda_lib, M, N, K, fmt):
+    """ldot_linear_dropout = dropout(A W^T + b) + residual with the mask of ldot_dropout at the same (seed, site): the
+    SAME elements are dropped as the CPU restatement says, kept values agree with the fp32 reference."""
+    from oracle import dropout as odrop
+    g = gen(21)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(DT[fmt])
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(DT[fmt])
+    b = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).to(DT[fmt])
+    out = torch.empty((M, N), device="cuda", dtype=DT[fmt])
+    p, seed, site = 0.1, 0x1234ABCD5678, 9
+    _lib.check(cuda_lib.ldot_linear_dropout(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(res), N, _lib.ptr(out), N,
+                                            M, N, K, fmt, p, seed, site, _lib.stream_ptr()))
+    keep = odrop.keep_mask((M, N), p, seed, site).cuda()
+    dense = a.float() @ w.float().T + b
+    ref = dense * keep / (1.0 - float(np.float32(p))) + res.float()
+    tol = dict(atol=4e-2, rtol=1.6e-2) if fmt == 1 else dict(atol=6e-3, rtol=2e-3)
+    torch.testing.assert_close(out.float(), ref, **tol)
+    # dropped positions carry the residual alone, exactly
+    assert torch.equal(out[~keep], res[~keep])
+    assert 0.85 < keep.float().mean().item() < 0.95 or M * N < 20000
+
+
+@pytest.mark.parametrize("M,N,K", [(37, 3072, 768), (20000, 3072, 768), (130, 200, 72)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_linear_gelu_pre_writes_both(cuda_lib, M, N, K, fmt):
+    """ldot_linear_gelu_pre: the pre-activation and GELU of it from one kernel, bit-identical to ldot_linear (act 0)
+    followed by ldot_gelu on its 16-bit output (GELU sees the rounded pre-activation, as under amp in the reference)."""
+    g = gen(22)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(DT[fmt])
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(DT[fmt])
+    b = torch.randn(N, device="cuda", generator=g)
+    pre = torch.zeros((M, N), device="cuda", dtype=DT[fmt])
+    out = torch.zeros((M, N), device="cuda", dtype=DT[fmt])
+    _lib.check(cuda_lib.ldot_linear_gelu_pre(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(pre), N, _lib.ptr(out), N,
+                                             M, N, K, fmt, _lib.stream_ptr()))
+    pre2 = torch.zeros_like(pre)
+    out2 = torch.zeros_like(out)
+    _lib.check(cuda_lib.ldot_linear(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), None, 0, _lib.ptr(pre2), N, M, N, K, fmt,
+                                    0, 0, _lib.stream_ptr()))
+    _lib.check(cuda_lib.ldot_gelu(_lib.ptr(pre2), _lib.ptr(out2), pre2.numel(), fmt, _lib.stream_ptr()))
+    assert torch.equal(pre, pre2)
+    assert torch.equal(out, out2)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().T + b)
+    tol = dict(atol=4e-2, rtol=1.6e-2) if fmt == 1 else dict(atol=6e-3, rtol=2e-3)
+    torch.testing.assert_close(out.float(), ref, **tol)
+
+
+@pytest.mark.parametrize("rows,H", [(1, 768), (37, 768), (20000, 768), (300, 256)])
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_layernorm_bwd_dropout(cuda_lib, rows, H, fmt):
+    """The fused form against LayerNorm backward (fp64 autograd) followed by the oracle's mask: dx, the masked dx, and the
+    column sums of the masked dx."""
+    from oracle import dropout as odrop
+    g = gen(23)
+    dt = DT[fmt]
+    x = (torch.randn(rows, H, device="cuda", generator=g) * 1.5 + 0.3).to(dt)
+    dy = (torch.randn(rows, H, device="cuda", generator=g) * 0.2).to(dt)
+    gamma = torch.rand(H, device="cuda", generator=g) + 0.5
+    dx = torch.empty((rows, H), device="cuda", dtype=dt)
+    dxm = torch.empty((rows, H), device="cuda", dtype=dt)
+    dgamma = torch.ones(H, device="cuda")
+    dbeta = torch.ones(H, device="cuda")
+    dxsum = torch.ones(H, device="cuda")
+    p, seed, site = 0.1, 0xBEEF0000CAFE, 6
+    _lib.check(cuda_lib.ldot_layernorm_bwd_dropout(_lib.ptr(dy), H, _lib.ptr(x), H, _lib.ptr(gamma), _lib.ptr(dx), _lib.ptr(dxm),
+                                                   H, _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dxsum), rows, H, p, seed,
+                                                   site, fmt, _lib.stream_ptr()))
+    xr = x.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    y = torch.nn.functional.layer_norm(xr, (H,), gr, torch.zeros(H, device="cuda", dtype=torch.float64), eps=1e-12)
+    y.backward(dy.double())
+    keep = odrop.keep_mask((rows, H), p, seed, site).cuda()
+    ref_m = xr.grad * keep / (1.0 - float(np.float32(p)))
+    tol = dict(atol=3e-2, rtol=1.6e-2) if fmt == 1 else dict(atol=4e-3, rtol=2e-3)
+    torch.testing.assert_close(dx.double(), xr.grad, **tol)
+    torch.testing.assert_close(dxm.double(), ref_m, **tol)
+    assert torch.all(dxm[~keep] == 0)
+    red = dict(atol=1e-3 * math.sqrt(rows), rtol=1e-4)
+    torch.testing.assert_close(dgamma.double() - 1, gr.grad, **red)
+    torch.testing.assert_close(dbeta.double() - 1, dy.double().sum(0), **red)
+    torch.testing.assert_close(dxsum.double() - 1, ref_m.sum(0), **red)
+
+
+def test_dropout_epoch_changes_masks_on_the_device(cuda_lib):
+    """ldot_dropout_epoch: the mask depends on a device word read at run time (what a replayed CUDA graph needs): same
+    word -> same mask, bumped word -> another mask, cleared -> the host-keyed mask again."""
+    rows, cols, p, seed, site = 64, 768, 0.3, 77, 3
+    x = torch.ones((rows, cols), device="cuda", dtype=torch.bfloat16)
+
+    def run():
+        out = torch.empty_like(x)
+        _lib.check(cuda_lib.ldot_dropout(_lib.ptr(x), None, _lib.ptr(out), rows, cols, cols, p, seed, site, 1, _lib.stream_ptr()))
+        return out
+
+    base = run()
+    epoch = torch.zeros(1, device="cuda", dtype=torch.int32)
+    try:
+        _lib.check(cuda_lib.ldot_dropout_epoch(_lib.ptr(epoch)))
+        e0, e0b = run(), run()
+        epoch.add_(1)
+        e1 = run()
+    finally:
+        _lib.check(cuda_lib.ldot_dropout_epoch(None))
+    again = run()
+    assert torch.equal(e0, e0b) and torch.equal(base, again)
+    assert not torch.equal(e0, e1) and not torch.equal(e0, base)
+    for t in (e0, e1):
+        assert abs((t == 0).float().mean().item() - p) < 0.02
+
+
+def test_adamw_dev_matches_adamw(cuda_lib):
+    """ldot_adamw_dev (step scalars from device memory) == ldot_adamw with the same scalars by value."""
+    n, lr, b1, b2, eps, wd, step = 10000, 3e-4, 0.9, 0.999, 1e-8, 0.01, 7
+    g = gen(24)
+    p0 = torch.randn(n, device="cuda", generator=g)
+    gr = torch.randn(n, device="cuda", generator=g)
+    m0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    v0 = torch.rand(n, device="cuda", generator=g) * 0.01
+    outs = []
+    for dev in (False, True):
+        p_, m_, v_ = p0.clone(), m0.clone(), v0.clone()
+        p16 = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+        if dev:
+            hyper = torch.tensor([lr, 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step)], dtype=torch.float32, device="cuda")
+            _lib.check(cuda_lib.ldot_adamw_dev(_lib.ptr(p_), _lib.ptr(gr), _lib.ptr(m_), _lib.ptr(v_), _lib.ptr(p16), n,
+                                               _lib.ptr(hyper), b1, b2, eps, wd, None, 0.0, 1, _lib.stream_ptr()))
+        else:
+            _lib.check(cuda_lib.ldot_adamw(_lib.ptr(p_), _lib.ptr(gr), _lib.ptr(m_), _lib.ptr(v_), _lib.ptr(p16), n, lr, b1, b2,
+                                           eps, wd, step, None, 0.0, 1, _lib.stream_ptr()))
+        outs.append((p_, m_, v_, p16))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a.float(), b.float(), atol=1e-7, rtol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------------ elementwise / sums
 @pytest.mark.parametrize("fmt", [0, 1])
 def test_gelu_and_gelu_bwd(cuda_lib, fmt):
