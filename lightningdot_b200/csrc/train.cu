@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd16_kernel(const LnBwdParams p) {
       xr[v] = __ldg(reinterpret_cast<const uint4*>(xg + row * p.ld_x + col));
       dr[v] = __ldg(reinterpret_cast<const uint4*>(dyg + row * p.ld_dy + col));
     }
+    // two reduction rounds per row: the mean, then (sum of squares, sum g, sum g (x - mean)) together
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -191,19 +192,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd16_kernel(const LnBwdParams p) {
       for (int j = 0; j < 8; ++j) s += x[j];
     }
     const float mean = warp_sum(s) * kInvH;
-    float q = 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      float x[8];
-      unpack(xr[v], x);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = x[j] - mean;
-        q = fmaf(d, d, q);
-      }
-    }
-    const float rstd = rsqrtf(warp_sum(q) * kInvH + kLnEps);
-    float c1 = 0.f, c2 = 0.f;
+    float q = 0.f, c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       float x[8], dy[8], gam[8];
@@ -212,13 +201,22 @@ __global__ void __launch_bounds__(256, 2) ln_bwd16_kernel(const LnBwdParams p) {
       load8_f32(p.gamma + (v * 32 + lane) * 8, gam);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const float d = x[j] - mean;
         const float g = dy[j] * gam[j];
+        q = fmaf(d, d, q);
         c1 += g;
-        c2 = fmaf(g, (x[j] - mean) * rstd, c2);
+        c2 = fmaf(g, d, c2);
       }
     }
-    c1 = warp_sum(c1) * kInvH;
-    c2 = warp_sum(c2) * kInvH;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q += __shfl_xor_sync(0xFFFFFFFFu, q, o);
+      c1 += __shfl_xor_sync(0xFFFFFFFFu, c1, o);
+      c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+    }
+    const float rstd = rsqrtf(q * kInvH + kLnEps);
+    // dx = rstd (g - mean(g) - xh mean(g xh)) with xh = (x - mean) rstd, as  k1 g + k3 xh + k2
+    const float k1 = rstd, k2 = -rstd * c1 * kInvH, k3 = -rstd * rstd * c2 * kInvH, m0 = -mean * rstd;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int col = (v * 32 + lane) * 8;
@@ -228,8 +226,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd16_kernel(const LnBwdParams p) {
       load8_f32(p.gamma + col, gam);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (x[j] - mean) * rstd;
-        dx[j] = rstd * (dy[j] * gam[j] - c1 - xh * c2);
+        const float xh = fmaf(x[j], rstd, m0);
+        dx[j] = fmaf(k1, dy[j] * gam[j], fmaf(k3, xh, k2));
         ag[v][j] = fmaf(dy[j], xh, ag[v][j]);
         ab[v][j] += dy[j];
       }

@@ -755,7 +755,8 @@ class FusedAdamW(torch.optim.Optimizer):
         for gi, (group, f) in enumerate(zip(self.param_groups, self._flat or [])):
             if f is None:
                 continue
-            b1, b2 = group["betas"]
+            # (the same arithmetic as ldot_adamw, which receives the betas as C floats: both entry points step alike)
+            b1, b2 = (float(torch.tensor(b, dtype=torch.float32)) for b in group["betas"])
             host = torch.tensor([float(group["lr"]), 1.0 - b1 ** self._steps, (1.0 - b2 ** self._steps) ** 0.5],
                                 dtype=torch.float32).pin_memory()
             if gi not in self._hyper:
@@ -786,7 +787,7 @@ class FusedAdamW(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             fmt = _lib.COARSE_FP16 if (f["p16"] is not None and f["p16"].dtype == torch.float16) else _lib.COARSE_BF16
             if self._hyper is not None:
-                gi = self.param_groups.index(group)
+                gi = next(j for j, gr in enumerate(self.param_groups) if gr is group)
                 if gi not in self._hyper:
                     if capturing:
                         raise _lib.LdotError("FusedAdamW: run one eager step() in device_hyper mode before capturing")

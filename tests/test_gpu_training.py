@@ -581,9 +581,12 @@ def test_graphed_train_step_follows_the_eager_trajectory(cuda_lib):
     batches = [{"txts": synth.text_batch(B, 24, seed=10 + s, ragged=True), "imgs": synth.image_batch(B, 20, seed=30 + s, ragged=True),
                 "caps": {"input_ids": None}, "sample_size": B, "pos_ctx_indices": list(range(B)), "neg_ctx_indices": []}
                for s in range(steps)]
-    # (a small step and eps 1e-4: training this random-init pair is chaotic - two EAGER runs at lr 5e-5 drift 1-3 % apart
-    # within seven steps through the atomics-order noise of the gradients, scripts/probes/graph_vs_eager.py - so the
-    # trajectories are compared where that noise stays below the bar, and the schedule is also checked directly below)
+    # What "agree" can mean here (scripts/probes/devhyper_diff.py, graph_bisect.py): the loss of this random-init pair has a
+    # bf16 rounding-noise floor of ~0.5 % - two state dicts that differ by ONE fp32 ulp in a few weights already give
+    # losses 0.5 % apart, because any change re-rolls the 16-bit roundings of the forward pass and the in-batch softmax
+    # over near-collinear embeddings amplifies them.  Runs with bit-identical weights agree to the last digit (the first
+    # steps below; graph vs eager over six steps in graph_bisect.py); once atomics-order noise has flipped one ulp they
+    # agree to that floor.  So: first three steps tight, the rest within 2 %, and the schedule checked directly.
     lr = 2e-6
     ma, oa = _bi_encoder(3, lr)
     ma.eval()
@@ -604,14 +607,15 @@ def test_graphed_train_step_follows_the_eager_trajectory(cuda_lib):
         graphed.append(gstep(bt).item())
     assert gstep.steps_taken == steps and ob._steps == oa._steps == steps
     assert sb.get_last_lr() == sa.get_last_lr()
-    np.testing.assert_allclose(graphed, eager, rtol=2e-3)
+    np.testing.assert_allclose(graphed[:3], eager[:3], rtol=1e-5)
+    np.testing.assert_allclose(graphed, eager, rtol=2e-2)
     assert len(set(round(v, 3) for v in graphed)) == steps      # (every replay read ITS batch)
     # the device-side hyper-parameters of the last replay: the scheduled lr of step 7 and Adam's bias corrections
     want_lr = lr * (50 - (steps - 1)) / (50 - 3)
     for gi, group in enumerate(ob.param_groups):
         got = ob._hyper[gi].cpu().tolist()
         b1, b2 = group["betas"]
-        np.testing.assert_allclose(got, [want_lr, 1 - b1 ** steps, (1 - b2 ** steps) ** 0.5], rtol=1e-6)
+        np.testing.assert_allclose(got, [want_lr, 1 - b1 ** steps, (1 - b2 ** steps) ** 0.5], rtol=2e-5)
     pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
     worst = max((pa[n].detach() - pb[n].detach()).abs().max().item() for n in pa)
     assert worst <= 2 * steps * lr, worst
