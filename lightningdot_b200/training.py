@@ -21,6 +21,8 @@ outputs before the residual add (uniter_model/model/layer.py:93,113,154; model.p
 function of (seed drawn from torch's CPU generator per tower call, site, element index) - csrc/dropout.cuh - so the
 backward kernels regenerate them instead of storing them.  eval() mode (or probabilities 0) runs the deterministic network.
 """
+import weakref
+
 import torch
 
 from . import _lib
@@ -257,9 +259,11 @@ class TowerTrainer(object):
         return self._forward_head(h, B, S, tape), tape
 
     # ------------------------------------------------------------------------------------------------ backward
-    def backward(self, tape, d_pooled, sinks=None):
+    def backward(self, tape, d_pooled, sinks=None, done=None):
         """d_pooled fp32 [B, D] -> {reference parameter name: fp32 gradient}.  `sinks`: {name: existing fp32 gradient
-        tensor}: those gradients are ACCUMULATED into the given tensors (and still listed in the result)."""
+        tensor}: those gradients are ACCUMULATED into the given tensors (and still listed in the result).
+        `done(names)`: called as soon as the gradients of `names` are final (head, then each layer from the last to the
+        first, then the embeddings) - what lets the gradient all-reduce start under the rest of the backward."""
         e, w, lib = self.e, self.e.w, _lib.load()
         H, F, dt, dev = e.H, e.ffn, e.dtype, d_pooled.device
         B, S = tape.B, tape.S
@@ -300,6 +304,7 @@ class TowerTrainer(object):
 
         ph = tape.p_hidden > 0
         self.p_hidden, self.p_attn, self.seed = tape.p_hidden, tape.p_attn, tape.seed   # (the forward's masks)
+        reported = set()
         for i in reversed(range(e.layers)):
             x, qkv, ctx, pre1, a, fpre, f, pre2 = tape.layers[i]
             p = f"bert.encoder.layer.{i}."
@@ -364,10 +369,15 @@ class TowerTrainer(object):
             self._dgrad(d_qkv, w[f"qkv_w{i}"], d_x, T, aux=d_pre1, epi=3)
             d_h = d_x
             tape.layers[i] = None   # release this layer's activations
+            if done is not None:
+                done([n for n in g if n not in reported])
+                reported.update(g)
 
         if ph:
             self._dropout(d_h, d_h, SITE_EMB, T, H)
         self._backward_embeddings(tape, d_h, g)
+        if done is not None:
+            done([n for n in g if n not in reported])
         return g
 
     def _backward_embeddings(self, tape, d_h, g):
@@ -453,12 +463,32 @@ class TowerFunction(torch.autograd.Function):
             if ctx.needs_input_grad[2 + i] and g is not None and g.dtype == torch.float32 and g.is_contiguous() \
                     and g.device == d_pooled.device and g.shape == p.shape:
                 sinks[nm] = g
-        grads = ctx.trainer.backward(ctx.tape, d_pooled, sinks)
+        grads = ctx.trainer.backward(ctx.tape, d_pooled, sinks, done=_early_sync_hook(ctx.names, ctx.params, sinks))
         ctx.tape = None
         out = []
         for i, nm in enumerate(ctx.names):
             out.append(grads.get(nm) if (ctx.needs_input_grad[2 + i] and nm not in sinks) else None)
         return (None, None) + tuple(out)
+
+
+def _early_sync_hook(names, params, sinks):
+    """-> done(names) for TowerTrainer.backward, or None: hands finished gradients to the FusedAdamW optimisers that asked
+    for an overlapped gradient all-reduce (`overlap_grad_sync`) and own the flat buffers those gradients live in."""
+    owners = []
+    for f in _lib.flat_buffers:
+        opt = f.get("owner") and f["owner"]()
+        if opt is not None and opt.overlap_grad_sync and opt.distributed and opt not in owners:
+            owners.append(opt)
+    if not owners:
+        return None
+    by_name = dict(zip(names, params))
+
+    def done(finished):
+        ps = [by_name[n] for n in finished if n in sinks and n in by_name]
+        if ps:
+            for opt in owners:
+                opt.reduce_early(ps)
+    return done
 
 
 class _Runner(object):
@@ -617,6 +647,14 @@ class FusedAdamW(torch.optim.Optimizer):
         # {group index: fp32 [3] device tensor} once device_hyper(True) was called: lr and the bias corrections are then
         # read by the kernel from device memory (ldot_adamw_dev), which is what lets step() be captured in a CUDA graph
         self._hyper = None
+        # Overlapped gradient averaging (opt-in: valid when every step() follows ONE backward - no gradient accumulation):
+        # the towers report finished gradients during backward (training._early_sync_hook) and their spans of the flat
+        # buffers are all-reduced asynchronously, under the rest of the backward; sync_gradients() reduces what is left.
+        self.overlap_grad_sync = False
+        self.early_sync_bytes = 32 << 20      # spans are batched up to this size per collective
+        self._early_pending = []              # parameters whose gradients are final, not yet handed to NCCL
+        self._early_spans = []                # (flat buffer index, lo, hi) already being reduced
+        self._early_works = []
 
     PAD = 64   # parameters start on 64-element boundaries (TMA operands need 16-byte aligned bases)
 
@@ -656,6 +694,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 off += (k + pad - 1) // pad * pad
             if self.shadow_dtype is not None and any(p.dim() >= 2 for p in ps):
                 f["p16"] = f["p"].to(self.shadow_dtype)
+            f["owner"] = weakref.ref(self)
             flat.append(f)
         self._flat = flat
         _lib.flat_buffers.extend(f for f in flat if f is not None)
@@ -693,6 +732,7 @@ class FusedAdamW(torch.optim.Optimizer):
     def zero_grad(self, set_to_none=False):
         """Clears the flat gradient buffers in place (the .grad views stay attached)."""
         self._synced = False
+        self._early_pending = []
         if self._flat is None:
             return super().zero_grad(set_to_none=True)
         for f in self._flat:
@@ -732,14 +772,75 @@ class FusedAdamW(torch.optim.Optimizer):
         return live
 
     @torch.no_grad()
+    def reduce_early(self, params, flush=False):
+        """Gradients of `params` are final for this step: queue them, and once early_sync_bytes are pending (or `flush`)
+        start the asynchronous average of their spans of the flat gradient buffers.  Every rank runs the same backward, so
+        every rank issues the same collectives in the same order."""
+        import torch.distributed as dist
+        if self._flat is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        self._early_pending.extend(params)
+        if not flush and sum(p.numel() for p in self._early_pending) * 4 < self.early_sync_bytes:
+            return
+        pending = set(id(p) for p in self._early_pending)
+        self._early_pending = []
+        pad = self.PAD
+        for fi, f in enumerate(self._flat):
+            if f is None:
+                continue
+            runs = []   # maximal runs of adjacent pending parameters: [lo, hi) in elements
+            for p, off in zip(f["params"], f["offsets"]):
+                if id(p) not in pending or p.grad is None or p.grad.data_ptr() != f["g"].data_ptr() + off * 4:
+                    continue
+                end = off + (p.numel() + pad - 1) // pad * pad
+                if runs and runs[-1][1] == off:
+                    runs[-1][1] = end
+                else:
+                    runs.append([off, end])
+            for lo, hi in runs:
+                hi = min(hi, f["g"].numel())
+                self._early_works.append(dist.all_reduce(f["g"][lo:hi], op=dist.ReduceOp.AVG, async_op=True)
+                                         if dist.get_backend() == "nccl" else
+                                         self._gloo_avg(f["g"][lo:hi]))
+                self._early_spans.append((fi, lo, hi))
+
+    @staticmethod
+    def _gloo_avg(t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t.div_(dist.get_world_size())
+        return None
+
+    @torch.no_grad()
     def sync_gradients(self, group=None):
-        """Average the gradients over the ranks: ONE all-reduce per parameter group over the flat buffer.  step() calls
-        it when `distributed` is set; call it yourself after backward() when something (clip_grad_norm_, logging) must
-        see the synchronised gradients before step()."""
+        """Average the gradients over the ranks: ONE all-reduce per parameter group over the flat buffer (minus the spans
+        reduce_early already handled).  step() calls it when `distributed` is set; call it yourself after backward() when
+        something (clip_grad_norm_, logging) must see the synchronised gradients before step()."""
         from .utils import sync_gradients
         if self._synced:
             return
-        sync_gradients([f["g"] for f in self._collect()], group)
+        live = self._collect()
+        if self._early_pending:
+            self.reduce_early([], flush=True)
+        if not self._early_spans:
+            sync_gradients([f["g"] for f in live], group)
+        else:
+            rest = []
+            for fi, f in enumerate(self._flat):
+                if f is None:
+                    continue
+                pos, n = 0, f["g"].numel()
+                for _, lo, hi in sorted(sp for sp in self._early_spans if sp[0] == fi):
+                    if lo > pos:
+                        rest.append(f["g"][pos:lo])
+                    pos = max(pos, hi)
+                if pos < n:
+                    rest.append(f["g"][pos:n])
+            sync_gradients(rest, group)
+            for w in self._early_works:
+                if w is not None:
+                    w.wait()        # (stream-level: the compute stream waits for NCCL's, the host does not)
+        self._early_spans, self._early_works = [], []
         self._synced = True
 
     def device_hyper(self, on=True):

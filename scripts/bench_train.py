@@ -56,6 +56,7 @@ def measure(a, rank, world, local_rank, dev):
     model, opt = make_model(42)
     model, opt = setup_for_distributed_mode(model, opt, dev, 1, local_rank if world > 1 else -1, a.fp16)
     model.train()
+    opt.overlap_grad_sync = world > 1   # one backward per step here: the gradient average may start under the backward
     sched = get_schedule_linear(opt, 10, 1000)
     largs = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=world)
 
@@ -110,6 +111,7 @@ def measure(a, rank, world, local_rank, dev):
         # distributed gradients (averaged over ranks) vs the same global batch on one rank alone; eval() mode = dropout
         # off (the two runs would otherwise draw different masks), gradients are recorded all the same
         model.eval()
+        overlap, opt.overlap_grad_sync = opt.overlap_grad_sync, False   # (the single-process leg below must not reduce)
         loss_d = step(model, None, None, batch, largs)
         opt.sync_gradients()
         g_dist = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
@@ -133,6 +135,7 @@ def measure(a, rank, world, local_rank, dev):
                  "grad_rel_l2_all_params": (num / den) ** 0.5, "worst_param": worst[0], "worst_param_rel": worst[1]}
         model.zero_grad()
         opt.zero_grad()
+        opt.overlap_grad_sync = overlap
 
     # batches arrive through PrefetchLoader (uniter_model/data/loader.py mirror): the H2D copy of step i + 1 (151 MB of
     # region features) runs on a side stream under step i, exactly how eval_itm.py / train_itm.py feed the model

@@ -173,7 +173,28 @@ def _train_worker(rank, world, port, tmp):
                 den += float(p.grad.norm()) ** 2
         rel = (num / den) ** 0.5
         assert rel <= 5e-3, rel     # 16-bit activation gradients take different reduction orders in the two runs
-        open(os.path.join(tmp, f"ok{rank}"), "w").write(f"{loss_s.item()} {rel}")
+        # overlapped gradient averaging (FusedAdamW.overlap_grad_sync): spans of the flat buffers are all-reduced while the
+        # backward is still running; the result must be the gradient average of the plain path
+        opt._collect()
+        opt.zero_grad()       # (also forgets that the gradients above were synchronised)
+        opt.overlap_grad_sync, opt.early_sync_bytes = True, 4 << 20
+        la = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=world)
+        run(batch(rank * b, rank * b + b), la)
+        torch.cuda.synchronize()
+        early = len(opt._early_spans)
+        covered = sum(hi - lo for _, lo, hi in opt._early_spans)
+        opt.sync_gradients()
+        total = sum(f["g"].numel() for f in opt._flat if f is not None)
+        assert early >= 6 and covered >= 0.5 * total, (early, covered, total)
+        assert not opt._early_spans and not opt._early_works
+        num = den = 0.0
+        for n, p in model.named_parameters():
+            if p.grad is not None:
+                num += float((g_dist[n] - p.grad).norm()) ** 2
+                den += float(g_dist[n].norm()) ** 2
+        rel2 = (num / den) ** 0.5
+        assert rel2 <= 1e-4, rel2   # (same computation; wgrad / column-sum atomics reorder)
+        open(os.path.join(tmp, f"ok{rank}"), "w").write(f"{loss_s.item()} {rel} {rel2}")
     finally:
         dist.destroy_process_group()
 
