@@ -189,7 +189,8 @@ int ldot_inbatch_nll(const float* d_scores, const float* d_scores_cap, float cap
  *                      wgrad    dW += dY^T X   a_mn 1, b_mn 1   A = dY [K = tokens, M = out], B = X [K = tokens, N = in],
  *                                                               accumulate = 1, fp32 out, split-K over the grid with
  *                                                               TMA reduce-add stores
- *                    epi: 0 none, 1 erf-GELU, 2 out = acc * GELU'(aux[m, n]), 3 out = acc + aux[m, n] (aux 16-bit)
+ *                    epi: 0 none, 1 erf-GELU, 2 out = acc * GELU'(aux[m, n]), 3 out = acc + aux[m, n], 4 out = acc * aux[m, n]
+ *                    (aux 16-bit)
  * ldot_layernorm_bwd dx = LayerNorm backward of y = LN(x) * gamma + beta given dy; dgamma / dbeta [H] += ; when
  *                    d_dxsum != NULL also dxsum[H] += sum_rows dx (the bias gradient of the Linear that produced x).
  *                    *_f32 flags: the tensor is fp32 instead of 16-bit.  H = 256 * {1,2,3,4,6}
@@ -242,8 +243,12 @@ int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16
  * ldot_linear_dropout   BertSelfOutput / BertOutput in training mode up to the LayerNorm (layer.py:111-115,152-156):
  *                       d_out = dropout(d_a . d_w^T + d_bias) (+ d_residual), the mask of ldot_dropout(site) applied in
  *                       the GEMM epilogue (element index row * N + col); 16-bit output, N % 8 == 0
- * ldot_linear_gelu_pre  BertIntermediate in training mode (layer.py:133-136): d_out = GELU(z) and d_pre = z =
- *                       d_a . d_w^T + d_bias, both 16-bit, written by one kernel (backward needs z, the next GEMM GELU(z))
+ * ldot_linear_gelu_grad BertIntermediate in training mode (layer.py:133-136): with z = d_a . d_w^T + d_bias rounded to 16 bit,
+ *                       d_out = GELU(z) and d_gp = GELU'(z), both 16-bit, from one kernel and one exponential: the next
+ *                       GEMM needs GELU(z), backward needs only GELU'(z) (ldot_gemm epi 4 multiplies by it)
+ * ldot_gelu_grad        the same pair from an elementwise pass over a stored pre-activation: d_out = GELU(z), and d_z_gp
+ *                       (z on entry) holds GELU'(z) on exit.  What the training forward uses: at K = 768 the GEMM epilogue
+ *                       that evaluates both is issue-bound (151 us against 60 + 51 us for GEMM + this pass, 17.6 k tokens)
  * ldot_layernorm_bwd_dropout   ldot_layernorm_bwd (16-bit dy / x / dx) for a LayerNorm whose input was
  *                       dropout(dense) + residual: d_dx gets the residual-branch gradient, d_dx_masked = mask * dx / keep
  *                       the dense-branch gradient (row pitch ld_dx), and d_dxsum sums the MASKED values (the dense bias
@@ -258,9 +263,10 @@ int ldot_adamw(float* d_p, const float* d_g, float* d_m, float* d_v, void* d_p16
 int ldot_linear_dropout(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias,
                         const void* d_residual, int64_t ldr, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K,
                         int32_t dtype, float drop_p, uint64_t seed, int32_t site, void* stream);
-int ldot_linear_gelu_pre(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_pre,
-                         int64_t ld_pre, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype,
+int ldot_linear_gelu_grad(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_gp,
+                          int64_t ld_gp, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype,
                          void* stream);
+int ldot_gelu_grad(void* d_z_gp, void* d_out, int64_t n, int32_t dtype, void* stream);
 int ldot_layernorm_bwd_dropout(const void* d_dy, int64_t ld_dy, const void* d_x, int64_t ld_x, const float* d_gamma,
                                void* d_dx, void* d_dx_masked, int64_t ld_dx, float* d_dgamma, float* d_dbeta,
                                float* d_dxsum, int64_t rows, int32_t H, float drop_p, uint64_t seed, int32_t site,

@@ -107,8 +107,9 @@ SIGNATURES = {
     # fused training forms + CUDA-graph support (ABI 6)
     "ldot_linear_dropout": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                       c_int64, c_int32, c_int32, c_int32, c_float, ctypes.c_uint64, c_int32, c_void_p]),
-    "ldot_linear_gelu_pre": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+    "ldot_linear_gelu_grad": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                        c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "ldot_gelu_grad": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "ldot_layernorm_bwd_dropout": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, ctypes.c_uint64,
                                              c_int32, c_int32, c_void_p]),

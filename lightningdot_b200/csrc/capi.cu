@@ -487,6 +487,12 @@ int ldot_gelu(const void* d_x, void* d_out, int64_t n, int32_t dtype, void* stre
   return gelu_run(d_x, nullptr, d_out, n, 0, dtype, stream);
 }
 
+int ldot_gelu_grad(void* d_z_gp, void* d_out, int64_t n, int32_t dtype, void* stream) {
+  LDOT_REQUIRE(d_z_gp && d_out && d_z_gp != d_out, "gelu_grad: two distinct buffers are required");
+  LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
+  return gelu_run(d_z_gp, d_z_gp, d_out, n, 2, dtype, stream);
+}
+
 int ldot_gelu_bwd(const void* d_x, const void* d_dy, void* d_dx, int64_t n, int32_t dtype, void* stream) {
   LDOT_REQUIRE(d_x && d_dy && d_dx, "null pointer argument");
   LDOT_REQUIRE(dtype == 0 || dtype == 1, "dtype must be 0 (fp16) or 1 (bf16)");
@@ -566,7 +572,7 @@ int ldot_linear_dropout(const void* d_a, int64_t lda, const void* d_w, int64_t l
   return linear_run(d_a, lda, d_w, ldw, d_bias, d_residual, ldr, d_out, ldo, M, N, K, dtype, 0, 0, stream, &drop);
 }
 
-int ldot_linear_gelu_pre(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_pre,
+int ldot_linear_gelu_grad(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, const float* d_bias, void* d_pre,
                          int64_t ld_pre, void* d_out, int64_t ldo, int64_t M, int32_t N, int32_t K, int32_t dtype,
                          void* stream) {
   LDOT_REQUIRE(d_a && d_w && d_out && d_pre, "null pointer argument");

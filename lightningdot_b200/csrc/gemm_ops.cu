@@ -47,7 +47,7 @@ template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0,
 static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, const LinSched& s,
                          const LinParams& p, int sms, cudaStream_t st) {
   auto kern = linear_tc_kernel<ACT, OUT_F32, CTAS, AMN, BMN, RED, TRAIN>;
-  using SM = LinSmemT<CTAS, lin_epi_warps(ACT)>;
+  using SM = LinSmemT<CTAS, lin_epi_warps(ACT, TRAIN)>;
   static bool configured = false;  // (one device per process)
   static int max_groups = 0;       // resident CTAs (CTAS = 1) or CTA pairs (CTAS = 2)
   cudaLaunchConfig_t cfg = {};
@@ -56,7 +56,7 @@ static int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const CUt
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(lin_threads(ACT));
+  cfg.blockDim = dim3(lin_threads(ACT, TRAIN));
   cfg.dynamicSmemBytes = SM::kDynamic;
   cfg.stream = st;
   cfg.attrs = attr;
@@ -157,8 +157,8 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
              int epi, int out_f32, int accumulate, void* stream) {
   LDOT_REQUIRE(M >= 1 && N >= 1 && K >= 1, "bad GEMM shape M=%lld N=%d K=%lld", M, N, K);
   LDOT_REQUIRE(fmt == 0 || fmt == 1, "fmt must be 0 (fp16) or 1 (bf16)");
-  LDOT_REQUIRE(epi >= 0 && epi <= 3, "epi must be 0 (none), 1 (GELU), 2 (* GELU'(aux)) or 3 (+ aux)");
-  LDOT_REQUIRE((epi == 2 || epi == 3) == (aux != nullptr), "aux is required by (and only by) epi 2 / 3");
+  LDOT_REQUIRE(epi >= 0 && epi <= 4, "epi must be 0 (none), 1 (GELU), 2 (* GELU'(aux)), 3 (+ aux) or 4 (* aux)");
+  LDOT_REQUIRE((epi >= 2) == (aux != nullptr), "aux is required by (and only by) epi 2 / 3 / 4");
   LDOT_REQUIRE(!accumulate || (out_f32 && epi == 0), "accumulate needs an fp32 output and no epilogue op");
   LDOT_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda / ldb must be multiples of 8 elements");
   LDOT_REQUIRE(a_mn ? (M % 8 == 0) : (K % 8 == 0), "the contiguous extent of A must be a multiple of 8");
@@ -170,7 +170,7 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
                "out / aux / bias must be 16-byte aligned");
   LDOT_REQUIRE(M < (1ll << 31) - 256 && K < (1ll << 31) - 64, "M / K too large");
   const int variant = (a_mn ? 2 : 0) | (b_mn ? 1 : 0);
-  if (variant == 0 && !accumulate && epi != 2)
+  if (variant == 0 && !accumulate && epi != 2 && epi != 4)
     return linear_run(a, lda, b, ldb, bias, epi == 3 ? aux : nullptr, ld_aux, out, ldo, M, N, static_cast<int>(K), fmt,
                       epi == 1 ? 1 : 0, out_f32, stream);
   // the forms the backward pass uses: dgrad (A K-major, B MN-major; 16-bit or fp32 out) and wgrad (both MN-major,
@@ -178,7 +178,7 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
   LDOT_REQUIRE((variant == 1 && !accumulate && epi != 1) || (variant == 3 && accumulate),
                "unsupported operand layout / epilogue combination (a_mn=%d b_mn=%d epi=%d accumulate=%d)", a_mn, b_mn,
                epi, accumulate);
-  LDOT_REQUIRE(!(epi == 2 && out_f32), "the GELU-gradient epilogue writes 16-bit output");
+  LDOT_REQUIRE(!((epi == 2 || epi == 4) && out_f32), "the GELU-gradient / product epilogues write 16-bit output");
   int sms = 0;
   if (int e = device_sm_count(&sms)) return e;
   // (wgrad tiles are few and K-split: CTA pairs would only halve the number of work items)
@@ -231,6 +231,7 @@ int gemm_run(const void* a, long long lda, int a_mn, const void* b, long long ld
              : launch_linear<ACT, F32, 1, AMN, BMN, RED>(ta, tb, to, s, p, sms, st))
   if (variant == 3) return launch_linear<0, 1, 1, 1, 1, 1>(ta, tb, to, s, p, sms, st);
   if (epi == 2) return LDOT_G(2, 0, 0, 1, 0);
+  if (epi == 4) return LDOT_G(3, 0, 0, 1, 0);
   return out_f32 ? LDOT_G(0, 1, 0, 1, 0) : LDOT_G(0, 0, 0, 1, 0);
 #undef LDOT_G
 }

@@ -40,8 +40,12 @@ constexpr int kLinThreads = 32 * (2 + kLinEpiWarps);
 // a pipe: it runs with 16 epilogue warps (4 per scheduler, 96 registers each) and pays for their staging buffers with
 // two pipeline stages.  Measured at 320k tokens: 8 warps 879, 12 warps 1004, 16 warps 1076 TFLOP/s.  The GELU' form of
 // the backward (ACT = 2, heavier per element, 128 registers) runs with 12.
-__host__ __device__ constexpr int lin_epi_warps(int act) { return act == 1 ? 16 : act == 2 ? 12 : 8; }
-__host__ __device__ constexpr int lin_threads(int act) { return 32 * (2 + lin_epi_warps(act)); }
+// The training form of the GELU epilogue (TRAIN: also stores the pre-activation and rounds it before GELU) does not fit 96
+// registers - ncu showed local-memory reloads on its critical path, tensor pipe 39 % - and runs with 12 warps of 128.
+__host__ __device__ constexpr int lin_epi_warps(int act, int train = 0) {
+  return act == 1 ? (train ? 12 : 16) : act == 2 ? 12 : 8;   // (act 3: out = acc * aux, as light as the residual add)
+}
+__host__ __device__ constexpr int lin_threads(int act, int train = 0) { return 32 * (2 + lin_epi_warps(act, train)); }
 
 struct LinSched {
   int m_tiles, n_tiles, num_tiles, k_blocks;
@@ -60,8 +64,8 @@ struct LinParams {
   int fmt;                // 0 = fp16, 1 = bf16 (A, W, residual, 16-bit output)
   // training forward (ACT 0): out = dropout(acc + bias) (+ residual), mask element index row * N + col (drop.thr 0: off)
   DropKey drop;
-  // training forward (ACT 1): the pre-activation acc + bias is ALSO written, 16-bit [M, ld_pre] (null: not written) -
-  // backward needs GELU's input and the next GEMM its output
+  // training forward (ACT 1): GELU'(z) of the pre-activation z = acc + bias is ALSO written, 16-bit [M, ld_pre] (null: not
+  // written) - the next GEMM needs GELU(z), backward only GELU'(z)
   void* pre;
   long long ld_pre;
 };
@@ -106,17 +110,18 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int fmt) {
 //                   64 (K rows) x 64 (MN, 128 B) SWIZZLE_128B boxes, 8 KB apart per 64-wide MN block; the shared-memory
 //                   descriptor carries LBO = 8192 (MN block pitch), SBO = 1024 (8 K rows), and one 16-deep K step
 //                   advances the start address by 2048 B.
-//   ACT = 2         out = acc * gelu'(aux[m, n]) with aux = p.residual (the saved FFN-up pre-activation)
+//   ACT = 2         out = acc * gelu'(aux[m, n]) with aux = p.residual (a saved FFN-up pre-activation)
+//   ACT = 3         out = acc * aux[m, n] (aux = the GELU'(z) the training forward stored)
 //   RED = 1         fp32 output boxes are ADDED to global memory (cp.reduce.async.bulk.tensor .add): gradient
 //                   accumulation, and what makes split-K (sched.k_splits > 1) a pure scheduling decision.
 //   TRAIN = 1       the training-forward epilogues: dropout of the dense output (ACT 0, p.drop) / the pre-activation
 //                   written next to GELU's output (ACT 1, p.pre).  A template flag so that the inference
 //                   instantiations keep their register budget (the 16-warp GELU form has 96 per thread).
 template <int ACT, int OUT_F32, int CTAS, int AMN = 0, int BMN = 0, int RED = 0, int TRAIN = 0>
-__global__ void __launch_bounds__(lin_threads(ACT), 1)
+__global__ void __launch_bounds__(lin_threads(ACT, TRAIN), 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_out, const LinSched sched, const LinParams p) {
-  constexpr int EW = lin_epi_warps(ACT);   // epilogue warps
+  constexpr int EW = lin_epi_warps(ACT, TRAIN);   // epilogue warps
   constexpr int EC = EW / 4;               // ... per TMEM lane quarter: they share the row block's 32-column boxes
   using SM = LinSmemT<CTAS, EW>;
   constexpr int kStages = SM::kStages;
@@ -297,11 +302,27 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     };
     const int mn_tiles = sched.m_tiles * sched.n_tiles;
+    // The residual / aux operand of the epilogue (p.residual: one 32-byte piece per thread and slice, rows 2 N bytes apart)
+    // is requested into L2 a whole tile ahead: read on first use it costs a DRAM round trip per slice on the epilogue's
+    // critical path (the GELU' dgrad of the training step: tensor pipe 38 %, every sample on the first use of the load).
+    auto prefetch_aux = [&](int t) {
+      if (ACT == 1 || p.residual == nullptr || t >= sched.num_tiles) return;   // (the GELU forms take no residual)
+      const int tt = t % mn_tiles;
+      const int m_pair = tt / sched.n_tiles, n_tile = tt - m_pair * sched.n_tiles;
+      const long long grow = static_cast<long long>(m_pair * CTAS + rank) * kBM + row;
+      if (grow >= p.M) return;
+      const uint16_t* base = static_cast<const uint16_t*>(p.residual) + grow * p.ldr + n_tile * kLinBN;
+      for (int bx = cgrp; bx < kLinBN / 32; bx += EC)
+        if (n_tile * kLinBN + bx * 32 < p.N)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + bx * 32));
+    };
+    prefetch_aux(first_tile);
     for (int t = first_tile; t < sched.num_tiles; t += tile_step) {
       const int ks = t / mn_tiles, tt = t - ks * mn_tiles;
       const int m_pair = tt / sched.n_tiles, n_tile = tt - m_pair * sched.n_tiles;
       const int m_tile = m_pair * CTAS + rank;   // 128-row block of this CTA
       const float* bias = ks == 0 ? p.bias : nullptr;   // (split-K: the first slice carries the bias)
+      prefetch_aux(t + tile_step);
       const long long grow = static_cast<long long>(m_tile) * kBM + row;
       const bool row_ok = grow < p.M;
       const int tile_col = n_tile * kLinBN;
@@ -380,38 +401,39 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
               }
               if (ACT == 1) {
-                if (TRAIN && p.pre != nullptr && row_ok) {
-                  uint16_t* pre = static_cast<uint16_t*>(p.pre) + grow * p.ld_pre + col;
-                  if (full_slice) {
+                if (TRAIN) {
+                  // training forward: GELU of the 16-bit-ROUNDED pre-activation (the tensor amp hands to F.gelu in the
+                  // reference) and, from the same exponential, GELU'(z) - stored as 16 bit in p.pre: all that backward
+                  // needs of z, so that the dgrad epilogue is one multiply instead of a second GELU evaluation
+                  float gp[16];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                      uint4 w;
-                      w.x = pack2(f[8 * j], f[8 * j + 1], p.fmt);
-                      w.y = pack2(f[8 * j + 2], f[8 * j + 3], p.fmt);
-                      w.z = pack2(f[8 * j + 4], f[8 * j + 5], p.fmt);
-                      w.w = pack2(f[8 * j + 6], f[8 * j + 7], p.fmt);
-                      reinterpret_cast<uint4*>(pre)[j] = w;
-                      // GELU sees the ROUNDED pre-activation, as in the reference (the 16-bit tensor is what amp hands to
-                      // F.gelu) and as backward's GELU'(pre) assumes
-                      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                  for (int j = 0; j < 8; ++j) {
+                    const float2 z = unpack2(pack2(f[2 * j], f[2 * j + 1], p.fmt), p.fmt);
+                    gelu_erf_both(z.x, f[2 * j], gp[2 * j]);
+                    gelu_erf_both(z.y, f[2 * j + 1], gp[2 * j + 1]);
+                  }
+                  if (p.pre != nullptr && row_ok) {
+                    uint16_t* pre = static_cast<uint16_t*>(p.pre) + grow * p.ld_pre + col;
+                    if (full_slice) {
 #pragma unroll
-                      for (int q = 0; q < 4; ++q) {
-                        const float2 x = unpack2(ww[q], p.fmt);
-                        f[8 * j + 2 * q] = x.x;
-                        f[8 * j + 2 * q + 1] = x.y;
+                      for (int j = 0; j < 2; ++j) {
+                        uint4 w;
+                        w.x = pack2(gp[8 * j], gp[8 * j + 1], p.fmt);
+                        w.y = pack2(gp[8 * j + 2], gp[8 * j + 3], p.fmt);
+                        w.z = pack2(gp[8 * j + 4], gp[8 * j + 5], p.fmt);
+                        w.w = pack2(gp[8 * j + 6], gp[8 * j + 7], p.fmt);
+                        reinterpret_cast<uint4*>(pre)[j] = w;
                       }
-                    }
-                  } else {
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                      const uint32_t h = pack2(f[j], 0.f, p.fmt);
-                      f[j] = unpack2(h, p.fmt).x;
-                      if (col + j < p.N) pre[j] = static_cast<uint16_t>(h & 0xFFFFu);
+                      for (int j = 0; j < 16; ++j)
+                        if (col + j < p.N) pre[j] = static_cast<uint16_t>(pack2(gp[j], 0.f, p.fmt) & 0xFFFFu);
                     }
                   }
-                }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+                  for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+                }
               }
               if (p.residual != nullptr && row_ok) {
                 if (full_slice) {
@@ -424,6 +446,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                       if (ACT == 2) {
                         f[j4 * 8 + q * 2] *= gelu_erf_grad(x.x);
                         f[j4 * 8 + q * 2 + 1] *= gelu_erf_grad(x.y);
+                      } else if (ACT == 3) {
+                        f[j4 * 8 + q * 2] *= x.x;
+                        f[j4 * 8 + q * 2 + 1] *= x.y;
                       } else {
                         f[j4 * 8 + q * 2] += x.x;
                         f[j4 * 8 + q * 2 + 1] += x.y;
@@ -437,6 +462,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (col + j < p.N) {
                       const float x = unpack2(static_cast<uint32_t>(r16[j]), p.fmt).x;
                       if (ACT == 2) f[j] *= gelu_erf_grad(x);
+                      else if (ACT == 3) f[j] *= x;
                       else f[j] += x;
                     }
                 }

@@ -137,10 +137,10 @@ class TowerTrainer(object):
             _lib.ptr(a), a.stride(0), _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(residual), residual.stride(0),
             _lib.ptr(out), out.stride(0), M, N, K, self.e.fmt, self.p_hidden, self.seed, site, _lib.stream_ptr()))
 
-    def _linear_gelu_pre(self, a, wt, bias, pre, out, M):
-        """pre = a . wt^T + bias and out = GELU(pre) from one kernel."""
+    def _linear_gelu_grad(self, a, wt, bias, pre, out, M):
+        """With z = a . wt^T + bias (rounded to 16 bit): out = GELU(z) and pre = GELU'(z) from one kernel."""
         N, K = wt.shape
-        _lib.check(_lib.load().ldot_linear_gelu_pre(
+        _lib.check(_lib.load().ldot_linear_gelu_grad(
             _lib.ptr(a), a.stride(0), _lib.ptr(wt), K, _lib.ptr(bias), _lib.ptr(pre), pre.stride(0), _lib.ptr(out),
             out.stride(0), M, N, K, self.e.fmt, _lib.stream_ptr()))
 
@@ -179,7 +179,10 @@ class TowerTrainer(object):
             else:
                 e._linear(ctx, H, w[f"o_w{i}"], w[f"o_b{i}"], pre1, T, residual=h)
             e._layernorm(pre1, w[f"ln1_g{i}"], w[f"ln1_b{i}"], a, T, H)
-            self._linear_gelu_pre(a, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, f, T)
+            # FFN-up: z = a W1^T + b1 from the plain GEMM, then one bandwidth-bound pass f = GELU(z), fpre <- GELU'(z)
+            # (the epilogue that evaluates both - _linear_gelu_grad - is issue-bound at K = 768 and slower than the pair)
+            e._linear(a, H, w[f"f1_w{i}"], w[f"f1_b{i}"], fpre, T)
+            _lib.check(lib.ldot_gelu_grad(_lib.ptr(fpre), _lib.ptr(f), fpre.numel(), e.fmt, stream))
             if ph:
                 self._linear_dropout(f, w[f"f2_w{i}"], w[f"f2_b{i}"], a, pre2, T, 4 * i + 2)
             else:
@@ -326,7 +329,7 @@ class TowerTrainer(object):
             g.z(p + "output.dense.weight", H, F)
             self._wgrad(d_o2, f, g[p + "output.dense.weight"], T)
             d_fpre = buf(T, F)
-            self._dgrad(d_o2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=2)
+            self._dgrad(d_o2, w[f"f2_w{i}"], d_fpre, T, aux=fpre, epi=4)   # d z = (d_o2 W2) * GELU'(z)
             del d_o2
             # BertIntermediate
             g.z(p + "intermediate.dense.weight", F, H)

@@ -52,6 +52,10 @@ def test_dgrad_epilogues(cuda_lib):
     torch.nn.functional.gelu(x).sum().backward()
     ref = (dy.float() @ w.float()) * x.grad
     torch.testing.assert_close(out.float(), ref, atol=4e-2, rtol=8e-3)
+    # epi 4: * aux (the GELU'(z) stored by the training forward)
+    _lib.check(cuda_lib.ldot_gemm(_lib.ptr(dy), K, 0, _lib.ptr(w), N, 1, None, _lib.ptr(aux), N, _lib.ptr(out), N, M, N, K,
+                                  fmt, 4, 0, 0, _lib.stream_ptr()))
+    torch.testing.assert_close(out.float(), (dy.float() @ w.float()) * aux.float(), atol=4e-2, rtol=8e-3)
 
 
 @pytest.mark.parametrize("T,O,I", [(64, 256, 128), (1000, 768, 768), (5000, 3072, 768), (4100, 768, 3072), (37, 1536, 768),
@@ -240,27 +244,56 @@ def test_linear_dropout_equals_linear_then_dropout(cuda_lib, M, N, K, fmt):
 
 @pytest.mark.parametrize("M,N,K", [(37, 3072, 768), (20000, 3072, 768), (130, 200, 72)])
 @pytest.mark.parametrize("fmt", [0, 1])
-def test_linear_gelu_pre_writes_both(cuda_lib, M, N, K, fmt):
-    """ldot_linear_gelu_pre: the pre-activation and GELU of it from one kernel, bit-identical to ldot_linear (act 0)
-    followed by ldot_gelu on its 16-bit output (GELU sees the rounded pre-activation, as under amp in the reference)."""
+def test_linear_gelu_grad_writes_both(cuda_lib, M, N, K, fmt):
+    """ldot_linear_gelu_grad: GELU(z) and GELU'(z) of the 16-bit-rounded pre-activation z from one kernel.  GELU(z) is
+    bit-identical to ldot_linear (act 0) followed by ldot_gelu on its 16-bit output (what amp does in the reference);
+    GELU'(z) against torch autograd on that same rounded z."""
     g = gen(22)
     a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(DT[fmt])
     w = (torch.randn(N, K, device="cuda", generator=g) * 0.1).to(DT[fmt])
     b = torch.randn(N, device="cuda", generator=g)
-    pre = torch.zeros((M, N), device="cuda", dtype=DT[fmt])
+    gp = torch.zeros((M, N), device="cuda", dtype=DT[fmt])
     out = torch.zeros((M, N), device="cuda", dtype=DT[fmt])
-    _lib.check(cuda_lib.ldot_linear_gelu_pre(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(pre), N, _lib.ptr(out), N,
-                                             M, N, K, fmt, _lib.stream_ptr()))
-    pre2 = torch.zeros_like(pre)
+    _lib.check(cuda_lib.ldot_linear_gelu_grad(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), _lib.ptr(gp), N, _lib.ptr(out), N,
+                                              M, N, K, fmt, _lib.stream_ptr()))
+    z = torch.zeros_like(out)
     out2 = torch.zeros_like(out)
-    _lib.check(cuda_lib.ldot_linear(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), None, 0, _lib.ptr(pre2), N, M, N, K, fmt,
+    _lib.check(cuda_lib.ldot_linear(_lib.ptr(a), K, _lib.ptr(w), K, _lib.ptr(b), None, 0, _lib.ptr(z), N, M, N, K, fmt,
                                     0, 0, _lib.stream_ptr()))
-    _lib.check(cuda_lib.ldot_gelu(_lib.ptr(pre2), _lib.ptr(out2), pre2.numel(), fmt, _lib.stream_ptr()))
-    assert torch.equal(pre, pre2)
+    _lib.check(cuda_lib.ldot_gelu(_lib.ptr(z), _lib.ptr(out2), z.numel(), fmt, _lib.stream_ptr()))
     assert torch.equal(out, out2)
+    zr = z.double().requires_grad_(True)
+    torch.nn.functional.gelu(zr).sum().backward()
+    tol = dict(atol=8e-3, rtol=8e-3) if fmt == 1 else dict(atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(gp.double(), zr.grad, **tol)
     ref = torch.nn.functional.gelu(a.float() @ w.float().T + b)
     tol = dict(atol=4e-2, rtol=1.6e-2) if fmt == 1 else dict(atol=6e-3, rtol=2e-3)
     torch.testing.assert_close(out.float(), ref, **tol)
+
+
+@pytest.mark.parametrize("fmt", [0, 1])
+def test_gelu_grad_in_place(cuda_lib, fmt):
+    """ldot_gelu_grad: out = GELU(z) (bit-identical to ldot_gelu) and the z buffer holds GELU'(z) afterwards."""
+    g = gen(25)
+    z = (torch.randn(777, 3072, device="cuda", generator=g) * 2).to(DT[fmt])
+    want_g = torch.empty_like(z)
+    _lib.check(cuda_lib.ldot_gelu(_lib.ptr(z), _lib.ptr(want_g), z.numel(), fmt, _lib.stream_ptr()))
+    zr = z.double().requires_grad_(True)
+    torch.nn.functional.gelu(zr).sum().backward()
+    buf, out = z.clone(), torch.empty_like(z)
+    _lib.check(cuda_lib.ldot_gelu_grad(_lib.ptr(buf), _lib.ptr(out), z.numel(), fmt, _lib.stream_ptr()))
+    assert torch.equal(out, want_g)
+    tol = dict(atol=8e-3, rtol=8e-3) if fmt == 1 else dict(atol=1e-3, rtol=1e-3)
+    torch.testing.assert_close(buf.double(), zr.grad, **tol)
+
+
+def test_gelu_grad_saturates_cleanly(cuda_lib):
+    """GELU' at extreme pre-activations (the polynomial argument is clamped): exactly 0 / 1, no NaN."""
+    x = torch.tensor([-3e38, -65504.0, -100.0, -21.0, 21.0, 100.0, 65504.0, 3e38], device="cuda").to(torch.bfloat16)
+    dy = torch.ones_like(x)
+    dx = torch.empty_like(x)
+    _lib.check(cuda_lib.ldot_gelu_bwd(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dx), x.numel(), 1, _lib.stream_ptr()))
+    assert dx.float().tolist() == [0.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, 1.0]
 
 
 @pytest.mark.parametrize("rows,H", [(1, 768), (37, 768), (20000, 768), (300, 256)])

@@ -139,8 +139,10 @@ def test_train_step_gradients_vs_oracle_and_reference(cuda_lib, golden_dir, dtyp
             g = params[str(n)].grad.cpu()
             assert abs(g.norm().item() - norm) <= gtol * norm + 2e-4 * top, (tag, n)
             got = g.reshape(-1)[otrain.sample_index(g.numel())].numpy()
-            assert np.abs(got - samples).max() <= (5 * gtol / 3) * np.abs(samples).max() + (gtol / 3) * norm / np.sqrt(g.numel()) \
-                + 2e-4 * top, (tag, n)
+            # (entry scale = rms over the entries that carry a gradient: embedding tables receive one for the rows the batch
+            # uses only - 1 of 512 rows of the image tower's position table)
+            rms = norm / np.sqrt(max(1, int((g != 0).sum())))
+            assert np.abs(got - samples).max() <= (5 * gtol / 3) * np.abs(samples).max() + (gtol / 3) * rms + 2e-4 * top, (tag, n)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
