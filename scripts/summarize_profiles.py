@@ -122,6 +122,10 @@ def main():
     for i, nm in enumerate(["linear_qkv", "linear_oproj", "linear_ffn1_gelu", "linear_ffn2", "linear_next"]):
         ncu_report(tag, "prof_linear.ncu-rep", nm, "linear_tcgen05" if nm == "linear_ffn1_gelu" else None, i, traffic)
     ncu_report(tag, "prof_attention.ncu-rep", "attention_fwd", None, 0, None)
+    # training-step kernels (scripts/ncu_train.sh)
+    for rep, nm in (("train_ln_bwd16.ncu-rep", "train_ln_bwd_dropout"), ("train_gelu_pre.ncu-rep", "train_ffn_up_fused_epilogue"),
+                    ("train_dgrad_gelu.ncu-rep", "train_ffn_up_dgrad"), ("train_attention_bwd.ncu-rep", "train_attention_bwd")):
+        ncu_report(tag, rep, nm, None, 0, None)
     shape_traffic(tag, traffic)
     old = os.path.join(OUT, "traffic.json")
     if os.path.exists(old):   # keep entries this run had no capture for
