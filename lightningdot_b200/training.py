@@ -945,12 +945,14 @@ class GraphedTrainStep(object):
     the end of every replay (ldot_dropout_epoch), lr and the Adam bias corrections are read from device memory
     (FusedAdamW.device_hyper), inputs are copied into the static batch the graph reads.  `pos_ctx_indices` (a Python list
     in the reference's batches) is kept as a device tensor.  `warmup` eager steps run first (they are real steps): they
-    lay out the optimiser's flat buffers and validate the batch (the checks a capture cannot perform).
+    lay out the optimiser's flat buffers and validate the batch (the checks a capture cannot perform); when the flat
+    buffers do not exist yet one extra eager step is added (`layout_step`), so that the capture is preceded by an eager
+    run of exactly the sequence it records - under a process group that is REQUIRED (NCCL connects lazily).
     Do not keep losses of EARLIER eager steps alive with their grad_fn (store loss.detach()): autograd caches a
     parameter's AccumulateGrad node, with the stream it was created on, for as long as any graph references it, and ends
     every backward by joining those streams - inside a capture that is a dependency on uncaptured work."""
 
-    def __init__(self, fwd_bwd, optimizer, batch, scheduler=None, warmup=2):
+    def __init__(self, fwd_bwd, optimizer, batch, scheduler=None, warmup=2, layout_step=True):
         if not isinstance(optimizer, FusedAdamW):
             raise TypeError("GraphedTrainStep drives FusedAdamW (get_optimizer returns it)")
         lib = _lib.load()
@@ -972,7 +974,12 @@ class GraphedTrainStep(object):
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
-            for _ in range(max(1, int(warmup))):
+            # The step that lays the optimiser's flat buffers out is not the steady-state step (no gradient sinks yet, no
+            # overlapped gradient average): one more eager step runs the exact launch / collective sequence the capture
+            # will record - NCCL establishes connections lazily at the first use of a collective, which must not happen
+            # under capture.
+            n_warm = max(1, int(warmup)) + (1 if (layout_step and optimizer._flat is None) else 0)
+            for _ in range(n_warm):
                 self.warmup_losses.append(self._eager().detach().clone())
         cur.wait_stream(side)
         torch.cuda.synchronize()

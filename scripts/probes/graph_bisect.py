@@ -50,7 +50,7 @@ def eager(clip, dev_hyper=False, reload=False):
 
 def graphed(clip):
     m, o, s = make(clip)
-    g = GraphedTrainStep(fb(m), o, batches[0], scheduler=s, warmup=1)
+    g = GraphedTrainStep(fb(m), o, batches[0], scheduler=s, warmup=1, layout_step=False)
     out = [g.warmup_losses[0].item()] + [g(bt).item() for bt in batches[1:]]
     return out, m
 

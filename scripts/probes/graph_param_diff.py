@@ -44,7 +44,7 @@ for s, bt in enumerate(batches):
     ga = {n: p.grad.clone() for n, p in ma.named_parameters() if p.grad is not None}
     oa.step(); sa.step(); oa.zero_grad()
     if g is None:
-        g = GraphedTrainStep(fb(mb), ob, bt, scheduler=sb, warmup=1)
+        g = GraphedTrainStep(fb(mb), ob, bt, scheduler=sb, warmup=1, layout_step=False)
         lb = g.warmup_losses[0].item()
     else:
         lb = g(bt).item()

@@ -43,7 +43,7 @@ for rep in range(2):
         out.append(r(bt).item()); o.step(); o.zero_grad()
     print("eager  ", " ".join(f"{v:.6f}" for v in out))
 m, o = make()
-g = GraphedTrainStep(fb(m), o, batches[0], warmup=1)
+g = GraphedTrainStep(fb(m), o, batches[0], warmup=1, layout_step=False)
 out = [v.item() for v in g.warmup_losses]
 for bt in batches[1:]:
     out.append(g(bt).item())

@@ -202,3 +202,71 @@ def _train_worker(rank, world, port, tmp):
 def test_global_batch_training_step_equals_single_gpu_step(tmp_path):
     mp.spawn(_train_worker, args=(2, _port(), str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(2))
+
+
+def _graph_worker(rank, world, port, tmp):
+    _init(rank, world, port)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    try:
+        from lightningdot_b200 import synth
+        from lightningdot_b200.bi_encoder import (BiEncoder, BiEncoderNllLoss, TowerConfig, get_optimizer, get_schedule_linear,
+                                                  setup_for_distributed_mode)
+        from lightningdot_b200.training import GraphedTrainStep
+        from lightningdot_b200.utils import _calc_loss
+        b, layers, steps = 16, 2, 5
+        B = b * world
+        torch.manual_seed(9)
+        cfg = dict(img_model_type='uniter-base', img_model_config=TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=layers),
+                   img_checkpoint=None, txt_model_type='bert-base',
+                   txt_model_config=TowerConfig(vocab_size=synth.VOCAB, num_hidden_layers=layers), txt_checkpoint=None)
+        model = BiEncoder(types.SimpleNamespace(**cfg), project_dim=768)
+        opt = get_optimizer(model, learning_rate=2e-6, adam_eps=1e-4, weight_decay=0.01)
+        opt.max_grad_norm = 2.0
+        model, opt = setup_for_distributed_mode(model, opt, dev, 1, rank, False)
+        model.train()                                   # dropout on: every rank draws its own masks
+        opt.overlap_grad_sync, opt.early_sync_bytes = True, 4 << 20
+        sched = get_schedule_linear(opt, 2, 50)
+        la = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=world)
+
+        def batch(seed):
+            tb, ib = synth.text_batch(B, 32, seed=seed, ragged=True), synth.image_batch(B, 36, seed=seed + 50, ragged=True)
+            lo, hi = rank * b, rank * b + b
+
+            def sl(d):
+                return {k: (v[lo:hi].contiguous() if (torch.is_tensor(v) and v.shape[0] == B) else v) for k, v in d.items()}
+            return {"txts": sl(tb), "imgs": sl(ib), "caps": {"input_ids": None}, "pos_ctx_indices": list(range(b))}
+
+        def fwd_bwd(bt):
+            t, i, _ = model(bt)
+            l1, _, _ = _calc_loss(la, BiEncoderNllLoss(), i, t, None, bt["pos_ctx_indices"], None)
+            l2, _, _ = _calc_loss(la, BiEncoderNllLoss(), t, i, None, bt["pos_ctx_indices"], None)
+            loss = 0.5 * l1 + 0.5 * l2
+            loss.backward()
+            return loss
+
+        gstep = GraphedTrainStep(fwd_bwd, opt, batch(0), scheduler=sched, warmup=1)
+        losses = [gstep(batch(s)).item() for s in range(2, steps)]
+        assert all(np.isfinite(losses)), losses
+        assert gstep.steps_taken == steps and int(gstep.epoch.item()) == steps - 2   # (two eager warm-up steps)
+        # the ranks took the same steps: parameters stay identical across the group (gradients were averaged inside the
+        # captured step - embedding all-gather, reduce-scatter, overlapped all-reduce are graph nodes)
+        worst = 0.0
+        for f in opt._flat:
+            if f is not None:
+                ref = f["p"].clone()
+                dist.broadcast(ref, src=0)
+                worst = max(worst, (ref - f["p"]).abs().max().item())
+        assert worst <= 1e-9, worst      # (the clip factor comes from an atomics-ordered norm: last-bit differences)
+        moved = max((f["m"].abs().max().item() for f in opt._flat if f is not None))
+        assert moved > 0
+        open(os.path.join(tmp, f"ok{rank}"), "w").write(json.dumps(losses))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_graphed_train_step_two_ranks(tmp_path):
+    """training.GraphedTrainStep under a 2-rank NCCL group: the captured step contains the collectives of the global-batch
+    loss and the overlapped gradient average; replays keep the ranks' parameters identical."""
+    mp.spawn(_graph_worker, args=(2, _port(), str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(2))

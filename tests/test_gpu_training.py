@@ -603,7 +603,7 @@ def test_graphed_train_step_follows_the_eager_trajectory(cuda_lib):
     mb, ob = _bi_encoder(3, lr)
     mb.eval()
     sb = get_schedule_linear(ob, 3, 50)
-    gstep = GraphedTrainStep(_fwd_bwd(mb, largs), ob, batches[0], scheduler=sb, warmup=1)
+    gstep = GraphedTrainStep(_fwd_bwd(mb, largs), ob, batches[0], scheduler=sb, warmup=1, layout_step=False)
     graphed = [v.item() for v in gstep.warmup_losses]
     for bt in batches[1:]:
         graphed.append(gstep(bt).item())
