@@ -948,6 +948,7 @@ class GraphedTrainStep(object):
     lay out the optimiser's flat buffers and validate the batch (the checks a capture cannot perform); when the flat
     buffers do not exist yet one extra eager step is added (`layout_step`), so that the capture is preceded by an eager
     run of exactly the sequence it records - under a process group that is REQUIRED (NCCL connects lazily).
+    Under a process group call release() before destroy_process_group() (see there).
     Do not keep losses of EARLIER eager steps alive with their grad_fn (store loss.detach()): autograd caches a
     parameter's AccumulateGrad node, with the stream it was created on, for as long as any graph references it, and ends
     every backward by joining those streams - inside a capture that is a dependency on uncaptured work."""
@@ -993,6 +994,17 @@ class GraphedTrainStep(object):
                 self.epoch.add_(1)
         finally:
             _lib.check(lib.ldot_dropout_epoch(None))
+
+    def release(self):
+        """Destroy the captured graph and its memory pool.  REQUIRED before torch.distributed.destroy_process_group() when the
+        step was captured under a process group: NCCL cannot tear a communicator down while a graph that captured its
+        collectives still exists - destroy_process_group() then blocks forever (scripts/probes/graph_two_ranks.py)."""
+        import gc
+        self.graph = None
+        self.loss = None
+        self.static = None
+        gc.collect()
+        torch.cuda.synchronize()
 
     def _eager(self):
         loss = self.fwd_bwd(self.static)

@@ -167,9 +167,13 @@ def measure(a, rank, world, local_rank, dev):
     # eager step goes away.  Batches still arrive through PrefetchLoader (H2D on the side stream) and are copied into the
     # graph's static inputs; lr schedule, Adam bias corrections and dropout masks advance per replay.
     graph_info = None
-    if getattr(a, "graph", True):
+    # (under a process group the captured step contains NCCL collectives - embedding all-gather / reduce-scatter, the
+    # overlapped gradient all-reduce; the graph is released below, before anything can destroy the process group)
+    want_graph = getattr(a, "graph", True)
+    if want_graph:
         from lightningdot_b200.training import GraphedTrainStep
         ok = 1
+        gstep = None
         try:
             dev_batch = next(iter(PrefetchLoader([batch], dev)))
             gstep = GraphedTrainStep(lambda bt: fwd_bwd(model, bt, largs), opt, dev_batch, scheduler=sched, warmup=1)
@@ -201,6 +205,8 @@ def measure(a, rank, world, local_rank, dev):
             ms_step = gms / a.steps
             graph_info = {"captured": True, "ms_per_step": ms_step, "eager_ms_per_step": eager_ms_step,
                           "loss_first_last": [glosses[0].item(), glosses[-1].item()]}
+        if gstep is not None:
+            gstep.release()
     peak_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peak_file)).get("bf16_tflops_sustained", 1400.0) if os.path.exists(peak_file) else 1400.0
     if rank == 0:

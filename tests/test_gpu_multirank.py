@@ -208,6 +208,7 @@ def _graph_worker(rank, world, port, tmp):
     _init(rank, world, port)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", device_id=dev)
+    gstep = None
     try:
         from lightningdot_b200 import synth
         from lightningdot_b200.bi_encoder import (BiEncoder, BiEncoderNllLoss, TowerConfig, get_optimizer, get_schedule_linear,
@@ -224,7 +225,7 @@ def _graph_worker(rank, world, port, tmp):
         opt = get_optimizer(model, learning_rate=2e-6, adam_eps=1e-4, weight_decay=0.01)
         opt.max_grad_norm = 2.0
         model, opt = setup_for_distributed_mode(model, opt, dev, 1, rank, False)
-        model.train()                                   # dropout on: every rank draws its own masks
+        model.train()                                   # dropout on
         opt.overlap_grad_sync, opt.early_sync_bytes = True, 4 << 20
         sched = get_schedule_linear(opt, 2, 50)
         la = types.SimpleNamespace(caption_score_weight=0.0, distributed_world_size=world)
@@ -247,8 +248,11 @@ def _graph_worker(rank, world, port, tmp):
 
         gstep = GraphedTrainStep(fwd_bwd, opt, batch(0), scheduler=sched, warmup=1)
         losses = [gstep(batch(s)).item() for s in range(2, steps)]
+        taken, epoch = gstep.steps_taken, int(gstep.epoch.item())
+        gstep.release()
+        gstep = None
         assert all(np.isfinite(losses)), losses
-        assert gstep.steps_taken == steps and int(gstep.epoch.item()) == steps - 2   # (two eager warm-up steps)
+        assert taken == steps and epoch == steps - 2    # (two eager warm-up steps: layout + steady state)
         # the ranks took the same steps: parameters stay identical across the group (gradients were averaged inside the
         # captured step - embedding all-gather, reduce-scatter, overlapped all-reduce are graph nodes)
         worst = 0.0
@@ -257,16 +261,17 @@ def _graph_worker(rank, world, port, tmp):
                 ref = f["p"].clone()
                 dist.broadcast(ref, src=0)
                 worst = max(worst, (ref - f["p"]).abs().max().item())
-        assert worst <= 1e-9, worst      # (the clip factor comes from an atomics-ordered norm: last-bit differences)
-        moved = max((f["m"].abs().max().item() for f in opt._flat if f is not None))
-        assert moved > 0
-        open(os.path.join(tmp, f"ok{rank}"), "w").write(json.dumps(losses))
+        ok = worst <= 1e-7 and max(f["m"].abs().max().item() for f in opt._flat if f is not None) > 0
+        open(os.path.join(tmp, f"{'ok' if ok else 'bad'}{rank}"), "w").write(json.dumps([losses, worst]))
     finally:
+        if gstep is not None:
+            gstep.release()     # (a live graph that captured NCCL collectives makes destroy_process_group() block)
         dist.destroy_process_group()
 
 
 def test_graphed_train_step_two_ranks(tmp_path):
     """training.GraphedTrainStep under a 2-rank NCCL group: the captured step contains the collectives of the global-batch
-    loss and the overlapped gradient average; replays keep the ranks' parameters identical."""
+    loss and the overlapped gradient average; replays keep the ranks' parameters identical (to the last bits of the
+    atomics-ordered clip norm)."""
     mp.spawn(_graph_worker, args=(2, _port(), str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(2))
