@@ -520,7 +520,12 @@ def run_ours(args):
         del indexer, x
         x = x_host_keep
         torch.cuda.empty_cache()
-        train_step = bt.measure(bt.default_args(steps=args.train_steps, warmup=3), rank, world, local_rank, dev)
+        try:
+            train_step = bt.measure(bt.default_args(steps=args.train_steps, warmup=3), rank, world, local_rank, dev)
+        except Exception as exc:   # noqa: BLE001 - the headline line must not depend on the secondary leg
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            train_step = {"error": f"{type(exc).__name__}: {exc}"[:300]} if rank == 0 else None
     barrier()
 
     if rank != 0:

@@ -571,3 +571,34 @@ def test_load_biencoder_checkpoint_variants(tmp_path):
         before = {k: v.clone() for k, v in m.state_dict().items()}
         load_biencoder_checkpoint(m, none)
         assert all(torch.equal(v, before[k]) for k, v in m.state_dict().items())
+
+
+def test_nll_positive_indices_are_checked_on_the_host():
+    """BiEncoderNllLoss.calc (bi_encoder.py:615-656): the reference's Python list of positives is range-checked without a
+    device round trip (no `.item()` in the training loop), and a wrong count is reported before any kernel runs."""
+    from lightningdot_b200.bi_encoder import BiEncoderNllLoss
+    q, c = torch.zeros(2, 8), torch.zeros(3, 8)
+    with pytest.raises(IndexError):
+        BiEncoderNllLoss().calc(q, c, None, [0, 3])
+    with pytest.raises(IndexError):
+        BiEncoderNllLoss().calc(q, c, None, [-1, 0])
+    with pytest.raises(ValueError):
+        BiEncoderNllLoss().calc(q, c, None, [0])
+    with pytest.raises(IndexError):
+        BiEncoderNllLoss().calc(q, c, None, torch.tensor([0, 7]))
+
+
+def test_graphed_step_batch_copy_rules():
+    """training._copy_leaves / _map_leaves (the static-batch plumbing of GraphedTrainStep): tensors are copied leaf by leaf
+    into the captured buffers, Python lists of indices are accepted where a tensor was captured, non-tensor leaves are
+    left alone, and a shape change is refused with a message that names the leaf."""
+    from lightningdot_b200.training import _copy_leaves, _map_leaves
+    static = _map_leaves({"txts": {"input_ids": torch.zeros(2, 3, dtype=torch.long), "note": "x"},
+                          "pos_ctx_indices": torch.zeros(2, dtype=torch.long), "caps": {"input_ids": None}}, lambda t: t.clone())
+    _copy_leaves(static, {"txts": {"input_ids": torch.arange(6).view(2, 3), "note": "y"}, "pos_ctx_indices": [1, 0],
+                          "caps": {"input_ids": None}})
+    assert static["txts"]["input_ids"].tolist() == [[0, 1, 2], [3, 4, 5]] and static["txts"]["note"] == "x"
+    assert static["pos_ctx_indices"].tolist() == [1, 0]
+    with pytest.raises(ValueError, match=r"batch\['txts'\]\['input_ids'\]"):
+        _copy_leaves(static, {"txts": {"input_ids": torch.zeros(2, 4, dtype=torch.long), "note": "x"},
+                              "pos_ctx_indices": [0, 1], "caps": {"input_ids": None}})
