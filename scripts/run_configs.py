@@ -61,12 +61,56 @@ def cfg2():
     _lib.prof_enable(False)
     prof = _lib.prof_read()
     kern = {k: round(v["ms"], 2) for k, v in prof.items() if v["launches"]}
+    oracle_leg = cfg2_oracle_leg(model, tb, ib, cap_per_img, eargs)
     return {"config": "BASELINE configs[1]: 5000 images x 25000 captions, encode + index + search both directions, top-100",
+            "oracle_leg": oracle_leg,
             "seconds_end_to_end": dt, "captions_per_s": n_cap / dt, "image_encodings": n_cap,
             "note": "images are re-encoded once per caption, as the reference's eval loader does (SURVEY 3.2)",
             "loss": loss, "in_batch_acc": acc, "recall_txt2img": r_txt, "recall_img2txt": r_img,
             "kernel_ms": kern, "kernel_ms_total": round(sum(kern.values()), 1),
             "ranked_lists": [len(rank_txt), len(rank_img)]}
+
+
+def cfg2_oracle_leg(model, tb, ib, cap_per_img, eargs, n_img_s=200):
+    """The same flow on the first 200 images x 1000 captions of configs[1], once through the CUDA towers + CUDA search and
+    once through the CPU oracle (fp32 towers of oracle/towers.py, eval loop of oracle/evalloop.py - the checker, used here
+    as in bench.py's cpu_baseline leg): recalls of both, top-10 overlap and top-1 agreement of the ranked lists."""
+    from oracle import evalloop, towers as otowers   # checker only
+    n_s = n_img_s * cap_per_img
+    n_cap, n_img = tb["input_ids"].shape[0], ib["img_feat"].shape[0]
+    txt_ids = [str(j) for j in range(n_s)]
+    img_ids = [f"img_{j // cap_per_img:07d}.npz" for j in range(n_s)]
+    img2txt = {f"img_{i:07d}.npz": [str(i * cap_per_img + c) for c in range(cap_per_img)] for i in range(n_img_s)}
+    batches = []
+    for b0 in range(0, n_s, 200):
+        rows = torch.arange(b0, b0 + 200)
+        irows = rows // cap_per_img
+        batches.append({"txts": {k: (v[rows] if torch.is_tensor(v) and v.shape[0] == n_cap else v) for k, v in tb.items()},
+                        "imgs": {k: (v[irows] if torch.is_tensor(v) and v.shape[0] == n_img else v) for k, v in ib.items()},
+                        "caps": {"input_ids": None}, "sample_size": 200, "txt_index": txt_ids[b0:b0 + 200],
+                        "img_fname": img_ids[b0:b0 + 200]})
+    _, _, _, (r_txt, r_img), (rank_txt, rank_img) = trainer.eval_model_on_dataloader(model, batches, eargs, img2txt, 100)
+    sd_t = {k: v.detach().float().cpu() for k, v in model.txt_model.state_dict().items()}
+    sd_i = {k: v.detach().float().cpu() for k, v in model.img_model.state_dict().items()}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        _, ot = otowers.text_tower(sd_t, tb["input_ids"][:n_s], tb["attention_mask"][:n_s], tb["position_ids"])
+        sl = {k: (v[:n_img_s] if torch.is_tensor(v) and v.shape[0] == n_img else v) for k, v in ib.items()}
+        _, oi = otowers.image_tower(sd_i, sl["input_ids"], sl["attention_mask"], sl["position_ids"], sl["img_feat"],
+                                    sl["img_pos_feat"], sl["gather_index"])
+    o_img = oi.numpy()[np.arange(n_s) // cap_per_img]
+    or_txt, or_img, orank_txt, orank_img = evalloop.recall_from_embeddings(ot.numpy(), o_img, txt_ids, img_ids, img2txt, 100)
+    cpu_s = time.perf_counter() - t0
+    ov_txt = float(np.mean([len(set(rank_txt[q][:10]) & set(orank_txt[q][:10])) / 10 for q in txt_ids]))
+    ov_img = float(np.mean([len(set(rank_img[q][:10]) & set(orank_img[q][:10])) / 10 for q in img2txt]))
+    top1 = float(np.mean([rank_txt[q][0] == orank_txt[q][0] for q in txt_ids]))
+    return {"sample": f"first {n_img_s} images x {n_s} captions of the configuration, 12-layer towers, bf16 kernels vs fp32 CPU oracle",
+            "recall_txt2img_gpu": r_txt, "recall_txt2img_oracle": {str(k): v for k, v in or_txt.items()},
+            "recall_img2txt_gpu": r_img, "recall_img2txt_oracle": {str(k): v for k, v in or_img.items()},
+            "top10_overlap_txt2img": ov_txt, "top10_overlap_img2txt": ov_img, "top1_equal_txt2img": top1,
+            "oracle_cpu_seconds": cpu_s,
+            "note": "random-init towers: recalls are chance level and 16-bit score noise reorders near-ties (DESIGN 3); "
+                    "Recall identity is pinned on the planted-margin labels of tests/test_gpu_configs0.py"}
 
 
 def cfg3():
