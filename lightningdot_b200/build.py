@@ -26,9 +26,31 @@ def _newest_dep():
     return t
 
 
+HOSTEXT_SRC = os.path.join(HERE, "hostext", "pylists.c")
+HOSTEXT_OUT = os.path.join(HERE, "_ldot_pyhost.so")
+
+
+def build_hostext(force=False):
+    """The small CPython helper behind DenseFlatIndexer.search_knn's id lists (hostext/pylists.c): host compiler only,
+    no CUDA.  Optional - the indexer falls back to its numpy formulation of the same host-side loop without it."""
+    import sysconfig
+    if not force and os.path.exists(HOSTEXT_OUT) and os.path.getmtime(HOSTEXT_OUT) >= os.path.getmtime(HOSTEXT_SRC):
+        return HOSTEXT_OUT
+    cc = os.environ.get("CC", "gcc")
+    cmd = [cc, "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], HOSTEXT_SRC, "-o", HOSTEXT_OUT]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"host extension build failed:\n{r.stdout}\n{r.stderr}")
+    return HOSTEXT_OUT
+
+
 def build(force=False, verbose=False):
     """Compile every .cu under csrc/ and link the shared library.  Returns the path of the .so."""
     os.makedirs(OBJ_DIR, exist_ok=True)
+    try:
+        build_hostext(force)
+    except Exception as exc:   # noqa: BLE001 - optional host-side helper: never block the CUDA build
+        sys.stderr.write(f"warning: {exc}\n")
     dep_t = _newest_dep()
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= dep_t:
         return OUT

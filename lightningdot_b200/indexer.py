@@ -11,6 +11,7 @@ queries whose exactness certificate fails are transparently re-run through the e
 There is no CPU path: without the CUDA extension and a B200 every call raises.
 """
 import gc
+import os
 import logging
 import pickle
 import struct
@@ -324,6 +325,27 @@ def read_flat_ip_index(path: str, **kw) -> "FlatIPIndex":
     return idx
 
 
+_PYHOST = [False, None]   # [looked for, ldot_py_gather_lists or None]
+
+
+def _pyhost_gather():
+    """The CPython helper that builds search_knn's id lists (lightningdot_b200/_ldot_pyhost.so, built by build.py), or
+    None when it is not there - the numpy formulation below is then used; both are host-side Python-object plumbing."""
+    if not _PYHOST[0]:
+        _PYHOST[0] = True
+        import ctypes
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ldot_pyhost.so")
+        if os.path.exists(path):
+            try:
+                fn = ctypes.PyDLL(path).ldot_py_gather_lists
+                fn.restype = ctypes.py_object
+                fn.argtypes = [ctypes.py_object, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong]
+                _PYHOST[1] = fn
+            except (OSError, AttributeError):
+                _PYHOST[1] = None
+    return _PYHOST[1]
+
+
 class DenseIndexer(object):
     """dvl/indexer/faiss_indexers.py:22-60."""
 
@@ -396,9 +418,21 @@ class DenseFlatIndexer(DenseIndexer):
         # convert to external ids (a label of -1 - index shorter than top_docs - maps to the LAST id through
         # negative indexing, exactly like faiss_indexers.py:85).  One vectorised gather over an object array
         # instead of nq * k Python list look-ups.
-        id_map = self._id_array()
-        if not len(id_map):
+        if not len(self.index_id_to_db_id):
             return [([], scores[i]) for i in range(len(indexes))]
+        gather = _pyhost_gather()
+        if gather is not None and isinstance(self.index_id_to_db_id, list):
+            # one C loop over the label matrix (hostext/pylists.c): nq lists of k references, nothing in between
+            idx = np.ascontiguousarray(indexes, dtype=np.int64)
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                rows = gather(self.index_id_to_db_id, idx.ctypes.data, idx.shape[0], idx.shape[1])
+                return list(zip(rows, scores))
+            finally:
+                if gc_was_on:
+                    gc.enable()
+        id_map = self._id_array()
         # building nq lists of k references allocates ~nq container objects: keep the cyclic GC from re-scanning the
         # (possibly million-entry) id list while they are created
         gc_was_on = gc.isenabled()

@@ -602,3 +602,37 @@ def test_graphed_step_batch_copy_rules():
     with pytest.raises(ValueError, match=r"batch\['txts'\]\['input_ids'\]"):
         _copy_leaves(static, {"txts": {"input_ids": torch.zeros(2, 4, dtype=torch.long), "note": "x"},
                               "pos_ctx_indices": [0, 1], "caps": {"input_ids": None}})
+
+
+def test_search_knn_id_lists_helper_equals_the_reference_comprehension():
+    """DenseFlatIndexer._format_result (faiss_indexers.py:85-87): the CPython helper (hostext/pylists.c) and the numpy
+    formulation both reproduce the reference's nested list comprehension, including label -1 -> LAST id, and an
+    out-of-range label raises IndexError as list indexing does."""
+    from lightningdot_b200 import indexer as ix
+    ix_obj = ix.DenseFlatIndexer.__new__(ix.DenseFlatIndexer)
+    ix.DenseIndexer.__init__(ix_obj, buffer_size=10)
+    n, nq, k = 5000, 300, 100
+    ix_obj.index_id_to_db_id = [f"img_{i:07d}.npz" for i in range(n)]
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, n, size=(nq, k), dtype=np.int64)
+    idx[7, 3] = -1
+    scores = rng.standard_normal((nq, k)).astype(np.float32)
+    want = [[ix_obj.index_id_to_db_id[i] for i in row] for row in idx]        # the reference's own formulation
+    saved = list(ix._PYHOST)
+    try:
+        ix._PYHOST[:] = [False, None]
+        helper = ix._pyhost_gather()
+        if helper is None:
+            pytest.skip("host extension not built (python -m lightningdot_b200.build)")
+        got = ix_obj._format_result(scores, idx)
+        assert [r[0] for r in got] == want and all((r[1] == scores[i]).all() for i, r in enumerate(got))
+        assert isinstance(got[0][0], list)
+        bad = idx.copy()
+        bad[0, 0] = n
+        with pytest.raises(IndexError):
+            ix_obj._format_result(scores, bad)
+        ix._PYHOST[:] = [True, None]                                         # numpy formulation
+        got2 = ix_obj._format_result(scores, idx)
+        assert [r[0] for r in got2] == want
+    finally:
+        ix._PYHOST[:] = saved
