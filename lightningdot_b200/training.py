@@ -736,6 +736,11 @@ class FusedAdamW(torch.optim.Optimizer):
         """Clears the flat gradient buffers in place (the .grad views stay attached)."""
         self._synced = False
         self._early_pending = []
+        if self._early_works or self._early_spans:   # (a backward whose step() was skipped: its early reductions are void)
+            for w in self._early_works:
+                if w is not None:
+                    w.wait()
+            self._early_spans, self._early_works = [], []
         if self._flat is None:
             return super().zero_grad(set_to_none=True)
         for f in self._flat:
@@ -781,6 +786,8 @@ class FusedAdamW(torch.optim.Optimizer):
         every rank issues the same collectives in the same order."""
         import torch.distributed as dist
         if self._flat is None or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if self._needs_layout():      # (a parameter is about to join the flat buffers: this step is reduced the plain way)
             return
         self._early_pending.extend(params)
         if not flush and sum(p.numel() for p in self._early_pending) * 4 < self.early_sync_bytes:
